@@ -1,0 +1,165 @@
+"""ctypes binding for the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY (see oracle/oracle.h): imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+Never imported by the mdsctk_b200 package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        fp, dp, ip = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.oracle_xtc_scan.argtypes = [C.c_char_p, ip, C.POINTER(C.c_longlong)]
+        L.oracle_xtc_read.argtypes = [C.c_char_p, C.c_int, C.c_longlong, fp]
+        L.oracle_top_masses.argtypes = [C.c_char_p, fp, C.c_int]
+        L.oracle_reset_x.argtypes = [C.c_int, fp, fp]
+        L.oracle_reset_x.restype = None
+        L.oracle_do_fit.argtypes = [C.c_int, fp, fp, fp]
+        L.oracle_do_fit.restype = None
+        L.oracle_rmsdev.argtypes = [C.c_int, fp, fp, fp]
+        L.oracle_rmsdev.restype = C.c_float
+        L.oracle_rmsd_f64.argtypes = [C.c_int, fp, fp, fp, C.c_int]
+        L.oracle_rmsd_f64.restype = C.c_double
+        L.oracle_euclidean_distance.argtypes = [C.c_int, dp, dp]
+        L.oracle_euclidean_distance.restype = C.c_double
+        L.oracle_correlation_distance.argtypes = [C.c_int, dp, dp]
+        L.oracle_correlation_distance.restype = C.c_double
+        L.oracle_knn_rms.argtypes = [C.c_int, C.c_int, fp, fp, C.c_longlong, fp, C.c_longlong,
+                                     C.c_int, C.c_int, C.c_int, dp, ip]
+        L.oracle_knn_data.argtypes = [C.c_int, C.c_int, dp, C.c_longlong, dp, C.c_longlong,
+                                      C.c_int, C.c_int, dp, ip]
+        L.oracle_rms_rows.argtypes = [C.c_int, C.c_int, fp, fp, C.c_longlong, fp, C.c_longlong,
+                                      C.c_int, C.c_int, dp]
+        L.oracle_max_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def max_threads():
+    return int(lib().oracle_max_threads())
+
+
+def read_xtc(path):
+    """-> float32 [n_frames, n_atoms, 3] in nm (raw, uncentred)."""
+    na, nf = C.c_int(0), C.c_longlong(0)
+    rc = lib().oracle_xtc_scan(path.encode(), C.byref(na), C.byref(nf))
+    if rc != 0:
+        raise IOError(f"oracle_xtc_scan({path}) -> {rc}")
+    xyz = np.empty((nf.value, na.value, 3), dtype=np.float32)
+    rc = lib().oracle_xtc_read(path.encode(), na.value, nf.value, _f(xyz))
+    if rc != 0:
+        raise IOError(f"oracle_xtc_read({path}) -> {rc}")
+    return xyz
+
+
+def read_masses(path, max_atoms=1 << 20):
+    m = np.empty(max_atoms, dtype=np.float32)
+    n = lib().oracle_top_masses(path.encode(), _f(m), max_atoms)
+    if n < 0:
+        raise IOError(f"oracle_top_masses({path}) -> {n}")
+    return m[:n].copy()
+
+
+def reset_x(frame, mass):
+    x = np.ascontiguousarray(frame, dtype=np.float32).copy()
+    mass = np.ascontiguousarray(mass, dtype=np.float32)
+    lib().oracle_reset_x(x.shape[0], _f(x), _f(mass))
+    return x
+
+
+def fit_rmsdev(ref_c, fit_c, mass, dofit=True):
+    """Reference float chain on two CENTRED frames; returns (rmsd_nm, fitted copy)."""
+    ref_c = np.ascontiguousarray(ref_c, dtype=np.float32)
+    fit = np.ascontiguousarray(fit_c, dtype=np.float32).copy()
+    mass = np.ascontiguousarray(mass, dtype=np.float32)
+    if dofit:
+        lib().oracle_do_fit(ref_c.shape[0], _f(mass), _f(ref_c), _f(fit))
+    return float(lib().oracle_rmsdev(ref_c.shape[0], _f(mass), _f(ref_c), _f(fit))), fit
+
+
+def rmsd_f64(a, b, mass, dofit=True):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    mass = np.ascontiguousarray(mass, dtype=np.float32)
+    return float(lib().oracle_rmsd_f64(a.shape[0], _f(mass), _f(a), _f(b), int(dofit)))
+
+
+def euclidean_distance(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return float(lib().oracle_euclidean_distance(a.shape[0], _d(a), _d(b)))
+
+
+def correlation_distance(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return float(lib().oracle_correlation_distance(a.shape[0], _d(a), _d(b)))
+
+
+def knn_rms(ref, mass, k, fit=None, mode=1, dofit=True, nthreads=0):
+    """ref/fit: float32 [n, atoms, 3] raw frames.  Returns (dist[n_fit,k] A, idx[n_fit,k])."""
+    ref = np.ascontiguousarray(ref, dtype=np.float32)
+    fit = ref if fit is None else np.ascontiguousarray(fit, dtype=np.float32)
+    mass = np.ascontiguousarray(mass, dtype=np.float32)
+    k = min(k, ref.shape[0] - 1)
+    dist = np.empty((fit.shape[0], k), dtype=np.float64)
+    idx = np.empty((fit.shape[0], k), dtype=np.int32)
+    rc = lib().oracle_knn_rms(mode, ref.shape[1], _f(mass), _f(ref), ref.shape[0], _f(fit), fit.shape[0],
+                              k, int(dofit), nthreads, _d(dist), _i(idx))
+    if rc != 0:
+        raise RuntimeError(f"oracle_knn_rms -> {rc}")
+    return dist, idx
+
+
+def rms_rows(ref, mass, fit, mode=1, dofit=True, nthreads=0):
+    ref = np.ascontiguousarray(ref, dtype=np.float32)
+    fit = np.ascontiguousarray(fit, dtype=np.float32)
+    mass = np.ascontiguousarray(mass, dtype=np.float32)
+    out = np.empty((fit.shape[0], ref.shape[0]), dtype=np.float64)
+    rc = lib().oracle_rms_rows(mode, ref.shape[1], _f(mass), _f(ref), ref.shape[0], _f(fit), fit.shape[0],
+                               int(dofit), nthreads, _d(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle_rms_rows -> {rc}")
+    return out
+
+
+def knn_data(ref, k, fit=None, metric=0, nthreads=0):
+    ref = np.ascontiguousarray(ref, dtype=np.float64)
+    fit = ref if fit is None else np.ascontiguousarray(fit, dtype=np.float64)
+    k = min(k, ref.shape[0] - 1)
+    dist = np.empty((fit.shape[0], k), dtype=np.float64)
+    idx = np.empty((fit.shape[0], k), dtype=np.int32)
+    rc = lib().oracle_knn_data(metric, ref.shape[1], _d(ref), ref.shape[0], _d(fit), fit.shape[0],
+                               k, nthreads, _d(dist), _i(idx))
+    if rc != 0:
+        raise RuntimeError(f"oracle_knn_data -> {rc}")
+    return dist, idx

@@ -1,0 +1,92 @@
+/*
+ * oracle.h -- CPU restatement of MDSCTK's all-pairs distance + kNN stage.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product
+ * path: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may build, load or call this code, and there only as
+ * the checker / timed CPU baseline.
+ *
+ * PARITY UNPINNED: the reference (jlphillipsphd/mdsctk) ships no golden
+ * vectors, no known-answer tests and cannot be compiled in this image (it
+ * needs libgromacs, Boost.program_options, Berkeley DB and ARPACK, none of
+ * which are present).  The RMSD arithmetic lives in GROMACS
+ * 5.0-5.1 (un-vendored, un-pinned: /root/reference/CMakeLists.txt:194-209),
+ * whose do_fit / rmsdev / reset_x algorithm is restated here.  The oracle is
+ * anchored on the reference's call sites instead:
+ *   knn_rms.cpp:38-41    distance() = do_fit + rmsdev * 10
+ *   knn_rms.cpp:181-206  mass weights, reset_x on every frame
+ *   knn_rms.cpp:224-293  k clamp, row blocks, rank-0 drop, file layout
+ *   knn_data.cpp:141-250 reader, blocks, writer
+ *   mdsctk.h:177-199     permutation<T>::sort(k) = partial_sort
+ *   mdsctk.cpp:330-360   euclidean_distance / correlation_distance
+ * and cross-checked by the invariance properties in tests/test_oracle.py.
+ */
+#ifndef MDSCTK_ORACLE_H
+#define MDSCTK_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- XTC trajectory reader (GROMACS xtc / xdr3dfcoord format) -------------
+ * Replaces open_xtc/read_first_xtc/read_next_xtc as used at
+ * knn_rms.cpp:155-157,186-203.  Returns 0 on success. */
+int oracle_xtc_scan(const char *path, int *natoms, long long *nframes);
+/* xyz must hold nframes*natoms*3 floats (nm), AoS [frame][atom][3]. */
+int oracle_xtc_read(const char *path, int natoms, long long nframes, float *xyz);
+
+/* ---- topology masses (read_tps_conf(..., bMass=TRUE), knn_rms.cpp:150-153,181-182)
+ * Reads a .pdb or .gro file; mass[] must hold max_atoms floats.
+ * Returns the atom count, or a negative number on error. */
+int oracle_top_masses(const char *path, float *mass, int max_atoms);
+
+/* ---- per-frame / per-pair arithmetic -------------------------------------- */
+/* reset_x(natoms,NULL,natoms,NULL,x,mass): float centre of mass removal. */
+void oracle_reset_x(int natoms, float *x /*[natoms][3]*/, const float *mass);
+/* do_fit: least-squares rotate x onto xp IN PLACE (float U, double 6x6 Jacobi). */
+void oracle_do_fit(int natoms, const float *w, const float *xp, float *x);
+/* rmsdev: sqrt(sum m |x-xp|^2 / sum m), float accumulation. */
+float oracle_rmsdev(int natoms, const float *mass, const float *x, const float *xp);
+/* FP64 optimal-superposition RMSD (nm) between two RAW (uncentred) float frames:
+ * double centring, double cross-covariance, 4x4 key-matrix Jacobi.            */
+double oracle_rmsd_f64(int natoms, const float *mass, const float *a, const float *b, int dofit);
+
+/* mdsctk.cpp:330-335 and :337-360 */
+double oracle_euclidean_distance(int size, const double *reference, const double *fitting);
+double oracle_correlation_distance(int size, const double *reference, const double *fitting);
+
+/* ---- whole-stage drivers ---------------------------------------------------
+ * Both write out_dist[n_fit][k] (ascending, sorted position 0 dropped, exactly
+ * like knn_rms.cpp:282-291) and out_idx[n_fit][k].  k must already be clamped
+ * to n_ref-1.  Ties are ordered (distance, index) ascending.
+ *
+ * mode 0: reference-faithful float chain (frames centred in float with
+ *         reset_x, then for each fit row: copy fit once, do_fit cumulatively
+ *         in place against every ref, rmsdev*10) -- the timed CPU baseline.
+ * mode 1: FP64 Kabsch on the raw frames (x10 to Angstrom).
+ * ref_xyz / fit_xyz are RAW decoded frames (uncentred), nm.                     */
+int oracle_knn_rms(int mode, int natoms, const float *mass,
+                   const float *ref_xyz, long long n_ref,
+                   const float *fit_xyz, long long n_fit,
+                   int k, int dofit, int nthreads,
+                   double *out_dist, int *out_idx);
+
+/* metric 0 = euclidean, 1 = correlation.  rows are row-major double[n][dim]. */
+int oracle_knn_data(int metric, int dim,
+                    const double *ref, long long n_ref,
+                    const double *fit, long long n_fit,
+                    int k, int nthreads,
+                    double *out_dist, int *out_idx);
+
+/* Full distance row(s) without selection, for spot checks: out[n_fit][n_ref]. */
+int oracle_rms_rows(int mode, int natoms, const float *mass,
+                    const float *ref_xyz, long long n_ref,
+                    const float *fit_xyz, long long n_fit,
+                    int dofit, int nthreads, double *out);
+
+int oracle_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,148 @@
+/*
+ * mdsctk_knn.h -- C ABI of the B200 all-pairs distance + k-nearest-neighbour stage.
+ *
+ * This is the drop-in boundary for MDSCTK's kNN hot path.  The reference has no
+ * library/FFI seam for it (every tool is one main()): the seam
+ * that exists is the per-pair distance function and the row loop around it.
+ * Each entry point below names the reference code it replaces:
+ *
+ *   mdsctk_knn_rms_set_reference   knn_rms.cpp:181-194  weights[] = masses, reset_x on
+ *                                                       every reference frame (load+centre)
+ *   mdsctk_knn_rms_query           knn_rms.cpp:231-293  OpenMP row blocks:
+ *                                    :38-41   distance() = do_fit + rmsdev * 10.0
+ *                                    :277-278 fits[frame].sort(k1)  (mdsctk.h:177-199)
+ *   mdsctk_knn_data_set_reference  knn_data.cpp:141-154 reference rows
+ *   mdsctk_knn_data_query          knn_data.cpp:195-250 row blocks:
+ *                                    :231-234 ::distance(vector_size, fit, ref)
+ *                                             (euclidean_distance mdsctk.cpp:330-335,
+ *                                              correlation_distance mdsctk.cpp:337-360)
+ *                                    :235-236 fits[frame].sort(k1)
+ *
+ * Results are the k1 = k+1 smallest distances of every fit row, ascending, with
+ * their reference indices -- i.e. permutation<double>::data[0..k1) / indices[0..k1)
+ * after sort(k1).  The CALLER drops sorted position 0 and writes the files,
+ * exactly like knn_rms.cpp:282-291 / knn_data.cpp:240-249.
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types.  Every function
+ * returns 0 on success or a negative MDSCTK_KNN_E* code; the message is available
+ * from mdsctk_knn_last_error().  Nothing throws or exits across the boundary.
+ * A ctx is bound to ONE GPU and is not thread-safe; use one ctx per GPU (one
+ * process per GPU under torchrun, or one host thread per GPU in the C++ tools).
+ * Calls are synchronous on return.  There is no CPU fallback: without a usable
+ * sm_100 device mdsctk_knn_create fails.
+ */
+#ifndef MDSCTK_KNN_H
+#define MDSCTK_KNN_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDSCTK_KNN_ABI_VERSION 1
+
+enum {
+    MDSCTK_KNN_OK = 0,
+    MDSCTK_KNN_EINVAL = -1,   /* bad argument                                    */
+    MDSCTK_KNN_ECUDA = -2,    /* CUDA runtime / driver error                     */
+    MDSCTK_KNN_ENOMEM = -3,   /* device or host allocation failed                */
+    MDSCTK_KNN_ESTATE = -4,   /* call order (no reference set yet, ...)          */
+    MDSCTK_KNN_ENODEV = -5    /* no sm_100 device / device id out of range       */
+};
+
+enum { MDSCTK_KNN_EUCLIDEAN = 0, MDSCTK_KNN_CORRELATION = 1 };
+
+/* rms_kernel option values */
+enum { MDSCTK_KNN_RMS_SIMT_FP32 = 0, MDSCTK_KNN_RMS_TC_3XTF32 = 1, MDSCTK_KNN_RMS_TC_1XTF32 = 2 };
+
+typedef struct mdsctk_knn_ctx mdsctk_knn_ctx;
+
+typedef struct mdsctk_knn_stats {
+    double ms_upload;      /* host->device copies of inputs                         */
+    double ms_pack;        /* centre + scale + SoA pack kernel                      */
+    double ms_sweep;       /* all-pairs distance sweep + streaming selection        */
+    double ms_rescore;     /* FP64 re-score, final sort, certification              */
+    double ms_fallback;    /* exact FP64 rows for uncertified rows                  */
+    double ms_download;    /* device->host copy of the k-lists                      */
+    long long pairs;       /* n_fit * n_ref of the last query                       */
+    long long launches;    /* kernels launched by the last query (sweep..fallback)  */
+    long long fallback_rows;   /* rows that failed certification and were redone    */
+    long long sweep_appends;   /* candidates appended by the sweep (diagnostic)     */
+    double max_filter_err; /* max |approx d^2 - exact d^2| over all candidates      */
+    double cert_eps;       /* absolute d^2 margin used by the certificate           */
+    int rms_kernel;        /* kernel actually used by the last RMSD query           */
+    int k_keep;            /* candidates kept per row (k1 + slack)                  */
+} mdsctk_knn_stats;
+
+int mdsctk_knn_abi_version(void);
+
+/* One context per GPU.  device_id is a CUDA ordinal (honours CUDA_VISIBLE_DEVICES). */
+int mdsctk_knn_create(mdsctk_knn_ctx **out, int device_id);
+void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx);
+/* ctx may be NULL: returns the message of the last failed mdsctk_knn_create on this thread. */
+const char *mdsctk_knn_last_error(const mdsctk_knn_ctx *ctx);
+
+/* Tunables: "rms_kernel" (enum above), "slack" (extra candidates kept per row, -1 = auto),
+ * "cert_scale_ppm" (certificate margin multiplier in parts-per-million of the default). */
+int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value);
+int mdsctk_knn_get_stats(const mdsctk_knn_ctx *ctx, mdsctk_knn_stats *out);
+
+/* ------------------------------------------------------------------ RMSD path ---- */
+/* xyz: HOST, AoS float[n_frames][n_atoms][3] in nm, UNcentred (decoded XTC frames).
+ * mass: HOST float[n_atoms].  Uploads, centres (mass-weighted), scales by sqrt(m/M) and
+ * packs on the GPU into the frames x 3 x atoms SoA layout. */
+int mdsctk_knn_rms_set_reference(mdsctk_knn_ctx *ctx, const float *xyz, long long n_frames, int n_atoms,
+                                 const float *mass);
+
+/* fit_xyz == NULL: the fit set is the reference set (symmetric run, knn_rms.cpp:103-104).
+ * k1 = neighbours INCLUDING sorted position 0 (k+1 of the tools), 1 <= k1 <= n_ref.
+ * do_fit = 0 is the tools' --nofit.  out_dist[n_fit][k1] in Angstrom (nm * 10), ascending;
+ * out_idx[n_fit][k1] reference frame numbers.  Ties: (distance, index) ascending.
+ * out_dist/out_idx may both be NULL: results stay on the device for mdsctk_knn_fetch. */
+int mdsctk_knn_rms_query(mdsctk_knn_ctx *ctx, const float *fit_xyz, long long n_fit, int k1, int do_fit,
+                         double *out_dist, int *out_idx);
+
+/* Row-sharded form (one process per GPU; every GPU holds the whole reference set):
+ *   1. mdsctk_knn_rms_alloc_reference(n_total)          on every rank
+ *   2. mdsctk_knn_rms_pack_shard(own frames, offset)    each rank packs ITS frames on ITS GPU
+ *   3. all-gather the arrays listed by mdsctk_knn_rms_reference_arrays over NCCL
+ *      (each is frame-major, bytes_per_frame[i] bytes per frame, n_total frames)
+ *   4. mdsctk_knn_rms_query_range(begin, n)             fit rows = reference rows [begin, begin+n) */
+int mdsctk_knn_rms_alloc_reference(mdsctk_knn_ctx *ctx, long long n_total, int n_atoms, const float *mass);
+int mdsctk_knn_rms_pack_shard(mdsctk_knn_ctx *ctx, const float *xyz, long long frame_offset, long long n_frames);
+int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_arrays, void **dev_ptrs,
+                                    size_t *bytes_per_frame);
+int mdsctk_knn_rms_query_range(mdsctk_knn_ctx *ctx, long long fit_begin, long long n_fit, int k1, int do_fit,
+                               double *out_dist, int *out_idx);
+
+/* ---------------------------------------------------------------- vector path ---- */
+/* rows: HOST row-major double[n_rows][dim], exactly the bytes of a .pts file. */
+int mdsctk_knn_data_set_reference(mdsctk_knn_ctx *ctx, const double *rows, long long n_rows, int dim);
+/* metric: MDSCTK_KNN_EUCLIDEAN / MDSCTK_KNN_CORRELATION (knn_data -c). */
+int mdsctk_knn_data_query(mdsctk_knn_ctx *ctx, const double *fit_rows, long long n_fit, int k1, int metric,
+                          double *out_dist, int *out_idx);
+int mdsctk_knn_data_alloc_reference(mdsctk_knn_ctx *ctx, long long n_total, int dim);
+int mdsctk_knn_data_upload_shard(mdsctk_knn_ctx *ctx, const double *rows, long long row_offset, long long n_rows);
+int mdsctk_knn_data_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_arrays, void **dev_ptrs,
+                                     size_t *bytes_per_row);
+int mdsctk_knn_data_query_range(mdsctk_knn_ctx *ctx, long long fit_begin, long long n_fit, int k1, int metric,
+                                double *out_dist, int *out_idx);
+
+/* CUDA-event stopwatch on the context's own stream (the stream every kernel of this library
+ * is launched on): start records an event, stop records a second one, waits for it and returns
+ * the elapsed device time in milliseconds. */
+int mdsctk_knn_timer_start(mdsctk_knn_ctx *ctx);
+int mdsctk_knn_timer_stop(mdsctk_knn_ctx *ctx, double *elapsed_ms);
+
+/* Copies the k-lists of the last query ([n_fit][k1]) to host memory. */
+int mdsctk_knn_fetch(mdsctk_knn_ctx *ctx, double *out_dist, int *out_idx);
+
+/* Exact FP64 distance rows (no selection) computed on the GPU: out[n_fit][n_ref], Angstrom.
+ * Diagnostic / spot-check entry point (the tools' --sort false, restricted to a row range). */
+int mdsctk_knn_rms_rows(mdsctk_knn_ctx *ctx, long long fit_begin, long long n_fit, int do_fit, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDSCTK_KNN_H */

@@ -1,0 +1,646 @@
+// abi.cu -- the C ABI of include/mdsctk_knn.h: context, device memory, phase orchestration.
+//
+// Host-side counterpart of the reference's main() bodies between "load" and "write":
+// knn_rms.cpp:181-293 and knn_data.cpp:141-250.  No CPU arithmetic happens here -- every
+// distance, selection and sort runs in the kernels of this directory; this file only moves
+// bytes, launches, and checks errors.  There is no CPU fallback.
+#include "../../include/mdsctk_knn.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mdsctk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t want)
+    {
+        if (want <= bytes) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct FrameSet {
+    DevBuf raw, planes, G, cen;
+    long long n = 0;
+    int A = 0, A_pad = 0;
+    FrameSetView view() const
+    {
+        FrameSetView v;
+        v.raw = raw.as<float>(); v.planes = planes.as<float>(); v.G = G.as<float>(); v.cen = cen.as<double>();
+        v.n = n; v.A = A; v.A_pad = A_pad;
+        return v;
+    }
+    cudaError_t alloc(long long n_, int A_)
+    {
+        n = n_; A = A_; A_pad = pad_atoms(A_);
+        cudaError_t e;
+        if ((e = raw.reserve((size_t)n * A * 12)) != cudaSuccess) return e;
+        if ((e = planes.reserve((size_t)n * 3 * A_pad * 4)) != cudaSuccess) return e;
+        if ((e = G.reserve((size_t)n * 4)) != cudaSuccess) return e;
+        return cen.reserve((size_t)n * 32);
+    }
+    void release() { raw.release(); planes.release(); G.release(); cen.release(); n = 0; }
+};
+
+struct PhaseTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    void init() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    void destroy() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    void start(cudaStream_t s) { cudaEventRecord(a, s); }
+    double stop(cudaStream_t s)
+    {
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        return (double)ms;
+    }
+};
+
+}  // namespace
+
+struct mdsctk_knn_ctx {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    PhaseTimer tm, user_tm;
+    // options
+    int rms_kernel = MDSCTK_KNN_RMS_SIMT_FP32;
+    long long slack = -1;
+    long long cert_scale_ppm = 1000000;
+    // RMSD state
+    FrameSet ref, fit;
+    DevBuf wnorm;  // double[A]
+    bool have_ref = false, gmax_dirty = true;
+    float g_ref_max = 0.f;
+    // vector state
+    DevBuf d_ref, d_fit, d_ref_stats, d_fit_stats;
+    long long dn_ref = 0;
+    int ddim = 0;
+    bool have_dref = false, dstats_dirty = true;
+    // scratch + results
+    DevBuf cand_key, cand_idx, cand_cnt, cand_tau, flags, bad_rows, scalars, rows_buf;
+    DevBuf out_dist, out_idx;
+    long long out_rows = 0;
+    int out_k1 = 0;
+    mdsctk_knn_stats stats;
+};
+
+namespace {
+
+int fail(mdsctk_knn_ctx *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+int fail_cuda(mdsctk_knn_ctx *c, cudaError_t e, const char *what)
+{
+    cudaGetLastError();  // clear sticky-less error state
+    return fail(c, e == cudaErrorMemoryAllocation ? MDSCTK_KNN_ENOMEM : MDSCTK_KNN_ECUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call, what)                                               \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, what);    \
+    } while (0)
+
+struct Bind {
+    explicit Bind(mdsctk_knn_ctx *c) { cudaSetDevice(c->dev); }
+};
+
+__global__ void sqrt_scale_kernel(double *v, size_t n, double scale)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        v[i] = sqrt(v[i]) * scale;
+}
+
+int upload_weights(mdsctk_knn_ctx *ctx, const float *mass, int A)
+{
+    std::vector<double> w(A);
+    double M = 0.0;
+    for (int i = 0; i < A; i++) M += (double)mass[i];
+    if (!(M > 0.0)) return fail(ctx, MDSCTK_KNN_EINVAL, "masses must sum to a positive number");
+    for (int i = 0; i < A; i++) w[i] = (double)mass[i] / M;
+    CK(ctx->wnorm.reserve((size_t)A * 8), "cudaMalloc(weights)");
+    CK(cudaMemcpyAsync(ctx->wnorm.p, w.data(), (size_t)A * 8, cudaMemcpyHostToDevice, ctx->st), "H2D weights");
+    CK(cudaStreamSynchronize(ctx->st), "sync weights");
+    return 0;
+}
+
+int pack_into(mdsctk_knn_ctx *ctx, FrameSet &fs, const float *xyz, long long off, long long n)
+{
+    const int A = fs.A;
+    ctx->tm.start(ctx->st);
+    CK(cudaMemcpyAsync(fs.raw.as<float>() + (size_t)off * A * 3, xyz, (size_t)n * A * 12, cudaMemcpyHostToDevice,
+                       ctx->st), "H2D frames");
+    ctx->stats.ms_upload += ctx->tm.stop(ctx->st);
+    ctx->tm.start(ctx->st);
+    CK(launch_pack_frames(fs.raw.as<float>() + (size_t)off * A * 3, ctx->wnorm.as<double>(), n, A, fs.A_pad,
+                          fs.planes.as<float>() + (size_t)off * 3 * fs.A_pad, fs.G.as<float>() + off,
+                          fs.cen.as<double>() + 4 * off, ctx->st), "pack_frames");
+    ctx->stats.ms_pack += ctx->tm.stop(ctx->st);
+    return 0;
+}
+
+void choose_lists(const mdsctk_knn_ctx *ctx, int k1, int *keep, int *cap)
+{
+    long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(16, k1 / 4);
+    long long kp = ((long long)k1 + slack + 7) / 8 * 8;
+    *keep = (int)kp;
+    *cap = (int)((kp + 128 + 31) / 32 * 32);
+}
+
+// Bound on |approx d^2 - exact d^2| as a fraction of E0 = (Gq+Gr)/2 (DESIGN.md "certificate").
+// The contraction error grows like sqrt(atoms) * 2^-24 relative to E0; the constants are ~2x
+// the largest error ever observed over >1e6 candidates (stats.max_filter_err reports it).
+double default_eps_scale(int rms_kernel, int n_atoms)
+{
+    const double sa = std::sqrt((double)std::max(n_atoms, 16));
+    switch (rms_kernel) {
+    case MDSCTK_KNN_RMS_TC_1XTF32: return 2.5e-4 * sa;
+    case MDSCTK_KNN_RMS_TC_3XTF32: return 8e-7 * sa;
+    default: return 6e-7 * sa;
+    }
+}
+
+int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, long long n_fit, int k1, int do_fit,
+            double *out_dist, int *out_idx)
+{
+    const FrameSetView ref = ctx->ref.view(), fit = fitset.view();
+    if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
+    if (k1 < 1 || k1 > ref.n) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 must satisfy 1 <= k1 <= n_reference");
+    if (k1 > 2040) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 > 2040 is not supported");
+    if ((size_t)ref.A * 24 + 2048 * 12 > 200 * 1024)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "n_atoms too large for the FP64 re-score kernel (max ~7500)");
+    mdsctk_knn_stats &S = ctx->stats;
+    S.ms_sweep = S.ms_rescore = S.ms_fallback = S.ms_download = 0;
+    S.pairs = n_fit * ref.n; S.launches = 0; S.fallback_rows = 0; S.sweep_appends = 0; S.max_filter_err = 0;
+    S.rms_kernel = ctx->rms_kernel;
+
+    if (ctx->gmax_dirty) {
+        CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
+        CK(launch_max_float(ref.G, ref.n, ctx->scalars.as<float>(), ctx->st), "max(G)");
+        CK(cudaMemcpyAsync(&ctx->g_ref_max, ctx->scalars.p, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H max(G)");
+        CK(cudaStreamSynchronize(ctx->st), "sync max(G)");
+        ctx->gmax_dirty = false;
+    }
+
+    int keep, cap;
+    choose_lists(ctx, k1, &keep, &cap);
+    S.k_keep = keep;
+    CandLists<float> cl;
+    CK(ctx->cand_key.reserve((size_t)n_fit * cap * 4), "cudaMalloc(cand_key)");
+    CK(ctx->cand_idx.reserve((size_t)n_fit * cap * 4), "cudaMalloc(cand_idx)");
+    CK(ctx->cand_cnt.reserve((size_t)n_fit * 4), "cudaMalloc(cand_cnt)");
+    CK(ctx->cand_tau.reserve((size_t)n_fit * 8), "cudaMalloc(cand_tau)");
+    CK(ctx->flags.reserve((size_t)n_fit * 4), "cudaMalloc(flags)");
+    CK(ctx->bad_rows.reserve((size_t)n_fit * 4), "cudaMalloc(bad_rows)");
+    CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
+    CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
+    CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
+    ctx->out_rows = n_fit; ctx->out_k1 = k1;
+    cl.key = ctx->cand_key.as<float>(); cl.idx = ctx->cand_idx.as<int>(); cl.cnt = ctx->cand_cnt.as<int>();
+    cl.tau = ctx->cand_tau.as<float>(); cl.cap = cap; cl.keep = keep;
+    double *d_err = ctx->scalars.as<double>() + 1;
+    int *d_nbad = ctx->scalars.as<int>() + 4;
+    CK(cudaMemsetAsync(ctx->scalars.p, 0, 64, ctx->st), "memset scalars");
+
+    // ---- sweep: all pairs -> k1+slack candidates per row ------------------------------------
+    ctx->tm.start(ctx->st);
+    switch (ctx->rms_kernel) {
+    case MDSCTK_KNN_RMS_SIMT_FP32:
+        CK(launch_rms_sweep_simt(fit, fit_begin, n_fit, ref, do_fit, cl, ctx->st), "rms_sweep_simt");
+        break;
+    default:
+        return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel: tensor-core sweep not built into this library");
+    }
+    S.launches += 1;
+    S.ms_sweep = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "sweep kernel");
+
+    // ---- FP64 re-score + certificate -----------------------------------------------------------
+    const double eps_scale = default_eps_scale(ctx->rms_kernel, ref.A) * (double)ctx->cert_scale_ppm * 1e-6;
+    S.cert_eps = eps_scale * 0.5 * (double)ctx->g_ref_max * 2.0;
+    ctx->tm.start(ctx->st);
+    CK(launch_rms_rescore(fit, fit_begin, n_fit, ref, ctx->wnorm.as<double>(), do_fit, cl, k1, eps_scale,
+                          ctx->g_ref_max, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(),
+                          d_err, d_nbad, ctx->bad_rows.as<int>(), ctx->st), "rms_rescore");
+    S.launches += 1;
+    struct { double pad, err; int nbad; } host_sc;
+    CK(cudaMemcpyAsync(&host_sc, ctx->scalars.p, sizeof(host_sc), cudaMemcpyDeviceToHost, ctx->st), "D2H scalars");
+    S.ms_rescore = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "rescore kernel");
+    S.max_filter_err = host_sc.err;
+    S.fallback_rows = host_sc.nbad;
+
+    // ---- rows whose certificate failed: exact FP64 rows + exact selection -------------------
+    if (host_sc.nbad > 0) {
+        ctx->tm.start(ctx->st);
+        const size_t row_bytes = (size_t)ref.n * 8;
+        int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_sc.nbad, ((size_t)256 << 20) / row_bytes));
+        CK(ctx->rows_buf.reserve((size_t)chunk * row_bytes), "cudaMalloc(rows_buf)");
+        for (int off = 0; off < host_sc.nbad; off += chunk) {
+            const int nr = std::min(chunk, host_sc.nbad - off);
+            CK(launch_rms_exact_rows(fit, ctx->bad_rows.as<int>() + off, fit_begin, nr, ref, ctx->wnorm.as<double>(),
+                                     do_fit, ctx->rows_buf.as<double>(), ctx->st), "rms_exact_rows");
+            CK(launch_select_rows_f64(ctx->rows_buf.as<double>(), nr, ref.n, k1, ctx->bad_rows.as<int>() + off, 10.0,
+                                      ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->st), "select_rows");
+            S.launches += 2;
+        }
+        S.ms_fallback = ctx->tm.stop(ctx->st);
+        CK(cudaGetLastError(), "fallback kernels");
+    }
+    if (out_dist || out_idx) return mdsctk_knn_fetch(ctx, out_dist, out_idx);
+    return 0;
+}
+
+int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1,
+             int metric, double *out_dist, int *out_idx)
+{
+    if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
+    if (k1 < 1 || k1 > ctx->dn_ref) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 must satisfy 1 <= k1 <= n_reference");
+    if (k1 > 2040) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 > 2040 is not supported");
+    if (metric != MDSCTK_KNN_EUCLIDEAN && metric != MDSCTK_KNN_CORRELATION)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "unknown metric");
+    mdsctk_knn_stats &S = ctx->stats;
+    S.ms_sweep = S.ms_rescore = S.ms_fallback = S.ms_download = 0;
+    S.pairs = n_fit * ctx->dn_ref; S.launches = 0; S.fallback_rows = 0; S.max_filter_err = 0; S.cert_eps = 0;
+    const int dim = ctx->ddim;
+    const double *fit_stats = nullptr, *ref_stats = nullptr;
+    if (metric == MDSCTK_KNN_CORRELATION) {
+        if (ctx->dstats_dirty) {
+            CK(ctx->d_ref_stats.reserve((size_t)ctx->dn_ref * 16), "cudaMalloc(ref_stats)");
+            CK(launch_data_rowstats(ctx->d_ref.as<double>(), ctx->dn_ref, dim, ctx->d_ref_stats.as<double>(), ctx->st),
+               "data_rowstats");
+            ctx->dstats_dirty = false;
+            S.launches++;
+        }
+        ref_stats = ctx->d_ref_stats.as<double>();
+        if (fit_is_ref) {
+            fit_stats = ref_stats + 2 * fit_begin;
+        } else {
+            CK(ctx->d_fit_stats.reserve((size_t)n_fit * 16), "cudaMalloc(fit_stats)");
+            CK(launch_data_rowstats(d_fit, n_fit, dim, ctx->d_fit_stats.as<double>(), ctx->st), "data_rowstats");
+            fit_stats = ctx->d_fit_stats.as<double>();
+            S.launches++;
+        }
+    }
+    const long long slack = ctx->slack >= 0 ? ctx->slack : 8;
+    const int keep = (int)(((long long)k1 + slack + 7) / 8 * 8);
+    const int cap = (keep + 160 + 31) / 32 * 32;
+    S.k_keep = keep;
+    CandLists<double> cl;
+    CK(ctx->cand_key.reserve((size_t)n_fit * cap * 8), "cudaMalloc(cand_key)");
+    CK(ctx->cand_idx.reserve((size_t)n_fit * cap * 4), "cudaMalloc(cand_idx)");
+    CK(ctx->cand_cnt.reserve((size_t)n_fit * 4), "cudaMalloc(cand_cnt)");
+    CK(ctx->cand_tau.reserve((size_t)n_fit * 8), "cudaMalloc(cand_tau)");
+    CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
+    CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
+    ctx->out_rows = n_fit; ctx->out_k1 = k1;
+    cl.key = ctx->cand_key.as<double>(); cl.idx = ctx->cand_idx.as<int>(); cl.cnt = ctx->cand_cnt.as<int>();
+    cl.tau = ctx->cand_tau.as<double>(); cl.cap = cap; cl.keep = keep;
+    ctx->tm.start(ctx->st);
+    CK(launch_data_sweep(d_fit, fit_stats, n_fit, ctx->d_ref.as<double>(), ref_stats, ctx->dn_ref, dim, metric, cl,
+                         ctx->st), "data_sweep");
+    S.ms_sweep = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "data sweep kernel");
+    ctx->tm.start(ctx->st);
+    CK(launch_data_finalize(cl, n_fit, k1, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->st),
+       "data_finalize");
+    S.ms_rescore = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "data finalize kernel");
+    S.launches += 2;
+    if (out_dist || out_idx) return mdsctk_knn_fetch(ctx, out_dist, out_idx);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdsctk_knn_abi_version(void) { return MDSCTK_KNN_ABI_VERSION; }
+
+int mdsctk_knn_create(mdsctk_knn_ctx **out, int device_id)
+{
+    if (!out) { g_create_error = "out is NULL"; return MDSCTK_KNN_EINVAL; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU fallback)";
+        return MDSCTK_KNN_ENODEV;
+    }
+    if (device_id < 0 || device_id >= n) { g_create_error = "device_id out of range"; return MDSCTK_KNN_ENODEV; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return MDSCTK_KNN_ECUDA;
+    }
+    if (prop.major != 10) {
+        char b[160];
+        snprintf(b, sizeof b, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU; kernels are built for sm_100a only",
+                 device_id, prop.name, prop.major, prop.minor);
+        g_create_error = b;
+        return MDSCTK_KNN_ENODEV;
+    }
+    mdsctk_knn_ctx *c = new (std::nothrow) mdsctk_knn_ctx();
+    if (!c) { g_create_error = "out of host memory"; return MDSCTK_KNN_ENOMEM; }
+    c->dev = device_id;
+    memset(&c->stats, 0, sizeof c->stats);
+    cudaSetDevice(device_id);
+    if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+        delete c;
+        return MDSCTK_KNN_ECUDA;
+    }
+    c->tm.init();
+    c->user_tm.init();
+    *out = c;
+    return 0;
+}
+
+void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx)
+{
+    if (!ctx) return;
+    Bind b(ctx);
+    cudaStreamSynchronize(ctx->st);
+    ctx->ref.release(); ctx->fit.release(); ctx->wnorm.release();
+    ctx->d_ref.release(); ctx->d_fit.release(); ctx->d_ref_stats.release(); ctx->d_fit_stats.release();
+    ctx->cand_key.release(); ctx->cand_idx.release(); ctx->cand_cnt.release(); ctx->cand_tau.release();
+    ctx->flags.release(); ctx->bad_rows.release(); ctx->scalars.release(); ctx->rows_buf.release();
+    ctx->out_dist.release(); ctx->out_idx.release();
+    ctx->tm.destroy();
+    ctx->user_tm.destroy();
+    cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+const char *mdsctk_knn_last_error(const mdsctk_knn_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
+{
+    if (!ctx || !key) return MDSCTK_KNN_EINVAL;
+    if (!strcmp(key, "rms_kernel")) {
+        if (value < 0 || value > 2) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel must be 0, 1 or 2");
+        ctx->rms_kernel = (int)value;
+    } else if (!strcmp(key, "slack")) {
+        if (value < -1 || value > 1024) return fail(ctx, MDSCTK_KNN_EINVAL, "slack out of range");
+        ctx->slack = value;
+    } else if (!strcmp(key, "cert_scale_ppm")) {
+        if (value < 0) return fail(ctx, MDSCTK_KNN_EINVAL, "cert_scale_ppm must be >= 0");
+        ctx->cert_scale_ppm = value;
+    } else {
+        return fail(ctx, MDSCTK_KNN_EINVAL, std::string("unknown option: ") + key);
+    }
+    return 0;
+}
+
+int mdsctk_knn_get_stats(const mdsctk_knn_ctx *ctx, mdsctk_knn_stats *out)
+{
+    if (!ctx || !out) return MDSCTK_KNN_EINVAL;
+    *out = ctx->stats;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ RMSD path ---- */
+int mdsctk_knn_rms_alloc_reference(mdsctk_knn_ctx *ctx, long long n_total, int n_atoms, const float *mass)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (n_total <= 0 || n_atoms <= 0 || !mass) return fail(ctx, MDSCTK_KNN_EINVAL, "bad reference shape or NULL mass");
+    if (n_total > 0x7fffffffLL) return fail(ctx, MDSCTK_KNN_EINVAL, "more than 2^31-1 reference frames");
+    Bind b(ctx);
+    ctx->have_ref = false;
+    int rc = upload_weights(ctx, mass, n_atoms);
+    if (rc) return rc;
+    CK(ctx->ref.alloc(n_total, n_atoms), "cudaMalloc(reference set)");
+    ctx->stats.ms_upload = ctx->stats.ms_pack = 0;
+    ctx->have_ref = true;
+    ctx->gmax_dirty = true;
+    return 0;
+}
+
+int mdsctk_knn_rms_pack_shard(mdsctk_knn_ctx *ctx, const float *xyz, long long frame_offset, long long n_frames)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "call mdsctk_knn_rms_alloc_reference first");
+    if (!xyz || frame_offset < 0 || n_frames < 0 || frame_offset + n_frames > ctx->ref.n)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "shard outside the allocated reference set");
+    Bind b(ctx);
+    ctx->gmax_dirty = true;
+    if (n_frames == 0) return 0;
+    return pack_into(ctx, ctx->ref, xyz, frame_offset, n_frames);
+}
+
+int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_arrays, void **dev_ptrs,
+                                    size_t *bytes_per_frame)
+{
+    if (!ctx || !n_arrays) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
+    *n_arrays = 4;
+    if (max_arrays < 4 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 4 arrays");
+    dev_ptrs[0] = ctx->ref.raw.p;    bytes_per_frame[0] = (size_t)ctx->ref.A * 12;
+    dev_ptrs[1] = ctx->ref.planes.p; bytes_per_frame[1] = (size_t)ctx->ref.A_pad * 12;
+    dev_ptrs[2] = ctx->ref.G.p;      bytes_per_frame[2] = 4;
+    dev_ptrs[3] = ctx->ref.cen.p;    bytes_per_frame[3] = 32;
+    ctx->gmax_dirty = true;  // the caller is about to overwrite them (all-gather)
+    return 0;
+}
+
+int mdsctk_knn_rms_set_reference(mdsctk_knn_ctx *ctx, const float *xyz, long long n_frames, int n_atoms,
+                                 const float *mass)
+{
+    int rc = mdsctk_knn_rms_alloc_reference(ctx, n_frames, n_atoms, mass);
+    if (rc) return rc;
+    return mdsctk_knn_rms_pack_shard(ctx, xyz, 0, n_frames);
+}
+
+int mdsctk_knn_rms_query_range(mdsctk_knn_ctx *ctx, long long fit_begin, long long n_fit, int k1, int do_fit,
+                               double *out_dist, int *out_idx)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
+    if (fit_begin < 0 || n_fit <= 0 || fit_begin + n_fit > ctx->ref.n)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "fit range outside the reference set");
+    Bind b(ctx);
+    return rms_run(ctx, ctx->ref, fit_begin, n_fit, k1, do_fit, out_dist, out_idx);
+}
+
+int mdsctk_knn_rms_query(mdsctk_knn_ctx *ctx, const float *fit_xyz, long long n_fit, int k1, int do_fit,
+                         double *out_dist, int *out_idx)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
+    if (!fit_xyz) {
+        if (n_fit != ctx->ref.n) return fail(ctx, MDSCTK_KNN_EINVAL, "fit_xyz == NULL requires n_fit == n_reference");
+        return mdsctk_knn_rms_query_range(ctx, 0, n_fit, k1, do_fit, out_dist, out_idx);
+    }
+    if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
+    Bind b(ctx);
+    CK(ctx->fit.alloc(n_fit, ctx->ref.A), "cudaMalloc(fit set)");
+    int rc = pack_into(ctx, ctx->fit, fit_xyz, 0, n_fit);
+    if (rc) return rc;
+    return rms_run(ctx, ctx->fit, 0, n_fit, k1, do_fit, out_dist, out_idx);
+}
+
+int mdsctk_knn_rms_rows(mdsctk_knn_ctx *ctx, long long fit_begin, long long n_fit, int do_fit, double *out)
+{
+    if (!ctx || !out) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
+    if (fit_begin < 0 || n_fit <= 0 || fit_begin + n_fit > ctx->ref.n)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "fit range outside the reference set");
+    Bind b(ctx);
+    const FrameSetView ref = ctx->ref.view();
+    const size_t row_bytes = (size_t)ref.n * 8;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_fit, ((size_t)256 << 20) / row_bytes));
+    CK(ctx->rows_buf.reserve((size_t)chunk * row_bytes), "cudaMalloc(rows_buf)");
+    for (long long off = 0; off < n_fit; off += chunk) {
+        const int nr = (int)std::min<long long>(chunk, n_fit - off);
+        CK(launch_rms_exact_rows(ref, nullptr, fit_begin + off, nr, ref, ctx->wnorm.as<double>(), do_fit,
+                                 ctx->rows_buf.as<double>(), ctx->st), "rms_exact_rows");
+        sqrt_scale_kernel<<<592, 256, 0, ctx->st>>>(ctx->rows_buf.as<double>(), (size_t)nr * ref.n, 10.0);
+        CK(cudaGetLastError(), "sqrt_scale");
+        CK(cudaMemcpyAsync(out + (size_t)off * ref.n, ctx->rows_buf.p, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost,
+                           ctx->st), "D2H rows");
+        CK(cudaStreamSynchronize(ctx->st), "sync rows");
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- vector path ---- */
+int mdsctk_knn_data_alloc_reference(mdsctk_knn_ctx *ctx, long long n_total, int dim)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (n_total <= 0 || dim <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "bad reference shape");
+    if (n_total > 0x7fffffffLL) return fail(ctx, MDSCTK_KNN_EINVAL, "more than 2^31-1 reference rows");
+    Bind b(ctx);
+    ctx->have_dref = false;
+    CK(ctx->d_ref.reserve((size_t)n_total * dim * 8), "cudaMalloc(reference rows)");
+    ctx->dn_ref = n_total; ctx->ddim = dim; ctx->have_dref = true; ctx->dstats_dirty = true;
+    ctx->stats.ms_upload = ctx->stats.ms_pack = 0;
+    return 0;
+}
+
+int mdsctk_knn_data_upload_shard(mdsctk_knn_ctx *ctx, const double *rows, long long row_offset, long long n_rows)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_dref) return fail(ctx, MDSCTK_KNN_ESTATE, "call mdsctk_knn_data_alloc_reference first");
+    if (!rows || row_offset < 0 || n_rows < 0 || row_offset + n_rows > ctx->dn_ref)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "shard outside the allocated reference set");
+    Bind b(ctx);
+    ctx->dstats_dirty = true;
+    if (n_rows == 0) return 0;
+    ctx->tm.start(ctx->st);
+    CK(cudaMemcpyAsync(ctx->d_ref.as<double>() + (size_t)row_offset * ctx->ddim, rows, (size_t)n_rows * ctx->ddim * 8,
+                       cudaMemcpyHostToDevice, ctx->st), "H2D rows");
+    ctx->stats.ms_upload += ctx->tm.stop(ctx->st);
+    return 0;
+}
+
+int mdsctk_knn_data_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_arrays, void **dev_ptrs,
+                                     size_t *bytes_per_row)
+{
+    if (!ctx || !n_arrays) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_dref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
+    *n_arrays = 1;
+    if (max_arrays < 1 || !dev_ptrs || !bytes_per_row) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 1 array");
+    dev_ptrs[0] = ctx->d_ref.p;
+    bytes_per_row[0] = (size_t)ctx->ddim * 8;
+    ctx->dstats_dirty = true;
+    return 0;
+}
+
+int mdsctk_knn_data_set_reference(mdsctk_knn_ctx *ctx, const double *rows, long long n_rows, int dim)
+{
+    int rc = mdsctk_knn_data_alloc_reference(ctx, n_rows, dim);
+    if (rc) return rc;
+    return mdsctk_knn_data_upload_shard(ctx, rows, 0, n_rows);
+}
+
+int mdsctk_knn_data_query_range(mdsctk_knn_ctx *ctx, long long fit_begin, long long n_fit, int k1, int metric,
+                                double *out_dist, int *out_idx)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_dref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
+    if (fit_begin < 0 || n_fit <= 0 || fit_begin + n_fit > ctx->dn_ref)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "fit range outside the reference set");
+    Bind b(ctx);
+    return data_run(ctx, ctx->d_ref.as<double>() + (size_t)fit_begin * ctx->ddim, true, fit_begin, n_fit, k1, metric,
+                    out_dist, out_idx);
+}
+
+int mdsctk_knn_data_query(mdsctk_knn_ctx *ctx, const double *fit_rows, long long n_fit, int k1, int metric,
+                          double *out_dist, int *out_idx)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_dref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
+    if (!fit_rows) {
+        if (n_fit != ctx->dn_ref) return fail(ctx, MDSCTK_KNN_EINVAL, "fit_rows == NULL requires n_fit == n_reference");
+        return mdsctk_knn_data_query_range(ctx, 0, n_fit, k1, metric, out_dist, out_idx);
+    }
+    if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
+    Bind b(ctx);
+    CK(ctx->d_fit.reserve((size_t)n_fit * ctx->ddim * 8), "cudaMalloc(fit rows)");
+    ctx->tm.start(ctx->st);
+    CK(cudaMemcpyAsync(ctx->d_fit.p, fit_rows, (size_t)n_fit * ctx->ddim * 8, cudaMemcpyHostToDevice, ctx->st),
+       "H2D fit rows");
+    ctx->stats.ms_upload += ctx->tm.stop(ctx->st);
+    return data_run(ctx, ctx->d_fit.as<double>(), false, 0, n_fit, k1, metric, out_dist, out_idx);
+}
+
+int mdsctk_knn_timer_start(mdsctk_knn_ctx *ctx)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    Bind b(ctx);
+    ctx->user_tm.start(ctx->st);
+    CK(cudaGetLastError(), "timer_start");
+    return 0;
+}
+
+int mdsctk_knn_timer_stop(mdsctk_knn_ctx *ctx, double *elapsed_ms)
+{
+    if (!ctx || !elapsed_ms) return MDSCTK_KNN_EINVAL;
+    Bind b(ctx);
+    *elapsed_ms = ctx->user_tm.stop(ctx->st);
+    CK(cudaGetLastError(), "timer_stop");
+    return 0;
+}
+
+int mdsctk_knn_fetch(mdsctk_knn_ctx *ctx, double *out_dist, int *out_idx)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (ctx->out_rows <= 0) return fail(ctx, MDSCTK_KNN_ESTATE, "no query results to fetch");
+    Bind b(ctx);
+    const size_t n = (size_t)ctx->out_rows * ctx->out_k1;
+    ctx->tm.start(ctx->st);
+    if (out_dist) CK(cudaMemcpyAsync(out_dist, ctx->out_dist.p, n * 8, cudaMemcpyDeviceToHost, ctx->st), "D2H distances");
+    if (out_idx) CK(cudaMemcpyAsync(out_idx, ctx->out_idx.p, n * 4, cudaMemcpyDeviceToHost, ctx->st), "D2H indices");
+    ctx->stats.ms_download = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "fetch");
+    return 0;
+}
+
+}  // extern "C"

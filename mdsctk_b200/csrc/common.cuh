@@ -1,0 +1,80 @@
+// common.cuh -- shared declarations of the B200 kNN stage (device layouts, launch entry points).
+//
+// HBM layout of a frame set (RMSD path).  "frames x 3 x atoms" SoA, frame-major so a
+// contiguous block of frames is a contiguous block of bytes in every array (that is what
+// makes the row-sharded all-gather a plain concatenation):
+//   raw    float  [n][A][3]        decoded coordinates, nm, uncentred (FP64 re-score input)
+//   planes float  [n][3][A_pad]    centred, scaled by sqrt(m_a / M); zero padded to A_pad
+//   G      float  [n]              sum_a (m_a/M) |x_a - c|^2          (fp32 copy for the sweep)
+//   cen    double [n][4]           mass-weighted centroid (x,y,z) and G in FP64
+// With the weights normalised to sum 1, min-RMSD^2 = G_q + G_r - 2*lambda_max (nm^2).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mdsctk {
+
+constexpr int kAtomPad = 16;  // A_pad = roundup(A, 16): SIMT k-chunk and 2 x UMMA_K(tf32)=8
+
+inline int pad_atoms(int a) { return (a + kAtomPad - 1) / kAtomPad * kAtomPad; }
+
+struct FrameSetView {
+    const float *raw;     // [n][A][3]
+    const float *planes;  // [n][3][A_pad]
+    const float *G;       // [n]
+    const double *cen;    // [n][4]
+    long long n;
+    int A, A_pad;
+};
+
+// Per-row candidate lists kept in HBM/L2 while the sweep streams the reference set.
+//   key [rows][cap]  approximate d^2 (float) or exact key (double path)
+//   idx [rows][cap]  reference index
+//   cnt [rows]       entries in use;  tau [rows] current admission threshold
+template <typename KeyT>
+struct CandLists {
+    KeyT *key;
+    int *idx;
+    int *cnt;
+    KeyT *tau;
+    int cap;   // list capacity per row
+    int keep;  // entries kept by a compaction (k1 + slack)
+};
+
+// ---- launch wrappers (defined in the .cu files) -----------------------------------
+cudaError_t launch_pack_frames(const float *raw, const double *mass_norm, long long n, int A, int A_pad,
+                               float *planes, float *G, double *cen, cudaStream_t st);
+
+cudaError_t launch_rms_sweep_simt(const FrameSetView &fit, long long fit_begin, long long n_fit,
+                                  const FrameSetView &ref, int do_fit, CandLists<float> cl, cudaStream_t st);
+
+// FP64 re-score of the kept candidates, final (distance, index) sort, certificate.
+//   out_dist [n_fit][k1] (Angstrom), out_idx [n_fit][k1], flags[n_fit] (1 = certified),
+//   err_max: device double, max |approx - exact| d^2 seen;  n_bad: device int counter.
+cudaError_t launch_rms_rescore(const FrameSetView &fit, long long fit_begin, long long n_fit,
+                               const FrameSetView &ref, const double *mass_norm, int do_fit,
+                               CandLists<float> cl, int k1, double eps_scale, float g_ref_max,
+                               double *out_dist, int *out_idx, int *flags, double *err_max, int *n_bad,
+                               int *bad_rows, cudaStream_t st);
+
+// Exact FP64 d^2 of fit row(s) against every reference frame: out[n_rows][n_ref] (nm^2).
+cudaError_t launch_rms_exact_rows(const FrameSetView &fit, const int *row_ids, long long fit_begin,
+                                  int n_rows, const FrameSetView &ref, const double *mass_norm, int do_fit,
+                                  double *out_d2, cudaStream_t st);
+
+// Exact top-k1 of full rows of doubles: rows_d2[n_rows][n_ref] -> out (written at row_ids[r]).
+cudaError_t launch_select_rows_f64(const double *rows_d2, int n_rows, long long n_ref, int k1,
+                                   const int *row_ids, double scale_sqrt, double *out_dist, int *out_idx,
+                                   cudaStream_t st);
+
+// Vector path (FP64 exact sweep).
+cudaError_t launch_data_rowstats(const double *rows, long long n, int dim, double *stats, cudaStream_t st);
+cudaError_t launch_data_sweep(const double *fit, const double *fit_stats, long long n_fit, const double *ref,
+                              const double *ref_stats, long long n_ref, int dim, int metric,
+                              CandLists<double> cl, cudaStream_t st);
+cudaError_t launch_data_finalize(CandLists<double> cl, long long n_fit, int k1, double *out_dist, int *out_idx,
+                                 cudaStream_t st);
+
+cudaError_t launch_max_float(const float *v, long long n, float *out, cudaStream_t st);
+
+}  // namespace mdsctk

@@ -1,0 +1,107 @@
+// qcp.cuh -- per-pair rotation: Theobald's quaternion characteristic polynomial (QCP).
+//
+// Replaces GROMACS do_fit (calc_fit_R + 6x6 Jacobi + rotate) followed by rmsdev, as called
+// from distance() at knn_rms.cpp:38-41.  For centred, sqrt(m/M)-scaled frames x, y with
+// S_ab = sum_n x_na y_nb, G = sum |x|^2 and E0 = (Gx+Gy)/2, the minimum over proper
+// rotations is  RMSD^2 = 2 (E0 - lambda_max(K))  where K is the 4x4 traceless key matrix of
+// S.  lambda_max is the largest root of
+//     P(l) = l^4 + C2 l^2 + C1 l + C0,   C2 = -2 |S|_F^2,  C1 = -8 det S,  C0 = det K,
+// found by Newton from l0 = E0 >= lambda_max.  All roots are real, so the iterates decrease
+// monotonically onto lambda_max and EVERY iterate gives a valid lower bound on RMSD^2 --
+// a pair is rejected as soon as that bound exceeds the row's admission threshold.
+// No rotation matrix is ever formed.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mdsctk {
+
+struct QcpCoef {
+    float c2, c1, c0;
+};
+
+// s[3*a+b] = S_ab
+__device__ __forceinline__ QcpCoef qcp_coefficients(const float *s)
+{
+    const float sxx = s[0], sxy = s[1], sxz = s[2];
+    const float syx = s[3], syy = s[4], syz = s[5];
+    const float szx = s[6], szy = s[7], szz = s[8];
+    QcpCoef c;
+    float f = sxx * sxx;
+    f = fmaf(sxy, sxy, f); f = fmaf(sxz, sxz, f);
+    f = fmaf(syx, syx, f); f = fmaf(syy, syy, f); f = fmaf(syz, syz, f);
+    f = fmaf(szx, szx, f); f = fmaf(szy, szy, f); f = fmaf(szz, szz, f);
+    c.c2 = -2.0f * f;
+    // det S by cofactors of the first row
+    const float m0 = fmaf(syy, szz, -syz * szy);
+    const float m1 = fmaf(syx, szz, -syz * szx);
+    const float m2 = fmaf(syx, szy, -syy * szx);
+    const float det = fmaf(sxx, m0, fmaf(-sxy, m1, sxz * m2));
+    c.c1 = -8.0f * det;
+    // key matrix (symmetric, traceless)
+    const float k00 = sxx + syy + szz;
+    const float k11 = sxx - syy - szz;
+    const float k22 = syy - sxx - szz;
+    const float k33 = szz - sxx - syy;
+    const float k01 = syz - szy, k02 = szx - sxz, k03 = sxy - syx;
+    const float k12 = sxy + syx, k13 = szx + sxz, k23 = syz + szy;
+    // det K from the 2x2 minors of rows (0,1) and rows (2,3)
+    const float a0 = fmaf(k00, k11, -k01 * k01);
+    const float a1 = fmaf(k00, k12, -k02 * k01);
+    const float a2 = fmaf(k00, k13, -k03 * k01);
+    const float a3 = fmaf(k01, k12, -k02 * k11);
+    const float a4 = fmaf(k01, k13, -k03 * k11);
+    const float a5 = fmaf(k02, k13, -k03 * k12);
+    const float b0 = fmaf(k02, k13, -k12 * k03);
+    const float b1 = fmaf(k02, k23, -k22 * k03);
+    const float b2 = fmaf(k02, k33, -k23 * k03);
+    const float b3 = fmaf(k12, k23, -k22 * k13);
+    const float b4 = fmaf(k12, k33, -k23 * k13);
+    const float b5 = fmaf(k22, k33, -k23 * k23);
+    float d = a0 * b5;
+    d = fmaf(-a1, b4, d);
+    d = fmaf(a2, b3, d);
+    d = fmaf(a3, b2, d);
+    d = fmaf(-a4, b1, d);
+    d = fmaf(a5, b0, d);
+    c.c0 = d;
+    return c;
+}
+
+// One Newton step on P from x; returns the new iterate.
+__device__ __forceinline__ float qcp_newton_step(const QcpCoef &c, float x)
+{
+    const float x2 = x * x;
+    const float b = (x2 + c.c2) * x;
+    const float a = b + c.c1;
+    const float p = fmaf(a, x, c.c0);
+    const float dp = fmaf(2.0f * x2, x, b + a);
+    return x - __fdividef(p, dp);
+}
+
+// Approximate min-RMSD^2 (nm^2) of one pair, or +inf as soon as a Newton iterate proves
+// RMSD^2 > tau.  e0 = (Gq+Gr)/2 with weights normalised to sum 1.
+__device__ __forceinline__ float qcp_msd_bounded(const float *s, float e0, float tau, int do_fit)
+{
+    const float kInf = __uint_as_float(0x7f800000u);
+    if (!do_fit) {  // --nofit: lambda = trace S
+        const float d2 = fmaxf(2.0f * (e0 - (s[0] + s[4] + s[8])), 0.0f);
+        return d2 < tau ? d2 : kInf;
+    }
+    const QcpCoef c = qcp_coefficients(s);
+    float x = e0;
+    float xn = qcp_newton_step(c, x);
+    if (!(xn == xn)) xn = x;  // 0/0 when both frames are degenerate
+    if (2.0f * (e0 - xn) > tau) return kInf;
+#pragma unroll 1
+    for (int it = 0; it < 24; ++it) {
+        if (fabsf(xn - x) <= 4e-7f * fabsf(xn)) break;
+        x = xn;
+        xn = qcp_newton_step(c, x);
+        if (!(xn == xn)) { xn = x; break; }
+        if (2.0f * (e0 - xn) > tau) return kInf;
+    }
+    const float d2 = fmaxf(2.0f * (e0 - xn), 0.0f);
+    return d2 < tau ? d2 : kInf;
+}
+
+}  // namespace mdsctk

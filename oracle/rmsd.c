@@ -35,23 +35,29 @@ static void jacobi_sym(int n, double a[JMAX][JMAX], double eval[JMAX], double ev
             diag += a[i][i] * a[i][i];
             for (int j = i + 1; j < n; j++) off += a[i][j] * a[i][j];
         }
-        if (off <= 1e-36 * (diag + off) || off == 0.0) break;
+        if (off <= 1e-32 * (diag + off) || off == 0.0) break;
         for (int p = 0; p < n - 1; p++) {
             for (int q = p + 1; q < n; q++) {
                 double apq = a[p][q];
                 if (apq == 0.0) continue;
+                /* an off-diagonal element below the rounding unit of both diagonals is dropped */
+                double g = 100.0 * fabs(apq);
+                if (sweep > 2 && fabs(a[p][p]) + g == fabs(a[p][p]) && fabs(a[q][q]) + g == fabs(a[q][q])) {
+                    a[p][q] = a[q][p] = 0.0;
+                    continue;
+                }
                 double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
                 double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < n; k++) { /* A <- A J */
+                /* A <- J^T A J, touching only rows/columns p and q of the symmetric matrix */
+                a[p][p] -= t * apq;
+                a[q][q] += t * apq;
+                a[p][q] = a[q][p] = 0.0;
+                for (int k = 0; k < n; k++) {
+                    if (k == p || k == q) continue;
                     double akp = a[k][p], akq = a[k][q];
-                    a[k][p] = c * akp - s * akq;
-                    a[k][q] = s * akp + c * akq;
-                }
-                for (int k = 0; k < n; k++) { /* A <- J^T A */
-                    double apk = a[p][k], aqk = a[q][k];
-                    a[p][k] = c * apk - s * aqk;
-                    a[q][k] = s * apk + c * aqk;
+                    a[k][p] = a[p][k] = c * akp - s * akq;
+                    a[k][q] = a[q][k] = s * akp + c * akq;
                 }
                 for (int k = 0; k < n; k++) {
                     double vkp = evec[k][p], vkq = evec[k][q];

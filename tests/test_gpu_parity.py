@@ -1,0 +1,190 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the oracle / committed golden vectors.
+
+Tolerances (BASELINE.json north_star): RMSD within 1e-4 relative of the reference float
+chain, neighbour indices identical except documented ties inside that tolerance; knn_data
+bit-exact.  Against the FP64 oracle the FP64 re-score is held to 1e-9 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA, GOLDEN, load_pts
+
+pytestmark = pytest.mark.gpu
+
+RTOL_REF_CHAIN = 1e-4   # vs the reference-faithful float chain (GROMACS do_fit/rmsdev restatement)
+RTOL_F64 = 1e-9         # vs the FP64 Kabsch oracle
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import mdsctk_b200
+    c = mdsctk_b200.KnnContext(0)
+    yield c
+    c.close()
+
+
+def assert_rms_matches(dist, idx, g_dist, g_idx, rtol):
+    assert dist.shape == g_dist.shape and idx.shape == g_idx.shape
+    assert np.abs(dist - g_dist).max() <= rtol * np.maximum(np.abs(g_dist), 1e-6).max()
+    rel = np.abs(dist - g_dist) / np.maximum(g_dist, 1e-6)
+    assert rel.max() <= rtol, f"max rel err {rel.max()}"
+    assert (np.diff(dist, axis=1) >= 0).all()
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_trpcage_knn_rms(ctx, trpcage, k):
+    import mdsctk_b200
+    xyz, mass = trpcage
+    g = np.load(os.path.join(GOLDEN, f"trpcage_rms_k{k}.npz"))
+    dist, idx = mdsctk_b200.knn_rms(xyz, mass, k, ctx=ctx)
+    st = ctx.stats()
+    # index-exact against the FP64 oracle, distances to 1e-9
+    assert np.array_equal(idx, g["idx_f64"])
+    assert_rms_matches(dist, idx, g["dist_f64"], g["idx_f64"], RTOL_F64)
+    # and within the north-star tolerance of the reference's float chain
+    assert_rms_matches(dist, idx, g["dist_ref"], g["idx_ref"], RTOL_REF_CHAIN)
+    if k == 10:
+        assert np.array_equal(idx, g["idx_ref"])
+    else:  # documented near-ties: adjacent swaps only, gaps < 1e-4 relative
+        diff = idx != g["idx_ref"]
+        assert diff.sum() <= 16
+        assert (np.sort(idx, axis=1) == np.sort(g["idx_ref"], axis=1)).all()
+    assert st["fallback_rows"] == 0
+    assert st["max_filter_err"] < 0.6 * st["cert_eps"]
+    assert (idx != np.arange(1000)[:, None]).all()  # self was sorted position 0 and is dropped
+
+
+def test_trpcage_nofit(ctx, trpcage):
+    import mdsctk_b200
+    xyz, mass = trpcage
+    g = np.load(os.path.join(GOLDEN, "trpcage_rms_nofit_k10.npz"))
+    dist, idx = mdsctk_b200.knn_rms(xyz, mass, 10, nofit=True, ctx=ctx)
+    assert np.array_equal(idx, g["idx_f64"])
+    assert_rms_matches(dist, idx, g["dist_f64"], g["idx_f64"], RTOL_F64)
+    assert_rms_matches(dist, idx, g["dist_ref"], g["idx_ref"], RTOL_REF_CHAIN)
+
+
+def test_trpcage_out_of_sample(ctx, trpcage):
+    import mdsctk_b200
+    xyz, mass = trpcage
+    g = np.load(os.path.join(GOLDEN, "trpcage_rms_oos_k10.npz"))
+    fit, ref = xyz[::10], np.delete(xyz, np.arange(0, 1000, 10), axis=0)
+    dist, idx = mdsctk_b200.knn_rms(ref, mass, 10, fit_xyz=fit, ctx=ctx)
+    assert np.array_equal(idx, g["idx_f64"])
+    assert_rms_matches(dist, idx, g["dist_f64"], g["idx_f64"], RTOL_F64)
+
+
+def test_exact_rows_match_oracle(ctx, trpcage):
+    from oracle import binding as ob
+    xyz, mass = trpcage
+    ctx.rms_set_reference(xyz, mass)
+    rows = ctx.rms_rows(5, 3)
+    want = ob.rms_rows(xyz, mass, xyz[5:8], mode=1)
+    # self pairs are ~1e-7 A of FP64 cancellation noise on both sides: absolute floor
+    assert (np.abs(rows - want) <= 1e-9 * want + 1e-6).all()
+    assert rows[0, 5] < 1e-5 and rows[1, 6] < 1e-5
+
+
+def test_forced_fallback_gives_same_answer(ctx, trpcage):
+    """Every row fails an impossibly strict certificate -> exact FP64 rows + exact selection."""
+    import mdsctk_b200
+    xyz, mass = trpcage
+    g = np.load(os.path.join(GOLDEN, "trpcage_rms_k10.npz"))
+    ctx.set_option("cert_scale_ppm", 10 ** 12)
+    try:
+        dist, idx = mdsctk_b200.knn_rms(xyz[:300], mass, 10, ctx=ctx)
+        assert ctx.stats()["fallback_rows"] == 300
+    finally:
+        ctx.set_option("cert_scale_ppm", 10 ** 6)
+    from oracle import binding as ob
+    d, i = ob.knn_rms(xyz[:300], mass, 10, mode=1)
+    assert np.array_equal(idx, i)
+    assert np.abs(dist - d).max() <= RTOL_F64 * d.max()
+
+
+def test_k_clamp_and_tiny_inputs(ctx, trpcage):
+    import mdsctk_b200
+    from oracle import binding as ob
+    xyz, mass = trpcage
+    small = xyz[:7]
+    dist, idx = mdsctk_b200.knn_rms(small, mass, 100, ctx=ctx)   # k clamps to n-1 (knn_rms.cpp:224-225)
+    assert dist.shape == (7, 6)
+    d, i = ob.knn_rms(small, mass, 6, mode=1)
+    assert np.array_equal(idx, i) and np.abs(dist - d).max() < 1e-9 * d.max()
+    # ragged sizes around the 64x32 tile edges
+    for n in (33, 65, 97):
+        dist, idx = mdsctk_b200.knn_rms(xyz[:n], mass, 5, ctx=ctx)
+        d, i = ob.knn_rms(xyz[:n], mass, 5, mode=1)
+        assert np.array_equal(idx, i)
+
+
+def test_synthetic_300_atoms(ctx):
+    import mdsctk_b200
+    from mdsctk_b200 import synth
+    from oracle import binding as ob
+    n = 3000
+    xyz = synth.traj_frames(n, 300, 16)
+    mass = synth.traj_masses(300)
+    dist, idx = mdsctk_b200.knn_rms(xyz, mass, 32, ctx=ctx)
+    st = ctx.stats()
+    d, i = ob.knn_rms(xyz, mass, 32, fit=xyz[:256], mode=1)
+    assert np.array_equal(idx[:256], i)
+    assert np.abs(dist[:256] - d).max() <= RTOL_F64 * d.max()
+    d0, i0 = ob.knn_rms(xyz, mass, 32, fit=xyz[:64], mode=0)
+    assert (np.abs(dist[:64] - d0) / d0).max() <= RTOL_REF_CHAIN
+    assert st["max_filter_err"] < 0.6 * st["cert_eps"]
+    # size-independent properties over all rows: ascending, self dropped, symmetric distances
+    assert (np.diff(dist, axis=1) >= 0).all() and (idx != np.arange(n)[:, None]).all()
+    j = idx[:, 0]
+    back = np.array([dist[j[r]][idx[j[r]] == r][0] if (idx[j[r]] == r).any() else np.nan for r in range(n)])
+    ok = ~np.isnan(back)
+    assert ok.sum() > n // 4 and np.abs(back[ok] - dist[ok, 0]).max() < 1e-9
+
+
+@pytest.mark.parametrize("name,dim,k", [("rings", 2, 10), ("rings", 2, 20), ("swissroll", 3, 10), ("swissroll", 3, 12)])
+def test_knn_data_bit_exact(ctx, name, dim, k):
+    import mdsctk_b200
+    pts = load_pts(f"{name}.pts", dim)
+    g = np.load(os.path.join(GOLDEN, f"{name}_data_k{k}.npz"))
+    dist, idx = mdsctk_b200.knn_data(pts, k, ctx=ctx)
+    assert np.array_equal(idx, g["idx"])
+    assert np.array_equal(dist, g["dist"])       # bit-identical doubles
+
+
+def test_knn_data_correlation_and_oos(ctx):
+    import mdsctk_b200
+    sw = load_pts("swissroll.pts", 3)
+    g = np.load(os.path.join(GOLDEN, "swissroll_data_corr_k10.npz"))
+    dist, idx = mdsctk_b200.knn_data(sw, 10, correlation=True, ctx=ctx)
+    # dim=3 correlation distances are massively tied (3-point correlations): compare values
+    assert np.array_equal(dist, g["dist"])
+    oos = load_pts("swissroll-outofsample.pts", 3)
+    g = np.load(os.path.join(GOLDEN, "swissroll_data_oos_k10.npz"))
+    dist, idx = mdsctk_b200.knn_data(sw, 10, fit_rows=oos, ctx=ctx)
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
+
+
+def test_knn_data_wide_rows(ctx):
+    import mdsctk_b200
+    from mdsctk_b200 import synth
+    from oracle import binding as ob
+    rows = synth.phipsi_rows(2500, 512, 8)
+    dist, idx = mdsctk_b200.knn_data(rows, 64, ctx=ctx)
+    d, i = ob.knn_data(rows, 64, fit=rows[:256])
+    assert np.array_equal(idx[:256], i) and np.array_equal(dist[:256], d)
+    rows = synth.phipsi_rows(700, 37 * 2, 4)      # dim not a multiple of the 16-wide chunk
+    dist, idx = mdsctk_b200.knn_data(rows, 12, correlation=True, ctx=ctx)
+    d, i = ob.knn_data(rows, 12, metric=1)
+    assert np.array_equal(idx, i) and np.array_equal(dist, d)
+
+
+def test_errors_are_reported_not_thrown(ctx, trpcage):
+    import mdsctk_b200
+    xyz, mass = trpcage
+    ctx.rms_set_reference(xyz[:10], mass)
+    with pytest.raises(mdsctk_b200.KnnError):
+        ctx.rms_query(11)                      # k1 > n_ref
+    with pytest.raises(mdsctk_b200.KnnError):
+        ctx.rms_query(3, fit_range=(8, 5))     # range outside the reference set

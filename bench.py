@@ -97,14 +97,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_peaks():
+def measured_peaks(rms_kernel):
+    """Roofline denominator: MEASURED_PEAKS.json's sustained dense bf16 figure for the bf16 kernel
+    (the sweep is timed inside a seconds-long step); half of it for the TF32 / FP32-recovering
+    kernels (dense TF32 runs at half the bf16 tensor rate; cuBLAS TF32 8192^3 measured on this pool:
+    775 burst / 621 sustained TFLOP/s, profiles/peaks_r01.json)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         m = json.load(open(p))
-        return {"tf32_tflops": m["bf16_tflops_sustained"] / 2.0, "source":
-                "MEASURED_PEAKS.json bf16_tflops_sustained/2 (dense TF32 = half the bf16 tensor rate; "
-                "cuBLAS TF32 8192^3 measured on this pool: profiles/peaks_r01.json)", "hbm_gbs": m["hbm_gbs"]}
-    return {"tf32_tflops": 1590.0 / 2.0, "source": "fallback 1.59 PFLOP/s bf16 / 2 (B200_PROFILING.md)", "hbm_gbs": 6650.0}
+        bf16, src = m["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
+    else:
+        bf16, src = 1400.0, "fallback ~1.4 PFLOP/s sustained bf16 (B200_PROFILING.md; of fallback)"
+    if rms_kernel == 3:
+        return {"tflops": bf16, "source": src + "; kernel issues bf16 MMAs"}
+    return {"tflops": bf16 / 2.0, "source": src + " / 2 = dense TF32 rate"}
 
 
 def cpu_baseline_sample(wl, rows=None):
@@ -295,12 +301,13 @@ def main():
     if rank == 0:
         pairs_per_step = world * rows * n_total
         value = pairs_per_step * args.steps / (dev_ms * 1e-3)
-        peaks = measured_peaks()
         sweep_tflops = world * rows * n_total * FLOP_PER_PAIR * args.steps / (sweep_ms * 1e-3) / 1e12 / world
         st = ctx.stats()
+        peaks = measured_peaks(st["rms_kernel"])
         kern = {0: "rms_sweep_simt_kernel (FP32 CUDA-core contraction + QCP + streaming top-k)",
-                1: "rms_sweep_tc_kernel (tcgen05 3xTF32 contraction + QCP + streaming top-k)",
-                2: "rms_sweep_tc_kernel (tcgen05 1xTF32 contraction + QCP + streaming top-k)"}[st["rms_kernel"]]
+                1: "rms_sweep_tc_kernel<1> (tcgen05 kind::tf32, 3xTF32 split contraction + QCP + streaming top-k)",
+                2: "rms_sweep_tc_kernel<2> (tcgen05 kind::tf32, 1xTF32 contraction + QCP + streaming top-k)",
+                3: "rms_sweep_tc_kernel<3> (tcgen05 kind::f16, 3xBF16 split contraction + QCP + streaming top-k)"}[st["rms_kernel"]]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
         if os.path.exists(tp):
@@ -308,7 +315,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if st["rms_kernel"] == 0 else "tf32", "data": "synthetic",
+            "dtype": {0: "f32", 1: "tf32", 2: "tf32", 3: "bf16"}[st["rms_kernel"]] + " contraction (fp32 accumulate), f64 re-score",
+            "data": "synthetic",
             "config": {"workload": wl["name"], "frames": n_total, "atoms": ATOMS, "k": wl["k"],
                        "fit_rows_per_rank_per_step": rows, "parallelism": f"row-sharded x{world}, reference replicated",
                        "l2": "inputs larger than L2 (reference planes %.0f MB + raw %.0f MB vs 126 MB L2)" %
@@ -319,8 +327,9 @@ def main():
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": sweep_tflops, "peak": peaks["tf32_tflops"], "unit": "TFLOP/s",
-                         "frac": sweep_tflops / peaks["tf32_tflops"], "traffic": traffic,
+            "roofline": {"bound": "tensor", "achieved": sweep_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": sweep_tflops / peaks["tflops"], "traffic": traffic,
+                         "mma_per_flop": 1 if st["rms_kernel"] in (0, 2) else 3,
                          "kernel": kern.split(" ")[0], "flop_per_pair": FLOP_PER_PAIR, "peak_source": peaks["source"],
                          "sweep_ms_per_step": sweep_ms / args.steps, "post_ms_per_step": post_ms / args.steps},
             "cpu_baseline": cpu_baseline_sample(wl),

@@ -54,7 +54,12 @@ enum {
 enum { MDSCTK_KNN_EUCLIDEAN = 0, MDSCTK_KNN_CORRELATION = 1 };
 
 /* rms_kernel option values */
-enum { MDSCTK_KNN_RMS_SIMT_FP32 = 0, MDSCTK_KNN_RMS_TC_3XTF32 = 1, MDSCTK_KNN_RMS_TC_1XTF32 = 2 };
+enum {
+    MDSCTK_KNN_RMS_SIMT_FP32 = 0,  /* FP32 CUDA-core contraction                                  */
+    MDSCTK_KNN_RMS_TC_3XTF32 = 1,  /* tcgen05 kind::tf32, hi/lo operand split (3 MMAs)              */
+    MDSCTK_KNN_RMS_TC_1XTF32 = 2,  /* tcgen05 kind::tf32, hi only (coarse filter)                   */
+    MDSCTK_KNN_RMS_TC_3XBF16 = 3   /* tcgen05 kind::f16 on bf16 hi/mid operand split (3 MMAs)       */
+};
 
 typedef struct mdsctk_knn_ctx mdsctk_knn_ctx;
 
@@ -70,9 +75,12 @@ typedef struct mdsctk_knn_stats {
     long long fallback_rows;   /* rows that failed certification and were redone    */
     long long sweep_appends;   /* candidates appended by the sweep (diagnostic)     */
     double max_filter_err; /* max |approx d^2 - exact d^2| over all candidates      */
-    double cert_eps;       /* absolute d^2 margin used by the certificate           */
+    double max_filter_spread; /* max over rows of max-min of (approx - exact) d^2        */
+    double cert_eps;       /* absolute d^2 noise margin used by the certificate     */
     int rms_kernel;        /* kernel actually used by the last RMSD query           */
     int k_keep;            /* candidates kept per row (k1 + slack)                  */
+    int lists_per_row;     /* candidate lists per row kept by the sweep             */
+    int rescored_max;      /* most candidates any row needed before its certificate held */
 } mdsctk_knn_stats;
 
 int mdsctk_knn_abi_version(void);
@@ -84,7 +92,8 @@ void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx);
 const char *mdsctk_knn_last_error(const mdsctk_knn_ctx *ctx);
 
 /* Tunables: "rms_kernel" (enum above), "slack" (extra candidates kept per row, -1 = auto),
- * "cert_scale_ppm" (certificate margin multiplier in parts-per-million of the default). */
+ * "cert_scale_ppm" (certificate margin multiplier in parts-per-million of the default),
+ * "debug_tile" (0/1, see mdsctk_knn_debug_fetch_tile). */
 int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value);
 int mdsctk_knn_get_stats(const mdsctk_knn_ctx *ctx, mdsctk_knn_stats *out);
 
@@ -128,6 +137,11 @@ int mdsctk_knn_data_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n
                                      size_t *bytes_per_row);
 int mdsctk_knn_data_query_range(mdsctk_knn_ctx *ctx, long long fit_begin, long long n_fit, int k1, int metric,
                                 double *out_dist, int *out_idx);
+
+/* Diagnostic: after set_option("debug_tile", 1) a tensor-core RMSD query also captures the raw
+ * TMEM accumulators of (fit tile 0, reference tile 0): out[128][9][48] floats, S_ab of fit row q
+ * against reference j at out[q][3*a+b][j]. */
+int mdsctk_knn_debug_fetch_tile(mdsctk_knn_ctx *ctx, float *out);
 
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of this library
  * is launched on): start records an event, stop records a second one, waits for it and returns

@@ -13,7 +13,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-RMS_SIMT_FP32, RMS_TC_3XTF32, RMS_TC_1XTF32 = 0, 1, 2
+RMS_SIMT_FP32, RMS_TC_3XTF32, RMS_TC_1XTF32, RMS_TC_3XBF16 = 0, 1, 2, 3
 EUCLIDEAN, CORRELATION = 0, 1
 
 SYMBOLS = [
@@ -24,6 +24,7 @@ SYMBOLS = [
     "mdsctk_knn_data_set_reference", "mdsctk_knn_data_query", "mdsctk_knn_data_alloc_reference",
     "mdsctk_knn_data_upload_shard", "mdsctk_knn_data_reference_arrays", "mdsctk_knn_data_query_range",
     "mdsctk_knn_fetch", "mdsctk_knn_rms_rows", "mdsctk_knn_timer_start", "mdsctk_knn_timer_stop",
+    "mdsctk_knn_debug_fetch_tile",
 ]
 
 
@@ -35,8 +36,9 @@ class Stats(C.Structure):
     _fields_ = [("ms_upload", C.c_double), ("ms_pack", C.c_double), ("ms_sweep", C.c_double),
                 ("ms_rescore", C.c_double), ("ms_fallback", C.c_double), ("ms_download", C.c_double),
                 ("pairs", C.c_longlong), ("launches", C.c_longlong), ("fallback_rows", C.c_longlong),
-                ("sweep_appends", C.c_longlong), ("max_filter_err", C.c_double), ("cert_eps", C.c_double),
-                ("rms_kernel", C.c_int), ("k_keep", C.c_int)]
+                ("sweep_appends", C.c_longlong), ("max_filter_err", C.c_double), ("max_filter_spread", C.c_double),
+                ("cert_eps", C.c_double), ("rms_kernel", C.c_int), ("k_keep", C.c_int), ("lists_per_row", C.c_int),
+                ("rescored_max", C.c_int)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -81,6 +83,7 @@ def load_library():
     L.mdsctk_knn_fetch.argtypes = [vp, dp, ip]
     L.mdsctk_knn_rms_rows.argtypes = [vp, ll, ll, C.c_int, dp]
     L.mdsctk_knn_timer_start.argtypes = [vp]
+    L.mdsctk_knn_debug_fetch_tile.argtypes = [vp, fp]
     L.mdsctk_knn_timer_stop.argtypes = [vp, dp]
     _LIB = L
     return L
@@ -229,6 +232,11 @@ class KnnContext:
                                                _ptr(dist, C.c_double), _ptr(idx, C.c_int))
         self._ck(rc, "data_query")
         return dist, idx
+
+    def debug_fetch_tile(self):
+        out = np.empty((128, 9, 48), dtype=np.float32)
+        self._ck(self._L.mdsctk_knn_debug_fetch_tile(self._h, _ptr(out, C.c_float)), "debug_fetch_tile")
+        return out
 
     def timer_start(self):
         self._ck(self._L.mdsctk_knn_timer_start(self._h), "timer_start")

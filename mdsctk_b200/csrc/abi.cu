@@ -41,7 +41,7 @@ struct DevBuf {
 };
 
 struct FrameSet {
-    DevBuf raw, planes, G, cen;
+    DevBuf raw, planes, hi, lo, bh, bm, G, cen;
     long long n = 0;
     int A = 0, A_pad = 0;
     FrameSetView view() const
@@ -57,10 +57,18 @@ struct FrameSet {
         cudaError_t e;
         if ((e = raw.reserve((size_t)n * A * 12)) != cudaSuccess) return e;
         if ((e = planes.reserve((size_t)n * 3 * A_pad * 4)) != cudaSuccess) return e;
-        if ((e = G.reserve((size_t)n * 4)) != cudaSuccess) return e;
+        if ((e = hi.reserve((size_t)n * 3 * A_pad * 4)) != cudaSuccess) return e;
+        if ((e = lo.reserve((size_t)n * 3 * A_pad * 4)) != cudaSuccess) return e;
+        if ((e = bh.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
+        if ((e = bm.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
+        if ((e = G.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;  // tensor-core epilogue reads G in 48-wide tiles
         return cen.reserve((size_t)n * 32);
     }
-    void release() { raw.release(); planes.release(); G.release(); cen.release(); n = 0; }
+    void release()
+    {
+        raw.release(); planes.release(); hi.release(); lo.release(); bh.release(); bm.release(); G.release();
+        cen.release(); n = 0;
+    }
 };
 
 struct PhaseTimer {
@@ -86,7 +94,7 @@ struct mdsctk_knn_ctx {
     std::string err;
     PhaseTimer tm, user_tm;
     // options
-    int rms_kernel = MDSCTK_KNN_RMS_SIMT_FP32;
+    int rms_kernel = MDSCTK_KNN_RMS_TC_3XBF16;
     long long slack = -1;
     long long cert_scale_ppm = 1000000;
     // RMSD state
@@ -101,7 +109,9 @@ struct mdsctk_knn_ctx {
     bool have_dref = false, dstats_dirty = true;
     // scratch + results
     DevBuf cand_key, cand_idx, cand_cnt, cand_tau, flags, bad_rows, scalars, rows_buf;
-    DevBuf out_dist, out_idx;
+    DevBuf out_dist, out_idx, debug_tile, row_tau;
+    bool debug_tile_on = false;
+    int n_sms = 148;
     long long out_rows = 0;
     int out_k1 = 0;
     mdsctk_knn_stats stats;
@@ -158,30 +168,40 @@ int pack_into(mdsctk_knn_ctx *ctx, FrameSet &fs, const float *xyz, long long off
     ctx->stats.ms_upload += ctx->tm.stop(ctx->st);
     ctx->tm.start(ctx->st);
     CK(launch_pack_frames(fs.raw.as<float>() + (size_t)off * A * 3, ctx->wnorm.as<double>(), n, A, fs.A_pad,
-                          fs.planes.as<float>() + (size_t)off * 3 * fs.A_pad, fs.G.as<float>() + off,
+                          fs.planes.as<float>() + (size_t)off * 3 * fs.A_pad,
+                          fs.hi.as<float>() + (size_t)off * 3 * fs.A_pad, fs.lo.as<float>() + (size_t)off * 3 * fs.A_pad,
+                          fs.bh.as<uint16_t>() + (size_t)off * 3 * fs.A_pad, fs.bm.as<uint16_t>() + (size_t)off * 3 * fs.A_pad,
+                          fs.G.as<float>() + off,
                           fs.cen.as<double>() + 4 * off, ctx->st), "pack_frames");
     ctx->stats.ms_pack += ctx->tm.stop(ctx->st);
     return 0;
 }
 
-void choose_lists(const mdsctk_knn_ctx *ctx, int k1, int *keep, int *cap)
+void choose_lists(const mdsctk_knn_ctx *ctx, int k1, bool single_list, int *keep, int *cap)
 {
-    long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(16, k1 / 4);
+    // The admission threshold is the keep-th smallest approximate distance of the row, so `slack`
+    // is what the adaptive re-score can fall back on when neighbours sit on a plateau of nearly
+    // equal distances (thermal noise): measured on the 100k x 300 workload, slack >= 96 certifies
+    // every row, and the sweep costs ~5% more per extra 64 kept candidates.
+    (void)single_list;
+    long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(96, 2LL * k1);
     long long kp = ((long long)k1 + slack + 7) / 8 * 8;
     *keep = (int)kp;
     *cap = (int)((kp + 128 + 31) / 32 * 32);
 }
 
-// Bound on |approx d^2 - exact d^2| as a fraction of E0 = (Gq+Gr)/2 (DESIGN.md "certificate").
-// The contraction error grows like sqrt(atoms) * 2^-24 relative to E0; the constants are ~2x
-// the largest error ever observed over >1e6 candidates (stats.max_filter_err reports it).
+// Bound on the NOISE of the filter, |(approx d^2 - exact d^2) - row-common bias|, as a fraction of
+// E0 = (Gq+Gr)/2 (DESIGN.md "certificate").  The contraction error grows like sqrt(atoms) * 2^-24
+// relative to E0; the constants are ~2x the largest half-spread observed over >1e6 candidates
+// (stats.max_filter_spread reports it, and the certificate re-checks it on every row).
 double default_eps_scale(int rms_kernel, int n_atoms)
 {
-    const double sa = std::sqrt((double)std::max(n_atoms, 16));
+    const double sa = std::sqrt((double)std::max(n_atoms, 128));
     switch (rms_kernel) {
-    case MDSCTK_KNN_RMS_TC_1XTF32: return 2.5e-4 * sa;
-    case MDSCTK_KNN_RMS_TC_3XTF32: return 8e-7 * sa;
-    default: return 6e-7 * sa;
+    case MDSCTK_KNN_RMS_TC_1XTF32: return 4e-5 * sa;
+    case MDSCTK_KNN_RMS_TC_3XBF16: return 1.5e-5;       // bf16 split residual 2^-18 per product dominates
+    case MDSCTK_KNN_RMS_TC_3XTF32:
+    default: return 5e-7 * sa;
     }
 }
 
@@ -197,6 +217,7 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
     mdsctk_knn_stats &S = ctx->stats;
     S.ms_sweep = S.ms_rescore = S.ms_fallback = S.ms_download = 0;
     S.pairs = n_fit * ref.n; S.launches = 0; S.fallback_rows = 0; S.sweep_appends = 0; S.max_filter_err = 0;
+    S.max_filter_spread = 0;
     S.rms_kernel = ctx->rms_kernel;
 
     if (ctx->gmax_dirty) {
@@ -208,13 +229,19 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
     }
 
     int keep, cap;
-    choose_lists(ctx, k1, &keep, &cap);
+    const bool use_tc = ctx->rms_kernel != MDSCTK_KNN_RMS_SIMT_FP32;
+    choose_lists(ctx, k1, !use_tc, &keep, &cap);
+    const int n_seg = use_tc ? rms_tc_choose_segments(n_fit, ref.n, ctx->n_sms) : 1;
+    const int H = use_tc ? rms_tc_lists_per_segment() * n_seg : 1;
     S.k_keep = keep;
+    S.lists_per_row = H;
+    if ((size_t)ref.A * 24 + (size_t)keep * H * 2 * 28 + 64 * 80 > 220 * 1024)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "k too large for the FP64 re-score kernel's shared memory");
     CandLists<float> cl;
-    CK(ctx->cand_key.reserve((size_t)n_fit * cap * 4), "cudaMalloc(cand_key)");
-    CK(ctx->cand_idx.reserve((size_t)n_fit * cap * 4), "cudaMalloc(cand_idx)");
-    CK(ctx->cand_cnt.reserve((size_t)n_fit * 4), "cudaMalloc(cand_cnt)");
-    CK(ctx->cand_tau.reserve((size_t)n_fit * 8), "cudaMalloc(cand_tau)");
+    CK(ctx->cand_key.reserve((size_t)n_fit * H * cap * 4), "cudaMalloc(cand_key)");
+    CK(ctx->cand_idx.reserve((size_t)n_fit * H * cap * 4), "cudaMalloc(cand_idx)");
+    CK(ctx->cand_cnt.reserve((size_t)n_fit * H * 4), "cudaMalloc(cand_cnt)");
+    CK(ctx->cand_tau.reserve((size_t)n_fit * H * 8), "cudaMalloc(cand_tau)");
     CK(ctx->flags.reserve((size_t)n_fit * 4), "cudaMalloc(flags)");
     CK(ctx->bad_rows.reserve((size_t)n_fit * 4), "cudaMalloc(bad_rows)");
     CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
@@ -222,9 +249,9 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
     CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
     ctx->out_rows = n_fit; ctx->out_k1 = k1;
     cl.key = ctx->cand_key.as<float>(); cl.idx = ctx->cand_idx.as<int>(); cl.cnt = ctx->cand_cnt.as<int>();
-    cl.tau = ctx->cand_tau.as<float>(); cl.cap = cap; cl.keep = keep;
-    double *d_err = ctx->scalars.as<double>() + 1;
-    int *d_nbad = ctx->scalars.as<int>() + 4;
+    cl.tau = ctx->cand_tau.as<float>(); cl.cap = cap; cl.keep = keep; cl.H = H;
+    double *d_err = ctx->scalars.as<double>() + 1;   // {max |err|, max spread}
+    int *d_nbad = ctx->scalars.as<int>() + 8;
     CK(cudaMemsetAsync(ctx->scalars.p, 0, 64, ctx->st), "memset scalars");
 
     // ---- sweep: all pairs -> k1+slack candidates per row ------------------------------------
@@ -234,7 +261,18 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
         CK(launch_rms_sweep_simt(fit, fit_begin, n_fit, ref, do_fit, cl, ctx->st), "rms_sweep_simt");
         break;
     default:
-        return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel: tensor-core sweep not built into this library");
+        if (ctx->debug_tile_on) CK(ctx->debug_tile.reserve(128 * 432 * 4), "cudaMalloc(debug_tile)");
+        CK(ctx->row_tau.reserve((size_t)n_fit * 4), "cudaMalloc(row_tau)");
+        CK(launch_fill_u32(ctx->row_tau.p, (size_t)n_fit, 0x7f800000u, ctx->st), "fill row_tau");  // +inf
+        {
+            const bool bf = ctx->rms_kernel == MDSCTK_KNN_RMS_TC_3XBF16;
+            CK(launch_rms_sweep_tc(ctx->rms_kernel, fit, bf ? fitset.bh.p : fitset.hi.p, bf ? fitset.bm.p : fitset.lo.p,
+                                   fit_begin, n_fit, ref, bf ? ctx->ref.bh.p : ctx->ref.hi.p,
+                                   bf ? ctx->ref.bm.p : ctx->ref.lo.p, do_fit, n_seg, cl, ctx->row_tau.as<float>(),
+                                   ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
+               "rms_sweep_tc");
+        }
+        break;
     }
     S.launches += 1;
     S.ms_sweep = ctx->tm.stop(ctx->st);
@@ -248,11 +286,13 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
                           ctx->g_ref_max, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(),
                           d_err, d_nbad, ctx->bad_rows.as<int>(), ctx->st), "rms_rescore");
     S.launches += 1;
-    struct { double pad, err; int nbad; } host_sc;
+    struct { double pad, err, spread, done_max; int nbad; } host_sc;
     CK(cudaMemcpyAsync(&host_sc, ctx->scalars.p, sizeof(host_sc), cudaMemcpyDeviceToHost, ctx->st), "D2H scalars");
     S.ms_rescore = ctx->tm.stop(ctx->st);
     CK(cudaGetLastError(), "rescore kernel");
     S.max_filter_err = host_sc.err;
+    S.max_filter_spread = host_sc.spread;
+    S.rescored_max = (int)host_sc.done_max;
     S.fallback_rows = host_sc.nbad;
 
     // ---- rows whose certificate failed: exact FP64 rows + exact selection -------------------
@@ -320,7 +360,7 @@ int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long lon
     CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
     ctx->out_rows = n_fit; ctx->out_k1 = k1;
     cl.key = ctx->cand_key.as<double>(); cl.idx = ctx->cand_idx.as<int>(); cl.cnt = ctx->cand_cnt.as<int>();
-    cl.tau = ctx->cand_tau.as<double>(); cl.cap = cap; cl.keep = keep;
+    cl.tau = ctx->cand_tau.as<double>(); cl.cap = cap; cl.keep = keep; cl.H = 1;
     ctx->tm.start(ctx->st);
     CK(launch_data_sweep(d_fit, fit_stats, n_fit, ctx->d_ref.as<double>(), ref_stats, ctx->dn_ref, dim, metric, cl,
                          ctx->st), "data_sweep");
@@ -370,6 +410,7 @@ int mdsctk_knn_create(mdsctk_knn_ctx **out, int device_id)
     mdsctk_knn_ctx *c = new (std::nothrow) mdsctk_knn_ctx();
     if (!c) { g_create_error = "out of host memory"; return MDSCTK_KNN_ENOMEM; }
     c->dev = device_id;
+    c->n_sms = prop.multiProcessorCount;
     memset(&c->stats, 0, sizeof c->stats);
     cudaSetDevice(device_id);
     if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -392,7 +433,7 @@ void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx)
     ctx->d_ref.release(); ctx->d_fit.release(); ctx->d_ref_stats.release(); ctx->d_fit_stats.release();
     ctx->cand_key.release(); ctx->cand_idx.release(); ctx->cand_cnt.release(); ctx->cand_tau.release();
     ctx->flags.release(); ctx->bad_rows.release(); ctx->scalars.release(); ctx->rows_buf.release();
-    ctx->out_dist.release(); ctx->out_idx.release();
+    ctx->out_dist.release(); ctx->out_idx.release(); ctx->debug_tile.release(); ctx->row_tau.release();
     ctx->tm.destroy();
     ctx->user_tm.destroy();
     cudaStreamDestroy(ctx->st);
@@ -405,7 +446,7 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
 {
     if (!ctx || !key) return MDSCTK_KNN_EINVAL;
     if (!strcmp(key, "rms_kernel")) {
-        if (value < 0 || value > 2) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel must be 0, 1 or 2");
+        if (value < 0 || value > 3) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel must be 0..3");
         ctx->rms_kernel = (int)value;
     } else if (!strcmp(key, "slack")) {
         if (value < -1 || value > 1024) return fail(ctx, MDSCTK_KNN_EINVAL, "slack out of range");
@@ -413,6 +454,8 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
     } else if (!strcmp(key, "cert_scale_ppm")) {
         if (value < 0) return fail(ctx, MDSCTK_KNN_EINVAL, "cert_scale_ppm must be >= 0");
         ctx->cert_scale_ppm = value;
+    } else if (!strcmp(key, "debug_tile")) {
+        ctx->debug_tile_on = value != 0;
     } else {
         return fail(ctx, MDSCTK_KNN_EINVAL, std::string("unknown option: ") + key);
     }
@@ -460,12 +503,16 @@ int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_
 {
     if (!ctx || !n_arrays) return MDSCTK_KNN_EINVAL;
     if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
-    *n_arrays = 4;
-    if (max_arrays < 4 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 4 arrays");
+    *n_arrays = 8;
+    if (max_arrays < 8 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 8 arrays");
     dev_ptrs[0] = ctx->ref.raw.p;    bytes_per_frame[0] = (size_t)ctx->ref.A * 12;
     dev_ptrs[1] = ctx->ref.planes.p; bytes_per_frame[1] = (size_t)ctx->ref.A_pad * 12;
     dev_ptrs[2] = ctx->ref.G.p;      bytes_per_frame[2] = 4;
     dev_ptrs[3] = ctx->ref.cen.p;    bytes_per_frame[3] = 32;
+    dev_ptrs[4] = ctx->ref.hi.p;     bytes_per_frame[4] = (size_t)ctx->ref.A_pad * 12;
+    dev_ptrs[5] = ctx->ref.lo.p;     bytes_per_frame[5] = (size_t)ctx->ref.A_pad * 12;
+    dev_ptrs[6] = ctx->ref.bh.p;     bytes_per_frame[6] = (size_t)ctx->ref.A_pad * 6;
+    dev_ptrs[7] = ctx->ref.bm.p;     bytes_per_frame[7] = (size_t)ctx->ref.A_pad * 6;
     ctx->gmax_dirty = true;  // the caller is about to overwrite them (all-gather)
     return 0;
 }
@@ -609,6 +656,15 @@ int mdsctk_knn_data_query(mdsctk_knn_ctx *ctx, const double *fit_rows, long long
        "H2D fit rows");
     ctx->stats.ms_upload += ctx->tm.stop(ctx->st);
     return data_run(ctx, ctx->d_fit.as<double>(), false, 0, n_fit, k1, metric, out_dist, out_idx);
+}
+
+int mdsctk_knn_debug_fetch_tile(mdsctk_knn_ctx *ctx, float *out)
+{
+    if (!ctx || !out) return MDSCTK_KNN_EINVAL;
+    if (!ctx->debug_tile.p) return fail(ctx, MDSCTK_KNN_ESTATE, "no debug tile captured");
+    Bind b(ctx);
+    CK(cudaMemcpy(out, ctx->debug_tile.p, 128 * 432 * 4, cudaMemcpyDeviceToHost), "D2H debug tile");
+    return 0;
 }
 
 int mdsctk_knn_timer_start(mdsctk_knn_ctx *ctx)

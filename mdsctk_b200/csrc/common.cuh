@@ -5,7 +5,9 @@
 // makes the row-sharded all-gather a plain concatenation):
 //   raw    float  [n][A][3]        decoded coordinates, nm, uncentred (FP64 re-score input)
 //   planes float  [n][3][A_pad]    centred, scaled by sqrt(m_a / M); zero padded to A_pad
-//   G      float  [n]              sum_a (m_a/M) |x_a - c|^2          (fp32 copy for the sweep)
+//   hi, lo float  [n][3][A_pad]    TF32 split of planes: hi = rn_tf32(x), lo = rn_tf32(x - hi)
+//   bh, bm bf16   [n][3][A_pad]    BF16 split of planes: bh = rn_bf16(x), bm = rn_bf16(x - bh)
+//   G      float  [n] (+64 pad)    sum_a (m_a/M) |x_a - c|^2          (fp32 copy for the sweep)
 //   cen    double [n][4]           mass-weighted centroid (x,y,z) and G in FP64
 // With the weights normalised to sum 1, min-RMSD^2 = G_q + G_r - 2*lambda_max (nm^2).
 #pragma once
@@ -37,24 +39,38 @@ struct CandLists {
     int *idx;
     int *cnt;
     KeyT *tau;
-    int cap;   // list capacity per row
+    int cap;   // list capacity
     int keep;  // entries kept by a compaction (k1 + slack)
+    int H;     // lists per fit row (list id = row * H + h): the tensor-core sweep keeps one list per
+               // (reference segment, column half) so that no list is shared between threads
 };
 
 // ---- launch wrappers (defined in the .cu files) -----------------------------------
 cudaError_t launch_pack_frames(const float *raw, const double *mass_norm, long long n, int A, int A_pad,
-                               float *planes, float *G, double *cen, cudaStream_t st);
+                               float *planes, float *hi, float *lo, void *bh, void *bm, float *G, double *cen,
+                               cudaStream_t st);
 
 cudaError_t launch_rms_sweep_simt(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                   const FrameSetView &ref, int do_fit, CandLists<float> cl, cudaStream_t st);
 
+// tcgen05 sweep (rms_tc.cu).  *_hi / *_lo: TF32 split planes, same [n][3][A_pad] layout as planes.
+// mode: 1 = 3xTF32 (hi/lo fp32 planes), 2 = 1xTF32 (hi only), 3 = 3xBF16 (bh/bm bf16 planes).
+// cl.H must be rms_tc_lists_per_segment() * n_seg (reference segments x column groups).
+cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *fit_hi, const void *fit_lo,
+                                long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,
+                                const void *ref_lo, int do_fit, int n_seg, CandLists<float> cl, float *row_tau,
+                                float *debug_tile, int n_sms, cudaStream_t st);
+int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms);
+int rms_tc_lists_per_segment();
+
 // FP64 re-score of the kept candidates, final (distance, index) sort, certificate.
 //   out_dist [n_fit][k1] (Angstrom), out_idx [n_fit][k1], flags[n_fit] (1 = certified),
-//   err_max: device double, max |approx - exact| d^2 seen;  n_bad: device int counter.
+//   err_stats: device double[2] = {max |approx - exact| d^2, max per-row spread of (approx - exact)};
+//   n_bad: device int counter of uncertified rows, listed in bad_rows.
 cudaError_t launch_rms_rescore(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                const FrameSetView &ref, const double *mass_norm, int do_fit,
                                CandLists<float> cl, int k1, double eps_scale, float g_ref_max,
-                               double *out_dist, int *out_idx, int *flags, double *err_max, int *n_bad,
+                               double *out_dist, int *out_idx, int *flags, double *err_stats, int *n_bad,
                                int *bad_rows, cudaStream_t st);
 
 // Exact FP64 d^2 of fit row(s) against every reference frame: out[n_rows][n_ref] (nm^2).
@@ -76,5 +92,6 @@ cudaError_t launch_data_finalize(CandLists<double> cl, long long n_fit, int k1, 
                                  cudaStream_t st);
 
 cudaError_t launch_max_float(const float *v, long long n, float *out, cudaStream_t st);
+cudaError_t launch_fill_u32(void *p, size_t n, uint32_t v, cudaStream_t st);
 
 }  // namespace mdsctk

@@ -4,15 +4,26 @@
 // knn_rms.cpp:186-206 (GROMACS: float centre-of-mass removal) and sets up the operand
 // layout of the contraction: AoS float[n][A][3] (nm) -> planes float[n][3][A_pad] holding
 // sqrt(m_a/M) * (x_a - c), G = sum (m_a/M)|x_a - c|^2, and the FP64 centroid for the re-score.
-// One warp per frame; HBM-bound: 12*A bytes read + 12*A_pad written per frame.
+// plus the TF32 hi/lo split planes of the tensor-core sweep.
+// One warp per frame; HBM-bound: 12*A bytes read + 36*A_pad written per frame.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace mdsctk {
+
+__device__ __forceinline__ float tf32_rn(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 
 __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restrict__ raw,
                                                           const double *__restrict__ wnorm,  // m_a / M (FP64)
                                                           long long n, int A, int A_pad,
-                                                          float *__restrict__ planes, float *__restrict__ G,
+                                                          float *__restrict__ planes, float *__restrict__ hi,
+                                                          float *__restrict__ lo, __nv_bfloat16 *__restrict__ bh,
+                                                          __nv_bfloat16 *__restrict__ bm, float *__restrict__ G,
                                                           double *__restrict__ cen)
 {
     const int lane = threadIdx.x & 31;
@@ -32,7 +43,8 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
         cy += __shfl_xor_sync(0xffffffffu, cy, o);
         cz += __shfl_xor_sync(0xffffffffu, cz, o);
     }
-    float *px = planes + (size_t)f * 3 * A_pad;
+    const size_t pbase = (size_t)f * 3 * A_pad;
+    float *px = planes + pbase;
     float *py = px + A_pad, *pz = py + A_pad;
     double g = 0.0;
     for (int a = lane; a < A_pad; a += 32) {
@@ -46,6 +58,21 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
             ox = (float)(s * dx); oy = (float)(s * dy); oz = (float)(s * dz);
         }
         px[a] = ox; py[a] = oy; pz[a] = oz;
+        if (hi) {  // 3xTF32 operand split for the tensor-core sweep: x ~= hi + lo, both exact TF32 values
+            const float hx = tf32_rn(ox), hy = tf32_rn(oy), hz = tf32_rn(oz);
+            hi[pbase + a] = hx; hi[pbase + A_pad + a] = hy; hi[pbase + 2 * A_pad + a] = hz;
+            lo[pbase + a] = tf32_rn(ox - hx); lo[pbase + A_pad + a] = tf32_rn(oy - hy);
+            lo[pbase + 2 * A_pad + a] = tf32_rn(oz - hz);
+        }
+        if (bh) {  // 3xBF16 split: x ~= bh + bm with a 2^-18 relative residual
+            const float o[3] = {ox, oy, oz};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(o[d]);
+                bh[pbase + d * A_pad + a] = h;
+                bm[pbase + d * A_pad + a] = __float2bfloat16_rn(o[d] - __bfloat162float(h));
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
@@ -56,12 +83,13 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
 }
 
 cudaError_t launch_pack_frames(const float *raw, const double *wnorm, long long n, int A, int A_pad, float *planes,
-                               float *G, double *cen, cudaStream_t st)
+                               float *hi, float *lo, void *bh, void *bm, float *G, double *cen, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
     const int warps = 8;
     const unsigned grid = (unsigned)((n + warps - 1) / warps);
-    pack_frames_kernel<<<grid, warps * 32, 0, st>>>(raw, wnorm, n, A, A_pad, planes, G, cen);
+    pack_frames_kernel<<<grid, warps * 32, 0, st>>>(raw, wnorm, n, A, A_pad, planes, hi, lo, static_cast<__nv_bfloat16 *>(bh),
+                                                    static_cast<__nv_bfloat16 *>(bm), G, cen);
     return cudaGetLastError();
 }
 
@@ -73,6 +101,18 @@ __global__ void max_float_kernel(const float *v, long long n, float *out)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));  // m >= 0
+}
+
+__global__ void fill_u32_kernel(uint32_t *p, size_t n, uint32_t v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+cudaError_t launch_fill_u32(void *p, size_t n, uint32_t v, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    fill_u32_kernel<<<148, 256, 0, st>>>(static_cast<uint32_t *>(p), n, v);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_max_float(const float *v, long long n, float *out, cudaStream_t st)

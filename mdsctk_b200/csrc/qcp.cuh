@@ -75,7 +75,9 @@ __device__ __forceinline__ float qcp_newton_step(const QcpCoef &c, float x)
     const float a = b + c.c1;
     const float p = fmaf(a, x, c.c0);
     const float dp = fmaf(2.0f * x2, x, b + a);
-    return x - __fdividef(p, dp);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dp));
+    return fmaf(-p, r, x);
 }
 
 // Approximate min-RMSD^2 (nm^2) of one pair, or +inf as soon as a Newton iterate proves
@@ -102,6 +104,57 @@ __device__ __forceinline__ float qcp_msd_bounded(const float *s, float e0, float
     }
     const float d2 = fmaxf(2.0f * (e0 - xn), 0.0f);
     return d2 < tau ? d2 : kInf;
+}
+
+// Newton refinement to convergence from a first iterate xn (previous iterate x); +inf as soon as
+// a bound exceeds tau.  Rarely executed: only pairs whose first bound is below the threshold.
+static __device__ __noinline__ float qcp_refine(QcpCoef c, float e0, float x, float xn, float tau)
+{
+    const float kInf = __uint_as_float(0x7f800000u);
+#pragma unroll 1
+    for (int it = 0; it < 24; ++it) {
+        if (fabsf(xn - x) <= 4e-7f * fabsf(xn)) break;
+        x = xn;
+        xn = qcp_newton_step(c, x);
+        if (!(xn == xn)) { xn = x; break; }
+        if (2.0f * (e0 - xn) > tau) return kInf;
+    }
+    const float d2 = fmaxf(2.0f * (e0 - xn), 0.0f);
+    return d2 < tau ? d2 : kInf;
+}
+
+// Batch form for the tensor-core epilogue: B independent pairs in straight-line code so the
+// coefficient and first-Newton chains of different pairs interleave (ILP).  sv[3a+b][j] = S_ab of pair j.
+template <int B>
+__device__ __forceinline__ void qcp_msd_batch(const float (&sv)[9][B], const float (&e0)[B], float tau, int do_fit,
+                                              float (&d2)[B])
+{
+    const float kInf = __uint_as_float(0x7f800000u);
+    if (!do_fit) {
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const float v = fmaxf(2.0f * (e0[j] - (sv[0][j] + sv[4][j] + sv[8][j])), 0.0f);
+            d2[j] = v < tau ? v : kInf;
+        }
+        return;
+    }
+    QcpCoef c[B];
+    float x1[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        const float s9[9] = {sv[0][j], sv[1][j], sv[2][j], sv[3][j], sv[4][j], sv[5][j], sv[6][j], sv[7][j], sv[8][j]};
+        c[j] = qcp_coefficients(s9);
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        float xn = qcp_newton_step(c[j], e0[j]);
+        x1[j] = (xn == xn) ? xn : e0[j];
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        if (2.0f * (e0[j] - x1[j]) > tau) d2[j] = kInf;
+        else d2[j] = qcp_refine(c[j], e0[j], e0[j], x1[j], tau);
+    }
 }
 
 }  // namespace mdsctk

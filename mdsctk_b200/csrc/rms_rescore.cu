@@ -88,24 +88,46 @@ struct RescoreArgs {
     FrameSetView fit, ref;
     long long fit_begin, n_fit;
     const double *wnorm;
-    int do_fit, k1, P;  // P = pow2 >= keep
+    int do_fit, k1, P;  // P = pow2 >= H * keep
     CandLists<float> cl;
     double eps_scale;
     float g_ref_max;
     double *out_dist;
     int *out_idx, *flags;
-    double *err_max;
+    double *err_stats;
     int *n_bad, *bad_rows;
 };
+
+// One block per fit row:
+//   0. merge the row's H candidate lists and order them by approximate key
+//   1. exact FP64 distance of the candidates in approximate order, one round (RESCORE_ROUND
+//      candidates) at a time: warps build the cross-covariances cooperatively, then one thread
+//      per candidate solves the FP64 QCP
+//   2. after each round: (distance, index) order of everything re-scored so far and the
+//      certificate.  Every pair not yet re-scored has approximate d^2 >= a_next (the next
+//      candidate's key, or the lists' admission threshold tau_row).  Write the filter error of
+//      a pair as (row-common bias) + noise with |noise| <= eps; then no such pair can beat the
+//      exact k1-th neighbour if   max approx key of the exact top-k1 + 2 eps < a_next
+//      (the bias -- fp32 accumulation truncation in the tensor core -- cancels).  eps is a
+//      model bound (eps_scale * E0), re-checked against the spread observed on the candidates.
+//      Rows that exhaust their candidates uncertified go to the exact FP64 fallback.
+constexpr int RESCORE_ROUND = 64;
 
 __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
-    const int A = a.fit.A;
+    const int A = a.fit.A, P = a.P;
     double *wq = reinterpret_cast<double *>(dsm);          // [3A]
-    double *s_d = wq + 3 * A;                              // [P] exact d^2, then distance
-    int *s_i = reinterpret_cast<int *>(s_d + a.P);         // [P]
-    __shared__ double s_err[4];
+    double *s_d = wq + 3 * A;                              // [P] sort keys
+    double *u_dist = s_d + P;                              // [P] exact distance, candidate order
+    double *s_S = u_dist + P;                              // [RESCORE_ROUND][10] cross-covariance + Gr
+    int *s_i = reinterpret_cast<int *>(s_S + RESCORE_ROUND * 10);  // [P]
+    int *u_i = s_i + P;                                    // [P] candidate reference index
+    float *u_apx = reinterpret_cast<float *>(u_i + P);     // [P] approximate d^2
+    __shared__ int s_total, s_ok;
+    __shared__ float s_taumin;
+    __shared__ unsigned s_dtil;
+    __shared__ unsigned long long s_emin, s_emax;   // order-preserving encodings of the error range
 
     const long long q = blockIdx.x;
     const long long qf = a.fit_begin + q;
@@ -113,69 +135,121 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
     const double *cen_q = a.fit.cen + 4 * qf;
     load_fit_frame(wq, a.fit.raw + (size_t)qf * A * 3, cen_q, a.wnorm, A);
     const double gq = cen_q[3];
-    const int cnt = min(a.cl.cnt[q], a.cl.keep);
-    const size_t lbase = (size_t)q * a.cl.cap;
-    for (int i = threadIdx.x; i < a.P; i += blockDim.x) {
-        s_d[i] = __longlong_as_double(0x7ff0000000000000LL);
-        s_i[i] = 0x7fffffff;
+    const double kInfD = __longlong_as_double(0x7ff0000000000000LL);
+    const float kInfF = __uint_as_float(0x7f800000u);
+    const int k1 = a.k1;
+
+    // ---- 0. gather + order by approximate key ---------------------------------------------------
+    if (threadIdx.x == 0) { s_total = 0; s_taumin = kInfF; s_ok = 0; s_emin = ~0ull; s_emax = 0ull; }
+    for (int i = threadIdx.x; i < P; i += blockDim.x) { s_d[i] = kInfD; s_i[i] = 0x7fffffff; }
+    __syncthreads();
+    for (int h = 0; h < a.cl.H; ++h) {
+        const size_t lid = (size_t)q * a.cl.H + h;
+        const int c = min(a.cl.cnt[lid], a.cl.keep);
+        if (threadIdx.x == 0) {
+            s_total += c;
+            s_taumin = fminf(s_taumin, a.cl.tau[lid]);
+        }
+        __syncthreads();
+        const int base = s_total - c;
+        for (int i = threadIdx.x; i < c; i += blockDim.x) {
+            s_d[base + i] = (double)a.cl.key[lid * a.cl.cap + i];
+            s_i[base + i] = a.cl.idx[lid * a.cl.cap + i];
+        }
+        __syncthreads();
+    }
+    const int total = s_total;
+    const float tau_row = s_taumin;
+    block_bitonic_sort(s_d, s_i, P);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        u_apx[i] = i < total ? (float)s_d[i] : kInfF;
+        u_i[i] = i < total ? s_i[i] : 0x7fffffff;
+        u_dist[i] = kInfD;
     }
     __syncthreads();
 
-    double err = 0.0;
-    for (int b = warp * 32; b < cnt; b += 4 * 32) {
-        double S[9];
-#pragma unroll
-        for (int c = 0; c < 9; ++c) S[c] = 0.0;
-        const int nb = min(32, cnt - b);
-        for (int c = 0; c < nb; ++c) {
-            const int r = a.cl.idx[lbase + b + c];
+    const double eps = a.eps_scale * 0.5 * (gq + (double)a.g_ref_max);
+    int done = 0;
+    bool certified = false;
+    while (done < total) {
+        // ---- 1. one round of exact distances ----------------------------------------------------
+        const int nb = min(RESCORE_ROUND, total - done);
+        for (int c = warp; c < nb; c += 4) {
+            const int r = u_i[done + c];
             double tot[9];
             warp_cross_cov(wq, a.ref.raw + (size_t)r * A * 3, a.ref.cen + 4 * (size_t)r, A, lane, tot);
-            if (lane == c) {
-#pragma unroll
-                for (int e = 0; e < 9; ++e) S[e] = tot[e];
-            }
+            if (lane < 9) s_S[c * 10 + lane] = tot[lane];
+            if (lane == 9) s_S[c * 10 + 9] = a.ref.cen[4 * (size_t)r + 3];
         }
-        if (lane < nb) {
-            const int r = a.cl.idx[lbase + b + lane];
-            const double e0 = 0.5 * (gq + a.ref.cen[4 * (size_t)r + 3]);
+        __syncthreads();
+        if (threadIdx.x < nb) {
+            const int c = threadIdx.x;
+            double S[9];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) S[e] = s_S[c * 10 + e];
+            const double e0 = 0.5 * (gq + s_S[c * 10 + 9]);
             const double lam = a.do_fit ? qcp_lambda_f64(S, e0) : (S[0] + S[4] + S[8]);
             const double d2 = fmax(2.0 * (e0 - lam), 0.0);
-            s_d[b + lane] = d2;
-            s_i[b + lane] = r;
-            err = fmax(err, fabs(d2 - (double)a.cl.key[lbase + b + lane]));
+            // distance exactly as distance() reports it: sqrt(msd) [nm] * 10.0 -> Angstrom
+            u_dist[done + c] = sqrt(d2) * 10.0;
+            const double err = (double)u_apx[done + c] - d2;
+            // monotone map double -> u64 so that atomicMin/Max order like the doubles
+            unsigned long long bits = (unsigned long long)__double_as_longlong(err);
+            bits = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+            atomicMin(&s_emin, bits);
+            atomicMax(&s_emax, bits);
         }
+        __syncthreads();
+        done += nb;
+        // ---- 2. order + certificate ----------------------------------------------------------------
+        for (int i = threadIdx.x; i < P; i += blockDim.x) { s_d[i] = u_dist[i]; s_i[i] = u_i[i]; }
+        if (threadIdx.x == 0) s_dtil = 0u;
+        __syncthreads();
+        block_bitonic_sort(s_d, s_i, P);
+        if (done >= k1) {
+            const double dk = s_d[k1 - 1];
+            const int ik = s_i[k1 - 1];
+            float dt = 0.0f;
+            for (int i = threadIdx.x; i < done; i += blockDim.x)
+                if (pair_less(u_dist[i], u_i[i], dk, ik) || (u_dist[i] == dk && u_i[i] == ik)) dt = fmaxf(dt, u_apx[i]);
+            atomicMax(&s_dtil, __float_as_uint(dt));  // keys are >= +0
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            auto dec = [](unsigned long long b) {
+                b = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
+                return __longlong_as_double((long long)b);
+            };
+            const double spread = dec(s_emax) - dec(s_emin);
+            const float a_next = done < total ? fminf(u_apx[done], tau_row) : tau_row;
+            bool ok = done >= k1;
+            if (ok && a_next != kInfF)  // a_next == inf: nothing was ever dropped, every pair has been re-scored
+                ok = 0.5 * spread <= eps && (double)__uint_as_float(s_dtil) + 2.0 * eps < (double)a_next;
+            s_ok = ok ? 1 : 0;
+        }
+        __syncthreads();
+        certified = s_ok != 0;
+        if (certified) break;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) err = fmax(err, __shfl_xor_sync(0xffffffffu, err, o));
-    if (lane == 0) s_err[warp] = err;
-    __syncthreads();
-    // distance exactly as distance() reports it: sqrt(msd) [nm] * 10.0 -> Angstrom
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) s_d[i] = sqrt(s_d[i]) * 10.0;
-    __syncthreads();
-    block_bitonic_sort(s_d, s_i, a.P);
+    if (total == 0 && threadIdx.x == 0) s_ok = 0;
 
-    const int k1 = a.k1;
     for (int j = threadIdx.x; j < k1; j += blockDim.x) {
         a.out_dist[(size_t)q * k1 + j] = s_d[j];
         a.out_idx[(size_t)q * k1 + j] = s_i[j];
     }
     if (threadIdx.x == 0) {
-        const double row_err = fmax(fmax(s_err[0], s_err[1]), fmax(s_err[2], s_err[3]));
-        atomic_max_nonneg(a.err_max, row_err);
-        const float tau = a.cl.tau[q];
-        bool ok;
-        if (tau == __uint_as_float(0x7f800000u)) {
-            ok = cnt >= k1;  // nothing was ever dropped: the list holds every pair
-        } else {
-            const double eps = a.eps_scale * 0.5 * (gq + (double)a.g_ref_max);
-            const double dk = s_d[k1 - 1] * 0.1;
-            // a non-candidate has approx d^2 >= tau, hence exact d^2 >= tau - eps: it cannot enter
-            // the top k1 if the exact k1-th candidate distance is below that.
-            ok = cnt >= k1 && (dk * dk + eps < (double)tau) && row_err <= eps;
+        auto dec = [](unsigned long long b) {
+            b = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
+            return __longlong_as_double((long long)b);
+        };
+        if (total > 0) {
+            const double lo = dec(s_emin), hi = dec(s_emax);
+            atomic_max_nonneg(a.err_stats + 0, fmax(fabs(lo), fabs(hi)));
+            atomic_max_nonneg(a.err_stats + 1, hi - lo);
+            atomic_max_nonneg(a.err_stats + 2, (double)done);
         }
-        a.flags[q] = ok ? 1 : 0;
-        if (!ok) {
+        a.flags[q] = certified ? 1 : 0;
+        if (!certified) {
             const int pos = atomicAdd(a.n_bad, 1);
             a.bad_rows[pos] = (int)q;
         }
@@ -185,18 +259,18 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
 cudaError_t launch_rms_rescore(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                const FrameSetView &ref, const double *wnorm, int do_fit, CandLists<float> cl, int k1,
                                double eps_scale, float g_ref_max, double *out_dist, int *out_idx, int *flags,
-                               double *err_max, int *n_bad, int *bad_rows, cudaStream_t st)
+                               double *err_stats, int *n_bad, int *bad_rows, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
     RescoreArgs a;
     a.fit = fit; a.ref = ref; a.fit_begin = fit_begin; a.n_fit = n_fit; a.wnorm = wnorm;
     a.do_fit = do_fit; a.k1 = k1; a.cl = cl; a.eps_scale = eps_scale; a.g_ref_max = g_ref_max;
-    a.out_dist = out_dist; a.out_idx = out_idx; a.flags = flags; a.err_max = err_max; a.n_bad = n_bad;
+    a.out_dist = out_dist; a.out_idx = out_idx; a.flags = flags; a.err_stats = err_stats; a.n_bad = n_bad;
     a.bad_rows = bad_rows;
     int P = 1;
-    while (P < cl.keep) P <<= 1;
+    while (P < cl.keep * cl.H) P <<= 1;
     a.P = P;
-    const size_t smem = (size_t)fit.A * 3 * 8 + (size_t)P * 12;
+    const size_t smem = (size_t)fit.A * 3 * 8 + (size_t)P * 28 + RESCORE_ROUND * 80;
     cudaError_t e = cudaFuncSetAttribute(rms_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     rms_rescore_kernel<<<(unsigned)n_fit, 128, smem, st>>>(a);

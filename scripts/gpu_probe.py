@@ -52,6 +52,8 @@ def main():
     ctx = mdsctk_b200.KnnContext(0)
     for kern in [int(x) for x in os.environ.get("PROBE_KERNELS", "0").split(",")]:
         ctx.set_option("rms_kernel", kern)
+        if os.environ.get("PROBE_SLACK"):
+            ctx.set_option("slack", int(os.environ["PROBE_SLACK"]))
         ctx.rms_set_reference(xyz, mass)
         for rep in range(3):
             t = time.time()

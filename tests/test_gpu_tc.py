@@ -1,0 +1,104 @@
+"""GPU parity tests of the tcgen05 (tensor-core) RMSD sweep: raw TMEM accumulators against a
+numpy contraction, then the same end-to-end parity bar as the FP32 kernel."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+TC_3X, TC_1X, TC_BF = 1, 2, 3
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import mdsctk_b200
+    c = mdsctk_b200.KnnContext(0)
+    yield c
+    c.close()
+
+
+def packed_planes(xyz, mass):
+    w = mass.astype(np.float64) / mass.astype(np.float64).sum()
+    x = xyz.astype(np.float64)
+    c = (x * w[None, :, None]).sum(axis=1, keepdims=True)
+    return ((x - c) * np.sqrt(w)[None, :, None]).astype(np.float32).astype(np.float64)   # [n, A, 3]
+
+
+@pytest.mark.parametrize("kern,rtol", [(TC_3X, 2e-6), (TC_1X, 2e-3), (TC_BF, 3e-5)])
+def test_tmem_accumulators_match_numpy(ctx, trpcage, kern, rtol):
+    xyz, mass = trpcage
+    xyz = xyz[:300]
+    ctx.set_option("rms_kernel", kern)
+    ctx.set_option("debug_tile", 1)
+    try:
+        ctx.rms_set_reference(xyz, mass)
+        ctx.rms_query(11)
+        tile = ctx.debug_fetch_tile()            # [128 q][3a+b][48 j]
+    finally:
+        ctx.set_option("debug_tile", 0)
+        ctx.set_option("rms_kernel", 0)
+    P = packed_planes(xyz, mass)
+    want = np.einsum("qna,jnb->qabj", P[:128], P[:48]).reshape(128, 9, 48)
+    scale = np.einsum("qna,jnb->qabj", np.abs(P[:128]), np.abs(P[:48])).reshape(128, 9, 48)
+    err = np.abs(tile - want) / scale.max()
+    assert err.max() < rtol, f"max scaled error {err.max()}"
+
+
+@pytest.mark.parametrize("kern", [TC_3X, TC_1X, TC_BF])
+@pytest.mark.parametrize("k", [10, 100])
+def test_trpcage_knn_rms_tc(ctx, trpcage, kern, k):
+    import mdsctk_b200
+    xyz, mass = trpcage
+    g = np.load(os.path.join(GOLDEN, f"trpcage_rms_k{k}.npz"))
+    dist, idx = mdsctk_b200.knn_rms(xyz, mass, k, ctx=ctx, rms_kernel=kern)
+    st = ctx.stats()
+    ctx.set_option("rms_kernel", 0)
+    assert st["rms_kernel"] == kern
+    assert np.array_equal(idx, g["idx_f64"])
+    assert (np.abs(dist - g["dist_f64"]) <= 1e-9 * g["dist_f64"]).all()
+    assert (np.abs(dist - g["dist_ref"]) <= 1e-4 * g["dist_ref"]).all()
+    if kern != TC_1X:
+        assert st["fallback_rows"] <= 2
+        assert 0.5 * st["max_filter_spread"] < st["cert_eps"]
+
+
+@pytest.mark.parametrize("kern", [TC_3X, TC_1X, TC_BF])
+def test_synthetic_300_atoms_tc(ctx, kern):
+    import mdsctk_b200
+    from mdsctk_b200 import synth
+    from oracle import binding as ob
+    n = 5000
+    xyz = synth.traj_frames(n, 300, 16)
+    mass = synth.traj_masses(300)
+    dist, idx = mdsctk_b200.knn_rms(xyz, mass, 32, ctx=ctx, rms_kernel=kern)
+    st = ctx.stats()
+    ctx.set_option("rms_kernel", 0)
+    d, i = ob.knn_rms(xyz, mass, 32, fit=xyz[:256], mode=1)
+    assert np.array_equal(idx[:256], i)
+    assert (np.abs(dist[:256] - d) <= 1e-9 * d).all()
+    assert (np.diff(dist, axis=1) >= 0).all() and (idx != np.arange(n)[:, None]).all()
+    # both kernels must agree on every row (the FP64 stage decides, the sweep only filters)
+    dist0, idx0 = mdsctk_b200.knn_rms(xyz, mass, 32, ctx=ctx, rms_kernel=0)
+    assert np.array_equal(idx, idx0) and np.array_equal(dist, dist0)
+    print("tc kernel", kern, {k: st[k] for k in ("ms_sweep", "fallback_rows", "max_filter_err", "max_filter_spread", "cert_eps", "k_keep", "lists_per_row")})
+
+
+def test_ragged_and_out_of_sample_tc(ctx, trpcage):
+    import mdsctk_b200
+    from oracle import binding as ob
+    xyz, mass = trpcage
+    for n in (7, 49, 129, 200):
+        dist, idx = mdsctk_b200.knn_rms(xyz[:n], mass, 5, ctx=ctx, rms_kernel=TC_BF)
+        d, i = ob.knn_rms(xyz[:n], mass, min(5, n - 1), mode=1)
+        assert np.array_equal(idx, i), n
+    g = np.load(os.path.join(GOLDEN, "trpcage_rms_oos_k10.npz"))
+    fit, ref = xyz[::10], np.delete(xyz, np.arange(0, 1000, 10), axis=0)
+    dist, idx = mdsctk_b200.knn_rms(ref, mass, 10, fit_xyz=fit, ctx=ctx, rms_kernel=TC_3X)
+    assert np.array_equal(idx, g["idx_f64"])
+    g = np.load(os.path.join(GOLDEN, "trpcage_rms_nofit_k10.npz"))
+    dist, idx = mdsctk_b200.knn_rms(xyz, mass, 10, nofit=True, ctx=ctx, rms_kernel=TC_3X)
+    ctx.set_option("rms_kernel", 0)
+    assert np.array_equal(idx, g["idx_f64"])

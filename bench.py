@@ -177,7 +177,7 @@ def main():
     import torch
     import torch.distributed as dist
     import mdsctk_b200
-    from mdsctk_b200 import synth
+    from mdsctk_b200 import sharding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,9 +198,7 @@ def main():
         ctx.set_option("rms_kernel", args.rms_kernel)
 
     # ---- this rank's frames (pinned host memory) ---------------------------------------------
-    shard = (n_total + world - 1) // world
-    begin = min(rank * shard, n_total)
-    count = min(shard, n_total - begin)
+    begin, count = sharding.shard_range(n_total, world, rank)
     host = torch.empty((count, ATOMS, 3), dtype=torch.float32).pin_memory()
     synth.traj_frames(n_total, ATOMS, wl["basins"], wl["seed"], begin, count, out=host.numpy())
 
@@ -215,13 +213,7 @@ def main():
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for t, b in zip(tens, bpf):
-            if n_total % world == 0:
-                dist.all_gather_into_tensor(t, t[begin * b:(begin + count) * b].clone())
-            else:  # ragged last shard: broadcast shard by shard
-                for r in range(world):
-                    rb, rc = min(r * shard, n_total), min(shard, n_total - min(r * shard, n_total))
-                    dist.broadcast(t[rb * b:(rb + rc) * b], src=r)
+        sharding.replicate_frame_major(tens, bpf, n_total, world, rank, dist)
         e1.record()
         torch.cuda.synchronize()
         allgather_ms = e0.elapsed_time(e1)
@@ -231,8 +223,7 @@ def main():
         fit_range = lambda s: (begin, count)
     else:
         rows = min(wl["rows_per_rank"], count)
-        nblk = max(1, count // rows)
-        fit_range = lambda s: (begin + (s % nblk) * rows, rows)
+        fit_range = lambda s: sharding.step_rows(begin, count, wl["rows_per_rank"], s)
 
     def barrier():
         torch.cuda.synchronize()

@@ -118,7 +118,7 @@ def cpu_baseline_sample(wl, rows=None):
     reference set sized for ~10-30 s; per-pair cost does not depend on either count."""
     from oracle import binding as ob
     from mdsctk_b200 import synth
-    threads = ob.max_threads()
+    threads = os.cpu_count() or ob.max_threads()   # torchrun exports OMP_NUM_THREADS=1; use every host core
     n_ref = min(wl["n_total"], 20_000)
     rows = rows or 32 * threads
     xyz = synth.traj_frames(wl["n_total"], ATOMS, wl["basins"], wl["seed"], 0, n_ref)
@@ -141,7 +141,7 @@ def run_reference(args):
     wl = workload(args.gpus)
     from oracle import binding as ob
     from mdsctk_b200 import synth
-    threads = ob.max_threads()
+    threads = os.cpu_count() or ob.max_threads()   # torchrun exports OMP_NUM_THREADS=1; use every host core
     n_ref = min(wl["n_total"], 20_000)
     rows = 8 * threads
     xyz = synth.traj_frames(wl["n_total"], ATOMS, wl["basins"], wl["seed"], 0, n_ref)
@@ -231,12 +231,14 @@ def main():
             dist.barrier()
 
     # ---- device-resident timing: W warm-up + K timed steps -------------------------------------
-    for s in range(args.warmup):
-        ctx.rms_query(k1, fit_range=fit_range(s), fetch=False)
-    barrier()
+    # the clock sampler (nvidia-smi, 200 ms period) starts before the warm-up so that short timed
+    # regions still get samples under load; it is stopped right after the timed steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for s in range(args.warmup):
+        ctx.rms_query(k1, fit_range=fit_range(s), fetch=False)
+    barrier()
     sweep_ms = rescore_ms = fallback_ms = 0.0
     launches = fallback_rows = 0
     err = 0.0

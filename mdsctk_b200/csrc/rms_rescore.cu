@@ -159,9 +159,11 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
         __syncthreads();
     }
     const int total = s_total;
+    int Pr = 32;                       // this row's working size: the lists are mostly short
+    while (Pr < total) Pr <<= 1;
     const float tau_row = s_taumin;
-    block_bitonic_sort(s_d, s_i, P);
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    block_bitonic_sort(s_d, s_i, Pr);
+    for (int i = threadIdx.x; i < Pr; i += blockDim.x) {
         u_apx[i] = i < total ? (float)s_d[i] : kInfF;
         u_i[i] = i < total ? s_i[i] : 0x7fffffff;
         u_dist[i] = kInfD;
@@ -202,10 +204,10 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
         __syncthreads();
         done += nb;
         // ---- 2. order + certificate ----------------------------------------------------------------
-        for (int i = threadIdx.x; i < P; i += blockDim.x) { s_d[i] = u_dist[i]; s_i[i] = u_i[i]; }
+        for (int i = threadIdx.x; i < Pr; i += blockDim.x) { s_d[i] = u_dist[i]; s_i[i] = u_i[i]; }
         if (threadIdx.x == 0) s_dtil = 0u;
         __syncthreads();
-        block_bitonic_sort(s_d, s_i, P);
+        block_bitonic_sort(s_d, s_i, Pr);
         if (done >= k1) {
             const double dk = s_d[k1 - 1];
             const int ik = s_i[k1 - 1];

@@ -231,6 +231,8 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
     int keep, cap;
     const bool use_tc = ctx->rms_kernel != MDSCTK_KNN_RMS_SIMT_FP32;
     choose_lists(ctx, k1, !use_tc, &keep, &cap);
+    // tensor-core sweep: four private sub-lists per (row, segment), merged into one at the end of the segment
+    if (use_tc) cap = rms_tc_list_stride(keep);
     const int n_seg = use_tc ? rms_tc_choose_segments(n_fit, ref.n, ctx->n_sms) : 1;
     const int H = use_tc ? rms_tc_lists_per_segment() * n_seg : 1;
     S.k_keep = keep;

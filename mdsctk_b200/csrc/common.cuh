@@ -62,6 +62,7 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
                                 float *debug_tile, int n_sms, cudaStream_t st);
 int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms);
 int rms_tc_lists_per_segment();
+int rms_tc_list_stride(int keep);
 
 // FP64 re-score of the kept candidates, final (distance, index) sort, certificate.
 //   out_dist [n_fit][k1] (Angstrom), out_idx [n_fit][k1], flags[n_fit] (1 = certified),

@@ -19,17 +19,24 @@ struct QcpCoef {
     float c2, c1, c0;
 };
 
-// s[3*a+b] = S_ab
-__device__ __forceinline__ QcpCoef qcp_coefficients(const float *s)
+// |S|_F^2 of pair j of a batch (sv[3a+b][j] = S_ab).  lambda_max <= sqrt(3 |S|_F^2) (the four
+// eigenvalues of K sum to 0 and their squares to 4 |S|_F^2), the cheapest lower bound on RMSD^2.
+template <int B>
+__device__ __forceinline__ float qcp_frob2(const float (&sv)[9][B], int j)
+{
+    float f = sv[0][j] * sv[0][j];
+#pragma unroll
+    for (int c = 1; c < 9; ++c) f = fmaf(sv[c][j], sv[c][j], f);
+    return f;
+}
+
+// s[3*a+b] = S_ab, f = |S|_F^2
+__device__ __forceinline__ QcpCoef qcp_coefficients(const float *s, float f)
 {
     const float sxx = s[0], sxy = s[1], sxz = s[2];
     const float syx = s[3], syy = s[4], syz = s[5];
     const float szx = s[6], szy = s[7], szz = s[8];
     QcpCoef c;
-    float f = sxx * sxx;
-    f = fmaf(sxy, sxy, f); f = fmaf(sxz, sxz, f);
-    f = fmaf(syx, syx, f); f = fmaf(syy, syy, f); f = fmaf(syz, syz, f);
-    f = fmaf(szx, szx, f); f = fmaf(szy, szy, f); f = fmaf(szz, szz, f);
     c.c2 = -2.0f * f;
     // det S by cofactors of the first row
     const float m0 = fmaf(syy, szz, -syz * szy);
@@ -65,6 +72,14 @@ __device__ __forceinline__ QcpCoef qcp_coefficients(const float *s)
     d = fmaf(a5, b0, d);
     c.c0 = d;
     return c;
+}
+
+__device__ __forceinline__ QcpCoef qcp_coefficients(const float *s)
+{
+    float f = s[0] * s[0];
+#pragma unroll
+    for (int c = 1; c < 9; ++c) f = fmaf(s[c], s[c], f);
+    return qcp_coefficients(s, f);
 }
 
 // One Newton step on P from x; returns the new iterate.

@@ -54,6 +54,8 @@ constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;   // + alignment slack
 constexpr int SUBW = TR / SUBS;               // 12 reference columns per epilogue warp
 constexpr int EB = 4;                         // pairs per epilogue batch
+constexpr int MERGE_EVERY = 4;                // passes between quarter-wide list merges (power of two)
+constexpr int SUB_APP = 2 * MERGE_EVERY * SUBW;   // 96: private append area per epilogue warp and row
 }  // namespace tc
 
 // ---------------------------------------------------------------- PTX wrappers ----
@@ -206,8 +208,9 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_tmem_full, bar_tmem_empty;
     __shared__ uint32_t s_tmem_base;
     __shared__ unsigned s_hist[EPI_WARPS][256];
-    __shared__ int s_cnt[TQ];
+    __shared__ int s_cnt[EPI_WARPS][32];
     __shared__ float s_tau[TQ];
+    __shared__ int s_mcnt[TQ];
 
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -316,49 +319,146 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         }
     } else {
         // =============================== epilogue ===================================
+        // List of a (fit row, reference segment): [0, keep) merged candidates, then one private append
+        // area of SUB_APP entries per epilogue warp of the lane quarter (cursor in the warp's own
+        // shared-memory slot), so the pass loop needs no barrier.  Every MERGE_EVERY passes the four
+        // warps of a quarter meet; rows with a filling append area are merged, reduced to the `keep`
+        // smallest by radix select and their admission threshold s_tau is lowered.  Pairs that
+        // survive the straight-line filter are queued per warp and refined with all lanes busy.
         const int ew = warp - 2;                      // 0..15
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
         const int sub = ew >> 2;                      // which 12 reference columns of every tile
+        const int e_of_quarter = (quarter + 2) & 3;   // ew = sub * 4 + e_of_quarter
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        unsigned *hist = s_hist[ew];
+        const unsigned lt_mask = (1u << lane) - 1u;
+        unsigned *hist = s_hist[ew];                  // radix histogram during merges, refine queue otherwise
+        float *q_c2 = reinterpret_cast<float *>(hist), *q_c1 = q_c2 + 32, *q_c0 = q_c2 + 64, *q_e0 = q_c2 + 96,
+              *q_x = q_c2 + 128;
+        int *q_ref = reinterpret_cast<int *>(hist) + 160, *q_own = reinterpret_cast<int *>(hist) + 192;
+        int *wcnt = s_cnt[ew];                        // fill of this warp's append area of row (quarter*32 + l)
+        const size_t row_stride = (size_t)a.cl.H * a.cl.cap;
         uint32_t tph = 0;
-        // The four warps of a quarter share one candidate list per fit row (cursor and threshold in
-        // shared memory).  Rows [duty0, duty0+8) of the quarter are compacted by this warp.
-        const int duty0 = quarter * 32 + sub * 8;
-        auto compact_duty_rows = [&](long long qt, int seg, int limit) {
-            for (int r = duty0; r < duty0 + 8; ++r) {
-                const int c = min(s_cnt[r], a.cl.cap);
-                const long long qrow = qt * TQ + r;
-                if (c > limit && qrow < a.n_q) {
-                    const size_t l = ((size_t)qrow * a.cl.H + seg) * a.cl.cap;
-                    const float nt = warp_compact_list<float>(a.cl.key + l, a.cl.idx + l, c, a.cl.keep, hist);
-                    if (lane == 0) { s_tau[r] = fminf(s_tau[r], nt); s_cnt[r] = a.cl.keep; }
+        int qn = 0;                                   // queue fill (warp-uniform)
+        size_t lbase0 = 0;                            // list of the quarter's row 0 in the current item
+        float *lkeys = a.cl.key;
+        int *lidxs = a.cl.idx;
+
+        auto drain = [&]() {
+            __syncwarp();
+            if (lane < qn) {
+                const int own = q_own[lane];
+                const int l = own & 31;
+                const float e0 = q_e0[lane], x1 = q_x[lane];
+                const float tau_r = *reinterpret_cast<volatile float *>(&s_tau[quarter * 32 + l]);
+                float d2;
+                if (own & 32) {                       // --nofit: already final
+                    d2 = fmaxf(2.0f * (e0 - x1), 0.0f);
+                } else {
+                    QcpCoef c; c.c2 = q_c2[lane]; c.c1 = q_c1[lane]; c.c0 = q_c0[lane];
+                    d2 = qcp_refine(c, e0, e0, x1, tau_r);
+                }
+                if (d2 < tau_r) {
+                    const int pos = atomicAdd(&wcnt[l], 1);
+                    if (pos < SUB_APP) {
+                        const size_t at = lbase0 + (size_t)l * row_stride + a.cl.keep + sub * SUB_APP + pos;
+                        lkeys[at] = d2;
+                        lidxs[at] = q_ref[lane];
+                    }
                 }
             }
+            qn = 0;
+            __syncwarp();
         };
+        auto push = [&](bool pred, float c2, float c1, float c0, float e0, float x1, int ridx, int own) {
+            const unsigned m = __ballot_sync(0xffffffffu, pred);
+            if (!m) return;
+            const int n = __popc(m);
+            if (qn + n > 32) drain();
+            if (pred) {
+                const int p = qn + __popc(m & lt_mask);
+                q_c2[p] = c2; q_c1[p] = c1; q_c0[p] = c0; q_e0[p] = e0; q_x[p] = x1; q_ref[p] = ridx; q_own[p] = own;
+            }
+            qn += n;
+        };
+        // Quarter-wide merge of the rows this warp is responsible for (8 per warp).  final: every row.
+        auto merge_rows = [&](long long qt, int seg, bool final) {
+            quarter_sync(quarter);
+            for (int r8 = 0; r8 < 8; ++r8) {
+                const int l = sub * 8 + r8;
+                const int row = quarter * 32 + l;
+                const long long qr = qt * TQ + row;
+                if (qr >= a.n_q) break;
+                int cs[SUBS], cmax = 0;
+#pragma unroll
+                for (int s2 = 0; s2 < SUBS; ++s2) {
+                    cs[s2] = min(s_cnt[s2 * 4 + e_of_quarter][l], SUB_APP);
+                    cmax = max(cmax, cs[s2]);
+                }
+                if (!final && cmax < SUB_APP - MERGE_EVERY * SUBW) continue;   // cannot overflow before the next merge
+                const size_t at = lbase0 + (size_t)l * row_stride;
+                int total = s_mcnt[row];
+#pragma unroll
+                for (int s2 = 0; s2 < SUBS; ++s2) {
+                    const size_t src = at + a.cl.keep + s2 * SUB_APP;
+                    for (int base = 0; base < cs[s2]; base += 32) {    // dest <= src: forward move is safe
+                        const int i = base + lane;
+                        float kv = 0.f; int iv = 0;
+                        if (i < cs[s2]) { kv = lkeys[src + i]; iv = lidxs[src + i]; }
+                        __syncwarp();
+                        if (i < cs[s2]) { lkeys[at + total + i] = kv; lidxs[at + total + i] = iv; }
+                        __syncwarp();
+                    }
+                    total += cs[s2];
+                }
+                float tl = s_tau[row];
+                if (total > a.cl.keep) {
+                    tl = fminf(tl, warp_compact_list<float>(lkeys + at, lidxs + at, total, a.cl.keep, hist));
+                    total = a.cl.keep;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    s_tau[row] = tl;
+                    s_mcnt[row] = total;
+#pragma unroll
+                    for (int s2 = 0; s2 < SUBS; ++s2) s_cnt[s2 * 4 + e_of_quarter][l] = 0;
+                    if (final) {
+                        const size_t lid = (size_t)qr * a.cl.H + seg;
+                        a.cl.cnt[lid] = total;
+                        a.cl.tau[lid] = tl;
+                        atomicMin(reinterpret_cast<unsigned *>(a.row_tau + qr), __float_as_uint(tl));  // tau >= +0
+                    }
+                }
+            }
+            quarter_sync(quarter);
+        };
+
         for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
             long long qt, rt0, rt1; int seg;
             item_range(it, qt, rt0, rt1, seg);
             const long long qrow = qt * TQ + row_in_tile;        // row within the query range
             const bool qvalid = qrow < a.n_q;
             const float hgq = 0.5f * a.q_G[a.q_begin + (qvalid ? qrow : a.n_q - 1)];
-            const size_t lid = (size_t)(qvalid ? qrow : 0) * a.cl.H + seg;
-            float *lkey = a.cl.key + lid * a.cl.cap;
-            int *lidx = a.cl.idx + lid * a.cl.cap;
+            lbase0 = ((size_t)(qt * TQ + quarter * 32) * a.cl.H + seg) * a.cl.cap;
+            wcnt[lane] = 0;
             if (sub == 0) {
-                s_cnt[row_in_tile] = 0;
+                s_mcnt[row_in_tile] = 0;
                 // admission threshold carried over from segments of this row that already finished
                 s_tau[row_in_tile] = qvalid ? __ldcg(a.row_tau + qrow) : 0.0f;
             }
+            quarter_sync(quarter);
             for (long long rt = rt0; rt < rt1; ++rt) {
                 const long long r0 = rt * TR + sub * SUBW;
+                float4 gv[SUBW / EB];
+#pragma unroll
+                for (int jb = 0; jb < SUBW / EB; ++jb) gv[jb] = __ldg(reinterpret_cast<const float4 *>(a.r_G + r0) + jb);
                 if (lane == 0) mbar_wait(&bar_tmem_full, tph, 4);
                 tph ^= 1;
-                quarter_sync(quarter);                // also publishes s_tau / s_cnt of the last compaction
+                __syncwarp();
                 tc_fence_after();
-                const float tau = s_tau[row_in_tile];
-#pragma unroll 1
+                const float tau = *reinterpret_cast<volatile float *>(&s_tau[row_in_tile]);
+                const float htau = 0.5f * tau;
+#pragma unroll
                 for (int jb = 0; jb < SUBW / EB; ++jb) {
                     float sv[9][EB];
 #pragma unroll
@@ -379,45 +479,62 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                             for (int j = 0; j < EB; ++j)
                                 a.debug_tile[(size_t)row_in_tile * (9 * TR) + c * TR + sub * SUBW + jb * EB + j] = sv[c][j];
                     }
-                    const float4 g = __ldg(reinterpret_cast<const float4 *>(a.r_G + r0 + jb * EB));
+                    const float4 g = gv[jb];
                     const float e0[EB] = {fmaf(0.5f, g.x, hgq), fmaf(0.5f, g.y, hgq), fmaf(0.5f, g.z, hgq),
                                           fmaf(0.5f, g.w, hgq)};
-                    float d2[EB];
+                    const long long rb = r0 + jb * EB;
                     if (a.dbg & 1) {
+                        float acc = 0.f;
 #pragma unroll
-                        for (int j = 0; j < EB; ++j) d2[j] = sv[0][j] + sv[4][j] + sv[8][j] + e0[j] == 12345.f ? 0.f : KeyBits<float>::inf();
-                    } else {
-                        qcp_msd_batch<EB>(sv, e0, tau, a.do_fit, d2);
+                        for (int j = 0; j < EB; ++j) acc += sv[0][j] + sv[4][j] + sv[8][j] + e0[j];
+                        if (acc == 12345.f) wcnt[lane] = 1;
+                        continue;
                     }
-                    if (fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3])) < tau && qvalid) {
+                    if (!a.do_fit) {                  // --nofit: lambda = trace S
 #pragma unroll
                         for (int j = 0; j < EB; ++j) {
-                            const long long ridx = r0 + jb * EB + j;
-                            if (d2[j] < tau && ridx < a.n_r) {
-                                const int pos = atomicAdd(&s_cnt[row_in_tile], 1);
-                                if (pos < a.cl.cap) { lkey[pos] = d2[j]; lidx[pos] = (int)ridx; }
-                            }
+                            const float tr = sv[0][j] + sv[4][j] + sv[8][j];
+                            push(qvalid && rb + j < a.n_r && 2.0f * (e0[j] - tr) < tau, 0.f, 0.f, 0.f, e0[j], tr,
+                                 (int)(rb + j), lane | 32);
                         }
+                        continue;
                     }
+                    // (1) cheap bound: lambda_max <= sqrt(3) |S|_F, so RMSD^2 >= 2 (E0 - sqrt(3 F)).  Far
+                    //     pairs (other conformational basins) are rejected for 9 FMAs; a batch whose
+                    //     128 pairs are all far skips the characteristic polynomial altogether.
+                    float f[EB];
+                    bool far = true;
+#pragma unroll
+                    for (int j = 0; j < EB; ++j) {
+                        f[j] = qcp_frob2(sv, j);
+                        const float t = e0[j] - htau;
+                        far = far && (t > 0.0f) && (3.0001f * f[j] < t * t);
+                    }
+                    if (!(a.dbg & 8) && __all_sync(0xffffffffu, far)) continue;
+                    // (2) QCP coefficients + one Newton step from E0: a valid lower bound on RMSD^2
+                    QcpCoef c[EB];
+                    float x1[EB];
+#pragma unroll
+                    for (int j = 0; j < EB; ++j) {
+                        const float s9[9] = {sv[0][j], sv[1][j], sv[2][j], sv[3][j], sv[4][j], sv[5][j], sv[6][j], sv[7][j], sv[8][j]};
+                        c[j] = qcp_coefficients(s9, f[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < EB; ++j) {
+                        const float xn = qcp_newton_step(c[j], e0[j]);
+                        x1[j] = (xn == xn) ? xn : e0[j];
+                    }
+                    // (3) survivors go to the warp's refine queue
+#pragma unroll
+                    for (int j = 0; j < EB; ++j)
+                        push(qvalid && rb + j < a.n_r && !(2.0f * (e0[j] - x1[j]) > tau), c[j].c2, c[j].c1, c[j].c0, e0[j],
+                             x1[j], (int)(rb + j), lane);
                 }
-                // lists that could overflow during the next pass (at most TR appends per row and pass)
-                quarter_sync(quarter);
-                compact_duty_rows(qt, seg, a.cl.cap - TR);
+                drain();
+                // an append area takes at most SUBW entries per pass
+                if ((((rt - rt0) & (MERGE_EVERY - 1)) == MERGE_EVERY - 1) && rt + 1 < rt1) merge_rows(qt, seg, false);
             }
-            quarter_sync(quarter);
-            compact_duty_rows(qt, seg, a.cl.keep);   // leave at most `keep` candidates per list
-            __syncwarp();
-            if (lane < 8) {
-                const int r = duty0 + lane;
-                const long long qr = qt * TQ + r;
-                if (qr < a.n_q) {
-                    const size_t l = (size_t)qr * a.cl.H + seg;
-                    a.cl.cnt[l] = min(s_cnt[r], a.cl.keep);
-                    a.cl.tau[l] = s_tau[r];
-                    atomicMin(reinterpret_cast<unsigned *>(a.row_tau + qr), __float_as_uint(s_tau[r]));  // tau >= +0
-                }
-            }
-            quarter_sync(quarter);                    // s_cnt / s_tau are re-initialised by the next item
+            merge_rows(qt, seg, true);                // leaves one list of <= keep candidates per row
         }
     }
 
@@ -483,6 +600,9 @@ int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms)
 }
 
 int rms_tc_lists_per_segment() { return 1; }
+
+// Entries reserved per (fit row, reference segment): keep merged + one append area per epilogue warp.
+int rms_tc_list_stride(int keep) { return (keep + tc::SUBS * tc::SUB_APP + 31) / 32 * 32; }
 
 cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *fit_hi, const void *fit_lo,
                                 long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,

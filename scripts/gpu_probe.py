@@ -47,7 +47,7 @@ def main():
     from mdsctk_b200 import synth
     res = {"gpu": torch.cuda.get_device_name(0), "host_cores": os.cpu_count(), "sms": torch.cuda.get_device_properties(0).multi_processor_count}
     n = int(os.environ.get("PROBE_N", "20000"))
-    xyz = synth.traj_frames(n, 300, 16)
+    xyz = synth.traj_frames(n, 300, int(os.environ.get("PROBE_BASINS", "16")))
     mass = synth.traj_masses(300)
     ctx = mdsctk_b200.KnnContext(0)
     for kern in [int(x) for x in os.environ.get("PROBE_KERNELS", "0").split(",")]:

@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
     "-ccbin", "/usr/bin/g++",
-]
+] + os.environ.get("MDSCTK_NVCC_FLAGS", "").split()
 
 
 def _newer(target, sources):

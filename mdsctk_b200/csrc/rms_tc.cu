@@ -3,27 +3,30 @@
 // Same job as rms_simt.cu (the row blocks of knn_rms.cpp:231-293) with the nine per-pair dot
 // products S_ab = sum_n x_na y_nb issued as a batched dense contraction:
 //
-//   work item    (fit tile of 128 frames, reference segment); persistent CTAs, one per SM.
-//   CTA tile     128 fit frames (M) x 48 reference frames per accumulator pass.
+//   work item    (fit super-tile of 256 frames, reference segment), taken by a CTA PAIR (cluster of 2,
+//                tcgen05 cta_group::2); persistent, one CTA per SM.  CTA r of the pair owns fit rows
+//                [128 r, 128 r + 128) of the super-tile and loads HALF of every reference tile; the
+//                pair's MMA (M = 256) reads the other half from the peer's shared memory, which is
+//                what keeps a single SM's shared-memory read bandwidth from capping the tensor pipe
+//                (measured: one-SM M=128 MMAs with both operands in shared memory run at ~82 B/clk of
+//                operand reads, i.e. 104 instead of 72 clk for N=144).
+//   pass         256 fit frames x 48 reference frames.
 //   operands     K-major tiles staged by TMA (cp.async.bulk.tensor.3d, SWIZZLE_64B, 64-byte rows)
-//                from the frames x 3 x atoms SoA planes through a 3-stage mbarrier ring.
-//                A_p = plane p (x|y|z) of the 128 fit frames, B = [x | y | z] planes of the 48
-//                reference frames (144 rows).
-//   MMA          tcgen05.mma.cta_group::1, M=128 N=144, issued by one elected thread.
+//                from the frames x 3 x atoms SoA planes through a 3-stage mbarrier ring; both CTAs'
+//                copies complete on the leader's "full" barrier.
+//                A_p = plane p (x|y|z) of the fit frames; B = [x|y|z of refs 0-23 | x|y|z of refs 24-47]
+//                (144 rows, the first 72 in CTA 0, the last 72 in CTA 1).
+//   MMA          tcgen05.mma.cta_group::2, M=256 N=144, issued by one elected lane of the leader CTA.
 //                Precision recovery by operand splitting (the pack kernel writes both parts):
 //                  3xBF16: x ~= h + m (bf16), D += Ah*Bh + Ah*Bm + Am*Bh   kind::f16,  K=16, 32 atoms/stage
 //                  3xTF32: x ~= h + l (tf32), D += Ah*Bh + Ah*Bl + Al*Bh   kind::tf32, K=8,  16 atoms/stage
 //                  1xTF32: D += Ah*Bh only (coarse filter).
-//   accumulators TMEM, 3 regions of 144 fp32 columns: D_p[lane q][b*48 + j] = S_pb(q, ref j).
-//                TMEM lane = fit frame: an epilogue thread reads the nine S values of ITS fit row
-//                with tcgen05.ld (no shuffles), solves QCP in registers (qcp.cuh) and appends the
-//                survivors to the row's list; cursor and threshold live in shared memory
-//                (select.cuh), thresholds are carried across reference segments through HBM.
+//   accumulators TMEM of each CTA: its 128 fit rows x 3 regions of 144 fp32 columns (432 of 512);
+//                TMEM lane = fit frame, so an epilogue thread reads the nine S values of ITS fit row
+//                with tcgen05.ld (no shuffles), bounds RMSD^2 from below (Frobenius bound, then QCP
+//                coefficients + one Newton step, qcp.cuh) and queues the survivors.
 //   roles        warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-17 epilogue
-//                (four warps per TMEM lane quarter, 12 of the 48 reference columns each; the QCP
-//                chains are latency-bound, so the epilogue is spread over many warps).
-// The accumulators are single-buffered (432 of 512 TMEM columns): the MMA of the next pass starts
-// when the epilogue has READ the previous accumulators, and runs under the epilogue's arithmetic.
+//                (four warps per TMEM lane quarter, 12 of the 48 reference columns each).
 #include "common.cuh"
 #include "qcp.cuh"
 #include "select.cuh"
@@ -32,28 +35,35 @@
 #include <cstdio>
 #include <cstdlib>
 
+#ifndef MDSCTK_TC_PROF_BUILD
+#define MDSCTK_TC_PROF_BUILD 0        // 1: compile the clock counters read by MDSCTK_TC_PROF=1 (costs registers)
+#endif
+
 namespace mdsctk {
 
 namespace tc {
-constexpr int TQ = 128;
-constexpr int TR = 48;
+constexpr int TQ = 128;                       // fit frames per CTA
+constexpr int TR = 48;                        // reference frames per pass (24 loaded by each CTA)
+constexpr int TRH = TR / 2;
 constexpr int NST = 3;
 constexpr int ROW_BYTES = 64;                 // one operand row per stage (SWIZZLE_64B)
-constexpr int A_TILE = TQ * ROW_BYTES;        // 8192 B : one plane of the fit tile
-constexpr int B_TILE = TR * ROW_BYTES;        // 3072 B : one plane of the reference tile
+constexpr int UMMA_M = 2 * TQ;                // 256 across the pair
+constexpr int UMMA_N = 3 * TR;                // 144
+constexpr int A_TILE = TQ * ROW_BYTES;        // 8192 B : one plane of the CTA's fit tile
+constexpr int A_PART = 3 * A_TILE;            // 24576 B: x|y|z planes of one split part
+constexpr int B_PART = 3 * TRH * ROW_BYTES;   // 4608 B : this CTA's 72 of the 144 reference operand rows
 constexpr int OFF_AHI = 0;
-constexpr int OFF_ALO = 3 * A_TILE;
-constexpr int OFF_BHI = 6 * A_TILE;
-constexpr int OFF_BLO = 6 * A_TILE + 3 * B_TILE;
-constexpr int STAGE_BYTES = 6 * A_TILE + 6 * B_TILE;   // 67584
+constexpr int OFF_ALO = A_PART;
+constexpr int OFF_BHI = 2 * A_PART;
+constexpr int OFF_BLO = 2 * A_PART + B_PART;
+constexpr int STAGE_BYTES = 2 * A_PART + 2 * B_PART;   // 58368
 constexpr int SUBS = 4;                       // epilogue warps per TMEM lane quarter
 constexpr int EPI_WARPS = 4 * SUBS;           // 16
 constexpr int NTHR = 64 + EPI_WARPS * 32;     // 576
-constexpr int UMMA_N = 3 * TR;                // 144
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;   // + alignment slack
 constexpr int SUBW = TR / SUBS;               // 12 reference columns per epilogue warp
-constexpr int EB = 4;                         // pairs per epilogue batch
+constexpr int EB = 4;                         // pairs per lane and epilogue batch
 constexpr int MERGE_EVERY = 4;                // passes between quarter-wide list merges (power of two)
 constexpr int SUB_APP = 2 * MERGE_EVERY * SUBW;   // 96: private append area per epilogue warp and row
 }  // namespace tc
@@ -100,7 +110,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int ta
             : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) return;
-        if (++polls > 4000000u) {
+        if (++polls > 400000u) {
             printf("rms_sweep_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x,
                    parity);
             __trap();
@@ -118,6 +128,51 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// CTA-pair copy: lands in THIS CTA's shared memory, completes on the mbarrier `bar_cluster_addr`
+// (a shared::cluster address; the leader's "full" barrier for both CTAs of the pair).
+__device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1,
+                                                int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// one lane of a converged warp (the others fall through); keeps the operands of the guarded
+// instruction in uniform registers instead of a per-lane "waterfall" loop
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
@@ -125,43 +180,42 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// pair MMA bookkeeping: arrives on the mbarrier at the same offset in every CTA of `mask` once the
+// cta_group::2 MMAs issued so far are done
+__device__ __forceinline__ void tc_commit2_mc(uint64_t *bar, uint16_t mask)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+// D[256 x N] (+)= A[256 x K] * B[N x K]^T over the CTA pair; descriptors are shared-memory offsets
+// valid in both CTAs, d_tmem likewise
 template <bool BF16>
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
 {
     if constexpr (BF16) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
             : "memory");
     } else {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
             : "memory");
     }
 }
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[9][8], int c)
-{
-    uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
-                 : "r"(taddr));
-    v[c][0] = __uint_as_float(r0); v[c][1] = __uint_as_float(r1); v[c][2] = __uint_as_float(r2);
-    v[c][3] = __uint_as_float(r3); v[c][4] = __uint_as_float(r4); v[c][5] = __uint_as_float(r5);
-    v[c][6] = __uint_as_float(r6); v[c][7] = __uint_as_float(r7);
-}
+// four consecutive accumulator columns of this thread's TMEM lane -> v[c][0..3] (valid after tc_wait_ld)
 __device__ __forceinline__ void tc_ld4(uint32_t taddr, float (&v)[9][4], int c)
 {
-    uint32_t r0, r1, r2, r3;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "=f"(v[c][0]), "=f"(v[c][1]), "=f"(v[c][2]), "=f"(v[c][3])
                  : "r"(taddr));
-    v[c][0] = __uint_as_float(r0); v[c][1] = __uint_as_float(r1); v[c][2] = __uint_as_float(r2);
-    v[c][3] = __uint_as_float(r3);
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -183,13 +237,14 @@ struct TcArgs {
     const float *q_G, *r_G;
     long long q_begin, n_q, n_r;
     int A_pad, do_fit, n_seg;
-    CandLists<float> cl;
+    CandLists<float> cl;        // H = n_seg lists per fit row
     float *debug_tile;          // optional [128][9][48]: raw accumulators of (fit tile 0, ref tile 0)
     float *row_tau;             // [n_q] running admission threshold per fit row (+inf before the first segment)
-    int dbg;                    // MDSCTK_TC_DEBUG bits: 1 skip QCP, 2 skip MMA issue, 4 skip TMA (timing experiments)
+    int dbg;                    // MDSCTK_TC_DEBUG bits: 1 skip QCP, 2 skip MMA issue, 4 skip TMA, 8 no cheap bound
+    long long *prof;            // MDSCTK_TC_PROF=1: [grid][8] clock sums (see launch_rms_sweep_tc)
 };
 
-// MODE: 1 = 3xTF32, 2 = 1xTF32, 3 = 3xBF16
+// MODE: 1 = 3xTF32, 2 = 1xTF32, 3 = 3xBF16.  Launched as clusters of 2 CTAs.
 template <int MODE>
 __global__ void __launch_bounds__(tc::NTHR, 1)
 rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
@@ -201,8 +256,8 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     constexpr bool SPLIT = MODE != 2;
     constexpr int KC = BF16 ? 32 : 16;                 // atoms per stage (64-byte rows)
     constexpr int KSTEPS = 2;                          // UMMA_K = 32 bytes; two per 64-byte row
-    constexpr uint32_t IDESC = umma_idesc(BF16 ? 1 : 2, TQ, UMMA_N);
-    constexpr uint32_t STAGE_TX = SPLIT ? STAGE_BYTES : (3 * A_TILE + 3 * B_TILE);
+    constexpr uint32_t IDESC = umma_idesc(BF16 ? 1 : 2, UMMA_M, UMMA_N);
+    constexpr uint32_t STAGE_TX = 2u * (SPLIT ? 2 : 1) * (A_PART + B_PART);   // both CTAs' bytes land on the leader's barrier
 
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_tmem_full, bar_tmem_empty;
@@ -214,107 +269,151 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();           // 0 = leader (issues the pair's MMAs)
     const int nk = (a.A_pad + KC - 1) / KC;
-    const long long n_qt = (a.n_q + TQ - 1) / TQ;
+    const long long n_qt = (a.n_q + UMMA_M - 1) / UMMA_M;          // fit super-tiles of 256 rows
     const long long n_rt = (a.n_r + TR - 1) / TR;
     const long long n_items = n_qt * a.n_seg;
+    const long long pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_tmem_full, 1);
-        mbar_init(&bar_tmem_empty, EPI_WARPS);
+        mbar_init(&bar_tmem_empty, 2 * EPI_WARPS);     // the epilogue warps of BOTH CTAs (used on the leader only)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                      "n"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                  // the peer's mbarriers and TMEM exist before anything is signalled to them
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
 
-    // item -> (fit tile, reference tile range); segment-major so that concurrently running CTAs
-    // stream the same part of the reference set (L2 reuse)
-    auto item_range = [&](long long it, long long &qt, long long &rt0, long long &rt1, int &seg) {
-        seg = (int)(it / n_qt);
-        qt = it - (long long)seg * n_qt;
+    // item -> (fit super-tile, reference segment).  Diagonal first: the first n_qt items pair every fit
+    // super-tile with the reference segment that holds its own frames (trajectory frames close in
+    // time are close in space), so a row's admission threshold is tight before the other segments
+    // run; those then reject almost every pair on the cheap bounds.  The remaining items are
+    // segment-major so that concurrently running pairs stream the same part of the reference set.
+    // Within the diagonal segment the tile order is rotated to start at the row's own tile.
+    auto item_range = [&](long long it, long long &qt, long long &rt0, long long &rt1, int &seg, long long &rot) {
+        int s_rest = -1;
+        if (it < n_qt) qt = it;
+        else { s_rest = (int)((it - n_qt) / n_qt); qt = (it - n_qt) - (long long)s_rest * n_qt; }
+        const long long own = min((a.q_begin + qt * UMMA_M) / TR, n_rt - 1);     // reference tile of the first fit frame
+        int sd = (int)(own * a.n_seg / n_rt);
+        while (sd + 1 < a.n_seg && n_rt * (sd + 1) / a.n_seg <= own) ++sd;
+        while (sd > 0 && n_rt * sd / a.n_seg > own) --sd;
+        seg = s_rest < 0 ? sd : (s_rest < sd ? s_rest : s_rest + 1);
         rt0 = n_rt * seg / a.n_seg;
         rt1 = n_rt * (seg + 1) / a.n_seg;
+        rot = s_rest < 0 ? own - rt0 : 0;
+    };
+    // i-th reference tile of an item
+    auto tile_at = [](long long i, long long rt0, long long rt1, long long rot) {
+        const long long t = rt0 + rot + i;
+        return t < rt1 ? t : t - (rt1 - rt0);
     };
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
-                long long qt, rt0, rt1; int seg;
-                item_range(it, qt, rt0, rt1, seg);
-                const int q0 = (int)(a.q_begin + qt * TQ);
-                for (long long rt = rt0; rt < rt1; ++rt) {
-                    const int r0 = (int)(rt * TR);
-                    for (int kc = 0; kc < nk; ++kc) {
-                        mbar_wait(&bar_empty[s], ph ^ 1, 1);
-                        unsigned char *st = smem + s * STAGE_BYTES;
-                        if (a.dbg & 4) { mbar_arrive(&bar_full[s]); if (++s == NST) { s = 0; ph ^= 1; } continue; }
-                        mbar_expect_tx(&bar_full[s], STAGE_TX);
-                        // one box = 64 bytes of atoms x rows frames x 3 planes, landing as [plane][frame][atoms]
-                        tma_load_3d(st + OFF_AHI, &map_q_hi, &bar_full[s], kc * KC, q0, 0);
-                        tma_load_3d(st + OFF_BHI, &map_r_hi, &bar_full[s], kc * KC, r0, 0);
-                        if constexpr (SPLIT) {
-                            tma_load_3d(st + OFF_ALO, &map_q_lo, &bar_full[s], kc * KC, q0, 0);
-                            tma_load_3d(st + OFF_BLO, &map_r_lo, &bar_full[s], kc * KC, r0, 0);
+        // converged warp; one elected lane issues.  Each CTA loads its own fit rows and its half of
+        // the reference tile; every copy completes on the LEADER's full barrier.
+        int s = 0;
+        uint32_t ph = 0;
+        for (long long it = pair_id; it < n_items; it += n_pairs) {
+            long long qt, rt0, rt1, rot; int seg;
+            item_range(it, qt, rt0, rt1, seg, rot);
+            const int q0 = (int)(a.q_begin + qt * UMMA_M + rank * TQ);
+            for (long long ti = 0; ti < rt1 - rt0; ++ti) {
+                const int r0 = (int)(tile_at(ti, rt0, rt1, rot) * TR + rank * TRH);
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(&bar_empty[s], ph ^ 1, 1);             // the pair's MMAs have read stage s (both CTAs)
+                    unsigned char *st = smem + s * STAGE_BYTES;
+                    const uint32_t full_leader = map_to_cta(&bar_full[s], 0);
+                    if (elect_one()) {
+                        if (a.dbg & 4) {
+                            if (rank == 0) mbar_arrive(&bar_full[s]);
+                        } else {
+                            if (rank == 0) mbar_expect_tx(&bar_full[s], STAGE_TX);
+                            // one box = 64 bytes of atoms x rows frames x 3 planes, landing as [plane][frame][atoms]
+                            tma_load_3d_2sm(st + OFF_AHI, &map_q_hi, full_leader, kc * KC, q0, 0);
+                            tma_load_3d_2sm(st + OFF_BHI, &map_r_hi, full_leader, kc * KC, r0, 0);
+                            if constexpr (SPLIT) {
+                                tma_load_3d_2sm(st + OFF_ALO, &map_q_lo, full_leader, kc * KC, q0, 0);
+                                tma_load_3d_2sm(st + OFF_BLO, &map_r_lo, full_leader, kc * KC, r0, 0);
+                            }
                         }
-                        if (++s == NST) { s = 0; ph ^= 1; }
                     }
+                    __syncwarp();
+                    if (++s == NST) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // =============================== MMA issuer =================================
-        if (lane == 0) {
+        // =============================== MMA issuer (leader CTA) ====================
+        // converged warp, descriptors in uniform registers, one elected lane issues
+        if (rank == 0) {
             int s = 0;
             uint32_t ph = 0, tph = 0;
             bool first_pass = true;
-            for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
-                long long qt, rt0, rt1; int seg;
-                item_range(it, qt, rt0, rt1, seg);
-                for (long long rt = rt0; rt < rt1; ++rt) {
-                    if (!first_pass) {  // the epilogue must have read the previous accumulators
+            long long t_wait_empty = 0, t_wait_full = 0, t_total0 = MDSCTK_TC_PROF_BUILD ? clock64() : 0, n_pass_done = 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+            for (long long it = pair_id; it < n_items; it += n_pairs) {
+                long long qt, rt0, rt1, rot; int seg;
+                item_range(it, qt, rt0, rt1, seg, rot);
+                for (long long ti = 0; ti < rt1 - rt0; ++ti) {
+                    if (!first_pass) {  // both epilogues must have read the previous accumulators
+                        const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                         mbar_wait(&bar_tmem_empty, tph, 2);
                         tph ^= 1;
+                        if (MDSCTK_TC_PROF_BUILD && a.prof) t_wait_empty += clock64() - t0;
                     }
+                    ++n_pass_done;
                     first_pass = false;
                     tc_fence_after();
                     for (int kc = 0; kc < nk; ++kc) {
-                        mbar_wait(&bar_full[s], ph, 3);
+                        {
+                            const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
+                            mbar_wait(&bar_full[s], ph, 3);
+                            if (MDSCTK_TC_PROF_BUILD && a.prof) t_wait_full += clock64() - t0;
+                        }
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                        const uint32_t sa = smem_u + s * STAGE_BYTES;
                         // atoms beyond A_pad are zero-filled by TMA; skip a k-step that is all padding
                         const int ksteps = (a.A_pad - kc * KC) * (BF16 ? 2 : 4) > 32 ? KSTEPS : 1;
-                        for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ++ks) {
-                            const uint32_t koff = ks * 32;
-                            const uint64_t bhi = umma_desc_sw64(sa + OFF_BHI + koff);
-                            const uint64_t blo = umma_desc_sw64(sa + OFF_BLO + koff);
+                        if (elect_one()) {
+                            for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ++ks) {
+                                const uint32_t koff = ks * 32;
+                                const uint64_t bhi = umma_desc_sw64(sa + OFF_BHI + koff);
+                                const uint64_t blo = umma_desc_sw64(sa + OFF_BLO + koff);
 #pragma unroll
-                            for (int p = 0; p < 3; ++p) {
-                                const uint32_t d = tmem_base + p * UMMA_N;
-                                const uint64_t ahi = umma_desc_sw64(sa + OFF_AHI + p * A_TILE + koff);
-                                tc_mma<BF16>(d, ahi, bhi, IDESC, (kc | ks) != 0);
-                                if constexpr (SPLIT) {
-                                    const uint64_t alo = umma_desc_sw64(sa + OFF_ALO + p * A_TILE + koff);
-                                    tc_mma<BF16>(d, ahi, blo, IDESC, 1);
-                                    tc_mma<BF16>(d, alo, bhi, IDESC, 1);
+                                for (int p = 0; p < 3; ++p) {
+                                    const uint32_t d = tmem_u + p * UMMA_N;
+                                    const uint64_t ahi = umma_desc_sw64(sa + OFF_AHI + p * A_TILE + koff);
+                                    tc_mma2<BF16>(d, ahi, bhi, IDESC, (kc | ks) != 0);
+                                    if constexpr (SPLIT) {
+                                        const uint64_t alo = umma_desc_sw64(sa + OFF_ALO + p * A_TILE + koff);
+                                        tc_mma2<BF16>(d, ahi, blo, IDESC, 1);
+                                        tc_mma2<BF16>(d, alo, bhi, IDESC, 1);
+                                    }
                                 }
                             }
+                            tc_commit2_mc(&bar_empty[s], 3);                       // frees stage s in both CTAs
+                            if (kc == nk - 1) tc_commit2_mc(&bar_tmem_full, 3);    // accumulators complete -> both epilogues
                         }
-                        tc_commit(&bar_empty[s]);  // frees the smem stage once these MMAs have read it
+                        __syncwarp();
                         if (++s == NST) { s = 0; ph ^= 1; }
                     }
-                    tc_commit(&bar_tmem_full);     // accumulators complete -> epilogue
                 }
+            }
+            if (MDSCTK_TC_PROF_BUILD && a.prof && lane == 0) {
+                long long *pr = a.prof + (size_t)blockIdx.x * 8;
+                pr[0] = clock64() - t_total0; pr[1] = t_wait_empty; pr[2] = t_wait_full; pr[3] = n_pass_done;
             }
         }
     } else {
@@ -327,10 +426,13 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         // survive the straight-line filter are queued per warp and refined with all lanes busy.
         const int ew = warp - 2;                      // 0..15
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-        const int sub = ew >> 2;                      // which 12 reference columns of every tile
+        const int sub = ew >> 2;                      // which 12 reference frames of every tile
         const int e_of_quarter = (quarter + 2) & 3;   // ew = sub * 4 + e_of_quarter
         const int row_in_tile = quarter * 32 + lane;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // accumulator column of (plane b, ref 12 sub + j): refs 0-23 come from CTA 0's operand rows
+        // (columns [0,72) = x|y|z x 24), refs 24-47 from CTA 1's (columns [72,144))
+        const uint32_t t_warp = tmem_base + ((uint32_t)(quarter * 32) << 16) + (sub >> 1) * (3 * TRH) + (sub & 1) * SUBW;
+        const uint32_t empty_leader = map_to_cta(&bar_tmem_empty, 0);
         const unsigned lt_mask = (1u << lane) - 1u;
         unsigned *hist = s_hist[ew];                  // radix histogram during merges, refine queue otherwise
         float *q_c2 = reinterpret_cast<float *>(hist), *q_c1 = q_c2 + 32, *q_c0 = q_c2 + 64, *q_e0 = q_c2 + 96,
@@ -339,6 +441,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         int *wcnt = s_cnt[ew];                        // fill of this warp's append area of row (quarter*32 + l)
         const size_t row_stride = (size_t)a.cl.H * a.cl.cap;
         uint32_t tph = 0;
+        long long t_wait_tmem = 0, t_hold = 0, t_post = 0, t_merge = 0;
         int qn = 0;                                   // queue fill (warp-uniform)
         size_t lbase0 = 0;                            // list of the quarter's row 0 in the current item
         float *lkeys = a.cl.key;
@@ -382,12 +485,12 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             qn += n;
         };
         // Quarter-wide merge of the rows this warp is responsible for (8 per warp).  final: every row.
-        auto merge_rows = [&](long long qt, int seg, bool final) {
+        auto merge_rows = [&](long long row0, int seg, bool final) {
             quarter_sync(quarter);
             for (int r8 = 0; r8 < 8; ++r8) {
                 const int l = sub * 8 + r8;
                 const int row = quarter * 32 + l;
-                const long long qr = qt * TQ + row;
+                const long long qr = row0 + row;
                 if (qr >= a.n_q) break;
                 int cs[SUBS], cmax = 0;
 #pragma unroll
@@ -433,13 +536,14 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             quarter_sync(quarter);
         };
 
-        for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
-            long long qt, rt0, rt1; int seg;
-            item_range(it, qt, rt0, rt1, seg);
-            const long long qrow = qt * TQ + row_in_tile;        // row within the query range
+        for (long long it = pair_id; it < n_items; it += n_pairs) {
+            long long qt, rt0, rt1, rot; int seg;
+            item_range(it, qt, rt0, rt1, seg, rot);
+            const long long row0 = qt * UMMA_M + rank * TQ;      // first fit row of this CTA within the query range
+            const long long qrow = row0 + row_in_tile;
             const bool qvalid = qrow < a.n_q;
             const float hgq = 0.5f * a.q_G[a.q_begin + (qvalid ? qrow : a.n_q - 1)];
-            lbase0 = ((size_t)(qt * TQ + quarter * 32) * a.cl.H + seg) * a.cl.cap;
+            lbase0 = ((size_t)(row0 + quarter * 32) * a.cl.H + seg) * a.cl.cap;
             wcnt[lane] = 0;
             if (sub == 0) {
                 s_mcnt[row_in_tile] = 0;
@@ -447,42 +551,48 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 s_tau[row_in_tile] = qvalid ? __ldcg(a.row_tau + qrow) : 0.0f;
             }
             quarter_sync(quarter);
-            for (long long rt = rt0; rt < rt1; ++rt) {
-                const long long r0 = rt * TR + sub * SUBW;
-                float4 gv[SUBW / EB];
+            for (long long ti = 0; ti < rt1 - rt0; ++ti) {
+                const long long rt = tile_at(ti, rt0, rt1, rot);
+                const long long rb = rt * TR + sub * SUBW;       // first reference frame of this warp's columns
+                float4 gv[SUBW / 4];
 #pragma unroll
-                for (int jb = 0; jb < SUBW / EB; ++jb) gv[jb] = __ldg(reinterpret_cast<const float4 *>(a.r_G + r0) + jb);
+                for (int j = 0; j < SUBW / 4; ++j) gv[j] = __ldg(reinterpret_cast<const float4 *>(a.r_G + min(rb, a.n_r & ~3LL)) + j);
+                const long long tp0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                 if (lane == 0) mbar_wait(&bar_tmem_full, tph, 4);
                 tph ^= 1;
                 __syncwarp();
                 tc_fence_after();
+                const long long tp1 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
+                long long tp2 = tp1;
                 const float tau = *reinterpret_cast<volatile float *>(&s_tau[row_in_tile]);
                 const float htau = 0.5f * tau;
+                const float ge[SUBW] = {gv[0].x, gv[0].y, gv[0].z, gv[0].w, gv[1].x, gv[1].y, gv[1].z, gv[1].w,
+                                        gv[2].x, gv[2].y, gv[2].z, gv[2].w};
 #pragma unroll
-                for (int jb = 0; jb < SUBW / EB; ++jb) {
+                for (int h = 0; h < SUBW; h += EB) {
                     float sv[9][EB];
 #pragma unroll
                     for (int p = 0; p < 3; ++p)
 #pragma unroll
                         for (int b = 0; b < 3; ++b)
-                            tc_ld4(t_lane + p * UMMA_N + b * TR + sub * SUBW + jb * EB, sv, p * 3 + b);
+                            tc_ld4(t_warp + p * UMMA_N + b * TRH + h, sv, p * 3 + b);
                     tc_wait_ld();
-                    if (jb == SUBW / EB - 1) {  // last TMEM read of this pass: hand the accumulators back
+                    if (h + EB == SUBW) {             // last TMEM read of this pass: hand the accumulators back
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_tmem_empty);
+                        if (lane == 0) mbar_arrive_cluster(empty_leader);
+                        if (MDSCTK_TC_PROF_BUILD && a.prof) tp2 = clock64();
                     }
-                    if (a.debug_tile && it == 0 && rt == 0) {
+                    if (a.debug_tile && it == 0 && rt == 0 && rank == 0) {
 #pragma unroll
                         for (int c = 0; c < 9; ++c)
 #pragma unroll
                             for (int j = 0; j < EB; ++j)
-                                a.debug_tile[(size_t)row_in_tile * (9 * TR) + c * TR + sub * SUBW + jb * EB + j] = sv[c][j];
+                                a.debug_tile[(size_t)row_in_tile * (9 * TR) + c * TR + sub * SUBW + h + j] = sv[c][j];
                     }
-                    const float4 g = gv[jb];
-                    const float e0[EB] = {fmaf(0.5f, g.x, hgq), fmaf(0.5f, g.y, hgq), fmaf(0.5f, g.z, hgq),
-                                          fmaf(0.5f, g.w, hgq)};
-                    const long long rb = r0 + jb * EB;
+                    float e0[EB];
+#pragma unroll
+                    for (int j = 0; j < EB; ++j) e0[j] = fmaf(0.5f, ge[h + j], hgq);
                     if (a.dbg & 1) {
                         float acc = 0.f;
 #pragma unroll
@@ -494,8 +604,8 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 #pragma unroll
                         for (int j = 0; j < EB; ++j) {
                             const float tr = sv[0][j] + sv[4][j] + sv[8][j];
-                            push(qvalid && rb + j < a.n_r && 2.0f * (e0[j] - tr) < tau, 0.f, 0.f, 0.f, e0[j], tr,
-                                 (int)(rb + j), lane | 32);
+                            push(qvalid && rb + h + j < a.n_r && 2.0f * (e0[j] - tr) < tau, 0.f, 0.f, 0.f, e0[j], tr,
+                                 (int)(rb + h + j), lane | 32);
                         }
                         continue;
                     }
@@ -527,23 +637,30 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     // (3) survivors go to the warp's refine queue
 #pragma unroll
                     for (int j = 0; j < EB; ++j)
-                        push(qvalid && rb + j < a.n_r && !(2.0f * (e0[j] - x1[j]) > tau), c[j].c2, c[j].c1, c[j].c0, e0[j],
-                             x1[j], (int)(rb + j), lane);
+                        push(qvalid && rb + h + j < a.n_r && !(2.0f * (e0[j] - x1[j]) > tau), c[j].c2, c[j].c1, c[j].c0, e0[j],
+                             x1[j], (int)(rb + h + j), lane);
                 }
                 drain();
+                const long long tp3 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                 // an append area takes at most SUBW entries per pass
-                if ((((rt - rt0) & (MERGE_EVERY - 1)) == MERGE_EVERY - 1) && rt + 1 < rt1) merge_rows(qt, seg, false);
+                if (((ti & (MERGE_EVERY - 1)) == MERGE_EVERY - 1) && ti + 1 < rt1 - rt0) merge_rows(row0, seg, false);
+                if (MDSCTK_TC_PROF_BUILD && a.prof) { t_wait_tmem += tp1 - tp0; t_hold += tp2 - tp1; t_post += tp3 - tp2; t_merge += clock64() - tp3; }
             }
-            merge_rows(qt, seg, true);                // leaves one list of <= keep candidates per row
+            merge_rows(row0, seg, true);              // leaves one list of <= keep candidates per row
+        }
+        if (MDSCTK_TC_PROF_BUILD && a.prof && ew == 0 && lane == 0) {
+            long long *pr = a.prof + (size_t)blockIdx.x * 8 + 4;
+            pr[0] = t_wait_tmem; pr[1] = t_hold; pr[2] = t_post; pr[3] = t_merge;
         }
     }
 
     // ---- teardown --------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                  // no CTA leaves (or frees TMEM) while the peer may still use it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
 
@@ -582,18 +699,19 @@ static bool make_plane_map(CUtensorMap *m, const void *planes, long long n, int 
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Reference segments per fit tile: enough work items for even waves over the SMs, but every
-// segment keeps at least 16 reference tiles (its lists warm up once per segment).
+// Reference segments per fit super-tile: enough work items for even waves over the CTA pairs, but
+// every segment keeps at least 16 reference tiles (its lists warm up once per segment).
 int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms)
 {
-    const long long n_qt = (n_fit + tc::TQ - 1) / tc::TQ;
+    const int n_pairs = n_sms / 2 > 0 ? n_sms / 2 : 1;
+    const long long n_qt = (n_fit + tc::UMMA_M - 1) / tc::UMMA_M;
     const long long n_rt = (n_ref + tc::TR - 1) / tc::TR;
     int best = 1;
     double best_eff = 0.0;
     for (int s = 1; s <= 8; ++s) {
         if (s > 1 && n_rt / s < 16) break;
         const long long items = n_qt * s;
-        const double eff = (double)items / (double)(((items + n_sms - 1) / n_sms) * n_sms);
+        const double eff = (double)items / (double)(((items + n_pairs - 1) / n_pairs) * n_pairs);
         if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
     }
     return best;
@@ -601,8 +719,31 @@ int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms)
 
 int rms_tc_lists_per_segment() { return 1; }
 
-// Entries reserved per (fit row, reference segment): keep merged + one append area per epilogue warp.
+// Entries reserved per list: keep merged + one append area per epilogue warp of a lane quarter.
 int rms_tc_list_stride(int keep) { return (keep + tc::SUBS * tc::SUB_APP + 31) / 32 * 32; }
+
+template <int M>
+static cudaError_t launch_tc_mode(const CUtensorMap &mq_hi, const CUtensorMap &mq_lo, const CUtensorMap &mr_hi,
+                                  const CUtensorMap &mr_lo, const TcArgs &a, long long n_items, int n_sms, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(rms_sweep_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(tc::NTHR); cfg.dynamicSmemBytes = tc::SMEM_BYTES; cfg.stream = st;
+    int max_pairs = n_sms / 2;
+    cfg.gridDim = dim3((unsigned)(max_pairs * 2));
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, rms_sweep_tc_kernel<M>, &cfg) == cudaSuccess && q > 0 && q < max_pairs)
+        max_pairs = q;                              // a GPC with an odd SM count cannot host every pair
+    (void)cudaGetLastError();
+    const long long n_pairs = n_items < max_pairs ? n_items : max_pairs;
+    cfg.gridDim = dim3((unsigned)(n_pairs * 2));
+    return cudaLaunchKernelEx(&cfg, rms_sweep_tc_kernel<M>, mq_hi, mq_lo, mr_hi, mr_lo, a);
+}
 
 cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *fit_hi, const void *fit_lo,
                                 long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,
@@ -610,33 +751,55 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
                                 float *debug_tile, int n_sms, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
-    if (cl.H != n_seg) return cudaErrorInvalidValue;
+    if (cl.H != n_seg || cl.cap < cl.keep + tc::SUBS * tc::SUB_APP) return cudaErrorInvalidValue;
     const bool bf16 = mode == 3;
     CUtensorMap mq_hi, mq_lo, mr_hi, mr_lo;
     if (!make_plane_map(&mq_hi, fit_hi, fit.n, fit.A_pad, tc::TQ, bf16) ||
         !make_plane_map(&mq_lo, fit_lo, fit.n, fit.A_pad, tc::TQ, bf16) ||
-        !make_plane_map(&mr_hi, ref_hi, ref.n, ref.A_pad, tc::TR, bf16) ||
-        !make_plane_map(&mr_lo, ref_lo, ref.n, ref.A_pad, tc::TR, bf16))
+        !make_plane_map(&mr_hi, ref_hi, ref.n, ref.A_pad, tc::TRH, bf16) ||
+        !make_plane_map(&mr_lo, ref_lo, ref.n, ref.A_pad, tc::TRH, bf16))
         return cudaErrorInvalidValue;
     TcArgs a;
     a.q_G = fit.G; a.r_G = ref.G; a.q_begin = fit_begin; a.n_q = n_fit; a.n_r = ref.n;
     a.A_pad = ref.A_pad; a.do_fit = do_fit; a.n_seg = n_seg; a.cl = cl; a.debug_tile = debug_tile; a.row_tau = row_tau;
     const char *dbg = getenv("MDSCTK_TC_DEBUG");
     a.dbg = dbg ? atoi(dbg) : 0;
-    const long long n_items = ((n_fit + tc::TQ - 1) / tc::TQ) * n_seg;
-    const unsigned grid = (unsigned)(n_items < n_sms ? n_items : n_sms);
+    // MDSCTK_TC_PROF=1: per-CTA clock sums {MMA warp: total, wait tmem_empty, wait full, passes |
+    // epilogue warp 0: wait tmem_full, TMEM hold, post-release compute, merges}, printed to stderr
+    static long long *d_prof = nullptr;
+    const char *pe = getenv("MDSCTK_TC_PROF");
+    const bool prof = MDSCTK_TC_PROF_BUILD && pe && atoi(pe) != 0;
+    a.prof = nullptr;
+    if (prof) {
+        if (!d_prof && cudaMalloc(&d_prof, 1024 * 8 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+        cudaMemsetAsync(d_prof, 0, 1024 * 8 * sizeof(long long), st);
+        a.prof = d_prof;
+    }
+    const long long n_items = ((n_fit + tc::UMMA_M - 1) / tc::UMMA_M) * n_seg;
     cudaError_t e;
-#define MDSCTK_LAUNCH_TC(M)                                                                                           \
-    e = cudaFuncSetAttribute(rms_sweep_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);   \
-    if (e != cudaSuccess) return e;                                                                                  \
-    rms_sweep_tc_kernel<M><<<grid, tc::NTHR, tc::SMEM_BYTES, st>>>(mq_hi, mq_lo, mr_hi, mr_lo, a)
     switch (mode) {
-    case 1: MDSCTK_LAUNCH_TC(1); break;
-    case 2: MDSCTK_LAUNCH_TC(2); break;
-    case 3: MDSCTK_LAUNCH_TC(3); break;
+    case 1: e = launch_tc_mode<1>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
+    case 2: e = launch_tc_mode<2>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
+    case 3: e = launch_tc_mode<3>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
     default: return cudaErrorInvalidValue;
     }
-#undef MDSCTK_LAUNCH_TC
+    if (e != cudaSuccess) return e;
+    if (prof) {
+        static long long h[1024 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        double sum[8] = {0}; int nb = 0;
+        for (int b = 0; b < 1024; b += 1) {
+            if (h[b * 8 + 4] == 0 && h[b * 8] == 0) continue;
+            nb++;
+            for (int k = 0; k < 8; ++k) sum[k] += (double)h[b * 8 + k];
+        }
+        // leaders carry the MMA columns (half of the CTAs); epilogue columns come from every CTA
+        fprintf(stderr, "[tc prof] ctas=%d  mma: total %.0f  wait_tmem_empty %.0f  wait_full %.0f  passes %.0f (clk, per leader) | "
+                        "epi warp0: wait_tmem_full %.0f  hold %.0f  post %.0f  merge %.0f (clk per CTA)\n",
+                nb, sum[0] / (nb / 2.0), sum[1] / (nb / 2.0), sum[2] / (nb / 2.0), sum[3] / (nb / 2.0), sum[4] / nb, sum[5] / nb,
+                sum[6] / nb, sum[7] / nb);
+    }
     return cudaGetLastError();
 }
 

@@ -117,6 +117,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int ta
         }
     }
 }
+// Latency-critical variant for the MMA issuer: plain try_wait polling (no suspend hint).
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity, int tag)
+{
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++polls > 200000000u) {
+            printf("rms_sweep_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
 __device__ __forceinline__ void quarter_sync(int quarter)
 {
     asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory");
@@ -129,14 +140,16 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 // CTA-pair copy: lands in THIS CTA's shared memory, completes on the mbarrier `bar_cluster_addr`
-// (a shared::cluster address; the leader's "full" barrier for both CTAs of the pair).
+// (a shared::cluster address; the leader's "full" barrier for both CTAs of the pair).  `policy` is
+// an L2 eviction-priority descriptor (kEvictLast for the fit tile, re-read every pass).
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull, kEvictFirst = 0x12F0000000000000ull, kEvictLast = 0x14F0000000000000ull;
 __device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1,
-                                                int c2)
+                                                int c2, uint64_t policy)
 {
     asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
 }
 // shared::cluster address of the same variable in CTA `rank` of the cluster
@@ -324,6 +337,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         // the reference tile; every copy completes on the LEADER's full barrier.
         int s = 0;
         uint32_t ph = 0;
+        const uint64_t pol_a = (a.dbg & 16) ? kEvictNormal : kEvictLast, pol_b = (a.dbg & 32) ? kEvictFirst : kEvictNormal;
         for (long long it = pair_id; it < n_items; it += n_pairs) {
             long long qt, rt0, rt1, rot; int seg;
             item_range(it, qt, rt0, rt1, seg, rot);
@@ -340,11 +354,11 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                         } else {
                             if (rank == 0) mbar_expect_tx(&bar_full[s], STAGE_TX);
                             // one box = 64 bytes of atoms x rows frames x 3 planes, landing as [plane][frame][atoms]
-                            tma_load_3d_2sm(st + OFF_AHI, &map_q_hi, full_leader, kc * KC, q0, 0);
-                            tma_load_3d_2sm(st + OFF_BHI, &map_r_hi, full_leader, kc * KC, r0, 0);
+                            tma_load_3d_2sm(st + OFF_AHI, &map_q_hi, full_leader, kc * KC, q0, 0, pol_a);
+                            tma_load_3d_2sm(st + OFF_BHI, &map_r_hi, full_leader, kc * KC, r0, 0, pol_b);
                             if constexpr (SPLIT) {
-                                tma_load_3d_2sm(st + OFF_ALO, &map_q_lo, full_leader, kc * KC, q0, 0);
-                                tma_load_3d_2sm(st + OFF_BLO, &map_r_lo, full_leader, kc * KC, r0, 0);
+                                tma_load_3d_2sm(st + OFF_ALO, &map_q_lo, full_leader, kc * KC, q0, 0, pol_a);
+                                tma_load_3d_2sm(st + OFF_BLO, &map_r_lo, full_leader, kc * KC, r0, 0, pol_b);
                             }
                         }
                     }
@@ -369,7 +383,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 for (long long ti = 0; ti < rt1 - rt0; ++ti) {
                     if (!first_pass) {  // both epilogues must have read the previous accumulators
                         const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
-                        mbar_wait(&bar_tmem_empty, tph, 2);
+                        if (a.dbg & 64) mbar_wait(&bar_tmem_empty, tph, 2); else mbar_wait_spin(&bar_tmem_empty, tph, 2);
                         tph ^= 1;
                         if (MDSCTK_TC_PROF_BUILD && a.prof) t_wait_empty += clock64() - t0;
                     }
@@ -379,7 +393,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     for (int kc = 0; kc < nk; ++kc) {
                         {
                             const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
-                            mbar_wait(&bar_full[s], ph, 3);
+                            if (a.dbg & 64) mbar_wait(&bar_full[s], ph, 3); else mbar_wait_spin(&bar_full[s], ph, 3);
                             if (MDSCTK_TC_PROF_BUILD && a.prof) t_wait_full += clock64() - t0;
                         }
                         tc_fence_after();

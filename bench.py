@@ -108,8 +108,8 @@ def measured_peaks(rms_kernel):
         bf16, src = m["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
     else:
         bf16, src = 1400.0, "fallback ~1.4 PFLOP/s sustained bf16 (B200_PROFILING.md; of fallback)"
-    if rms_kernel == 3:
-        return {"tflops": bf16, "source": src + "; kernel issues bf16 MMAs"}
+    if rms_kernel >= 3:
+        return {"tflops": bf16, "source": src + "; kernel issues 16-bit (kind::f16) MMAs"}
     return {"tflops": bf16 / 2.0, "source": src + " / 2 = dense TF32 rate"}
 
 
@@ -300,15 +300,17 @@ def main():
         kern = {0: "rms_sweep_simt_kernel (FP32 CUDA-core contraction + QCP + streaming top-k)",
                 1: "rms_sweep_tc_kernel<1> (tcgen05 kind::tf32, 3xTF32 split contraction + QCP + streaming top-k)",
                 2: "rms_sweep_tc_kernel<2> (tcgen05 kind::tf32, 1xTF32 contraction + QCP + streaming top-k)",
-                3: "rms_sweep_tc_kernel<3> (tcgen05 kind::f16, 3xBF16 split contraction + QCP + streaming top-k)"}[st["rms_kernel"]]
+                3: "rms_sweep_tc_kernel<3> (tcgen05 cta_group::2 kind::f16, 3xBF16 split contraction + QCP bounds + streaming top-k)",
+                4: "rms_sweep_tc_kernel<4> (tcgen05 cta_group::2 kind::f16, 3xFP16 split contraction + QCP bounds + streaming top-k)",
+                5: "rms_sweep_tc_kernel<5> (tcgen05 cta_group::2 kind::f16, 2xFP16 contraction + QCP bounds + streaming top-k)"}[st["rms_kernel"]]
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        tp = os.path.join(ROOT, "profiles", "traffic_r01b.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(str(st["rms_kernel"]))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "tf32", 2: "tf32", 3: "bf16"}[st["rms_kernel"]] + " contraction (fp32 accumulate), f64 re-score",
+            "dtype": {0: "f32", 1: "tf32", 2: "tf32", 3: "bf16", 4: "f16", 5: "f16"}[st["rms_kernel"]] + " contraction (fp32 accumulate), f64 re-score",
             "data": "synthetic",
             "config": {"workload": wl["name"], "frames": n_total, "atoms": ATOMS, "k": wl["k"],
                        "fit_rows_per_rank_per_step": rows, "parallelism": f"row-sharded x{world}, reference replicated",
@@ -322,7 +324,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": sweep_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": sweep_tflops / peaks["tflops"], "traffic": traffic,
-                         "mma_per_flop": 1 if st["rms_kernel"] in (0, 2) else 3,
+                         "mma_per_flop": {0: 1, 2: 1, 5: 2}.get(st["rms_kernel"], 3),
                          "kernel": kern.split(" ")[0], "flop_per_pair": FLOP_PER_PAIR, "peak_source": peaks["source"],
                          "sweep_ms_per_step": sweep_ms / args.steps, "post_ms_per_step": post_ms / args.steps},
             "cpu_baseline": cpu_baseline_sample(wl),

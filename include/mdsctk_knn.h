@@ -58,7 +58,9 @@ enum {
     MDSCTK_KNN_RMS_SIMT_FP32 = 0,  /* FP32 CUDA-core contraction                                  */
     MDSCTK_KNN_RMS_TC_3XTF32 = 1,  /* tcgen05 kind::tf32, hi/lo operand split (3 MMAs)              */
     MDSCTK_KNN_RMS_TC_1XTF32 = 2,  /* tcgen05 kind::tf32, hi only (coarse filter)                   */
-    MDSCTK_KNN_RMS_TC_3XBF16 = 3   /* tcgen05 kind::f16 on bf16 hi/mid operand split (3 MMAs)       */
+    MDSCTK_KNN_RMS_TC_3XBF16 = 3,  /* tcgen05 kind::f16 on bf16 hi/mid operand split (3 MMAs)       */
+    MDSCTK_KNN_RMS_TC_3XFP16 = 4,  /* tcgen05 kind::f16 on fp16 hi/lo split of 64x (3 MMAs, 22 bits) */
+    MDSCTK_KNN_RMS_TC_2XFP16 = 5   /* fit operand fp16 hi only, reference hi/lo (2 MMAs)            */
 };
 
 typedef struct mdsctk_knn_ctx mdsctk_knn_ctx;

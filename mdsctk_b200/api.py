@@ -13,7 +13,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-RMS_SIMT_FP32, RMS_TC_3XTF32, RMS_TC_1XTF32, RMS_TC_3XBF16 = 0, 1, 2, 3
+RMS_SIMT_FP32, RMS_TC_3XTF32, RMS_TC_1XTF32, RMS_TC_3XBF16, RMS_TC_3XFP16, RMS_TC_2XFP16 = 0, 1, 2, 3, 4, 5
 EUCLIDEAN, CORRELATION = 0, 1
 
 SYMBOLS = [
@@ -161,9 +161,9 @@ class KnnContext:
 
     def _arrays(self, fn, n_rows):
         n = C.c_int(0)
-        ptrs = (C.c_void_p * 8)()
-        bpf = (C.c_size_t * 8)()
-        self._ck(fn(self._h, 8, C.byref(n), ptrs, bpf), "reference_arrays")
+        ptrs = (C.c_void_p * 16)()
+        bpf = (C.c_size_t * 16)()
+        self._ck(fn(self._h, 16, C.byref(n), ptrs, bpf), "reference_arrays")
         return [DeviceArray(ptrs[i], bpf[i] * n_rows) for i in range(n.value)], [bpf[i] for i in range(n.value)]
 
     def rms_reference_arrays(self):

@@ -41,7 +41,7 @@ struct DevBuf {
 };
 
 struct FrameSet {
-    DevBuf raw, planes, hi, lo, bh, bm, G, cen;
+    DevBuf raw, planes, hi, lo, bh, bm, fh, fl, G, cen;
     long long n = 0;
     int A = 0, A_pad = 0;
     FrameSetView view() const
@@ -61,12 +61,14 @@ struct FrameSet {
         if ((e = lo.reserve((size_t)n * 3 * A_pad * 4)) != cudaSuccess) return e;
         if ((e = bh.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
         if ((e = bm.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
+        if ((e = fh.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
+        if ((e = fl.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
         if ((e = G.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;  // tensor-core epilogue reads G in 48-wide tiles
         return cen.reserve((size_t)n * 32);
     }
     void release()
     {
-        raw.release(); planes.release(); hi.release(); lo.release(); bh.release(); bm.release(); G.release();
+        raw.release(); planes.release(); hi.release(); lo.release(); bh.release(); bm.release(); fh.release(); fl.release(); G.release();
         cen.release(); n = 0;
     }
 };
@@ -171,6 +173,7 @@ int pack_into(mdsctk_knn_ctx *ctx, FrameSet &fs, const float *xyz, long long off
                           fs.planes.as<float>() + (size_t)off * 3 * fs.A_pad,
                           fs.hi.as<float>() + (size_t)off * 3 * fs.A_pad, fs.lo.as<float>() + (size_t)off * 3 * fs.A_pad,
                           fs.bh.as<uint16_t>() + (size_t)off * 3 * fs.A_pad, fs.bm.as<uint16_t>() + (size_t)off * 3 * fs.A_pad,
+                          fs.fh.as<uint16_t>() + (size_t)off * 3 * fs.A_pad, fs.fl.as<uint16_t>() + (size_t)off * 3 * fs.A_pad,
                           fs.G.as<float>() + off,
                           fs.cen.as<double>() + 4 * off, ctx->st), "pack_frames");
     ctx->stats.ms_pack += ctx->tm.stop(ctx->st);
@@ -200,6 +203,8 @@ double default_eps_scale(int rms_kernel, int n_atoms)
     switch (rms_kernel) {
     case MDSCTK_KNN_RMS_TC_1XTF32: return 4e-5 * sa;
     case MDSCTK_KNN_RMS_TC_3XBF16: return 1.5e-5;       // bf16 split residual 2^-18 per product dominates
+    case MDSCTK_KNN_RMS_TC_2XFP16: return 1.2e-4;       // fit operand rounded to 11 bits; measured half-spread 9e-5 E0
+    case MDSCTK_KNN_RMS_TC_3XFP16:
     case MDSCTK_KNN_RMS_TC_3XTF32:
     default: return 5e-7 * sa;
     }
@@ -267,10 +272,17 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
         CK(ctx->row_tau.reserve((size_t)n_fit * 4), "cudaMalloc(row_tau)");
         CK(launch_fill_u32(ctx->row_tau.p, (size_t)n_fit, 0x7f800000u, ctx->st), "fill row_tau");  // +inf
         {
-            const bool bf = ctx->rms_kernel == MDSCTK_KNN_RMS_TC_3XBF16;
-            CK(launch_rms_sweep_tc(ctx->rms_kernel, fit, bf ? fitset.bh.p : fitset.hi.p, bf ? fitset.bm.p : fitset.lo.p,
-                                   fit_begin, n_fit, ref, bf ? ctx->ref.bh.p : ctx->ref.hi.p,
-                                   bf ? ctx->ref.bm.p : ctx->ref.lo.p, do_fit, n_seg, cl, ctx->row_tau.as<float>(),
+            const void *q_hi = fitset.hi.p, *q_lo = fitset.lo.p, *r_hi = ctx->ref.hi.p, *r_lo = ctx->ref.lo.p;
+            if (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_3XBF16) {
+                q_hi = fitset.bh.p; q_lo = fitset.bm.p; r_hi = ctx->ref.bh.p; r_lo = ctx->ref.bm.p;
+            } else if (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_3XFP16 || ctx->rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16) {
+                q_hi = fitset.fh.p; q_lo = fitset.fl.p; r_hi = ctx->ref.fh.p; r_lo = ctx->ref.fl.p;
+                // 64 * sqrt(G) bounds every operand element; fp16 overflows at 65504
+                if (64.0 * std::sqrt((double)ctx->g_ref_max) > 3.0e4)
+                    return fail(ctx, MDSCTK_KNN_EINVAL, "coordinates too large for the fp16 kernels; use rms_kernel=1 (3xTF32)");
+            }
+            CK(launch_rms_sweep_tc(ctx->rms_kernel, fit, q_hi, q_lo, fit_begin, n_fit, ref, r_hi, r_lo, do_fit, n_seg, cl,
+                                   ctx->row_tau.as<float>(),
                                    ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
                "rms_sweep_tc");
         }
@@ -450,7 +462,7 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
 {
     if (!ctx || !key) return MDSCTK_KNN_EINVAL;
     if (!strcmp(key, "rms_kernel")) {
-        if (value < 0 || value > 3) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel must be 0..3");
+        if (value < 0 || value > 5) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel must be 0..5");
         ctx->rms_kernel = (int)value;
     } else if (!strcmp(key, "slack")) {
         if (value < -1 || value > 1024) return fail(ctx, MDSCTK_KNN_EINVAL, "slack out of range");
@@ -507,8 +519,8 @@ int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_
 {
     if (!ctx || !n_arrays) return MDSCTK_KNN_EINVAL;
     if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
-    *n_arrays = 8;
-    if (max_arrays < 8 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 8 arrays");
+    *n_arrays = 10;
+    if (max_arrays < 10 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 10 arrays");
     dev_ptrs[0] = ctx->ref.raw.p;    bytes_per_frame[0] = (size_t)ctx->ref.A * 12;
     dev_ptrs[1] = ctx->ref.planes.p; bytes_per_frame[1] = (size_t)ctx->ref.A_pad * 12;
     dev_ptrs[2] = ctx->ref.G.p;      bytes_per_frame[2] = 4;
@@ -517,6 +529,8 @@ int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_
     dev_ptrs[5] = ctx->ref.lo.p;     bytes_per_frame[5] = (size_t)ctx->ref.A_pad * 12;
     dev_ptrs[6] = ctx->ref.bh.p;     bytes_per_frame[6] = (size_t)ctx->ref.A_pad * 6;
     dev_ptrs[7] = ctx->ref.bm.p;     bytes_per_frame[7] = (size_t)ctx->ref.A_pad * 6;
+    dev_ptrs[8] = ctx->ref.fh.p;     bytes_per_frame[8] = (size_t)ctx->ref.A_pad * 6;
+    dev_ptrs[9] = ctx->ref.fl.p;     bytes_per_frame[9] = (size_t)ctx->ref.A_pad * 6;
     ctx->gmax_dirty = true;  // the caller is about to overwrite them (all-gather)
     return 0;
 }

@@ -7,6 +7,7 @@
 //   planes float  [n][3][A_pad]    centred, scaled by sqrt(m_a / M); zero padded to A_pad
 //   hi, lo float  [n][3][A_pad]    TF32 split of planes: hi = rn_tf32(x), lo = rn_tf32(x - hi)
 //   bh, bm bf16   [n][3][A_pad]    BF16 split of planes: bh = rn_bf16(x), bm = rn_bf16(x - bh)
+//   fh, fl fp16   [n][3][A_pad]    FP16 split of 64*planes: fh = rn_f16(64x), fl = rn_f16(64x - fh)
 //   G      float  [n] (+64 pad)    sum_a (m_a/M) |x_a - c|^2          (fp32 copy for the sweep)
 //   cen    double [n][4]           mass-weighted centroid (x,y,z) and G in FP64
 // With the weights normalised to sum 1, min-RMSD^2 = G_q + G_r - 2*lambda_max (nm^2).
@@ -16,6 +17,7 @@
 
 namespace mdsctk {
 
+constexpr float kRmsHalfScale = 64.0f;  // FP16 operand planes hold 64 * sqrt(w) (x - c): keeps the lo part normal
 constexpr int kAtomPad = 16;  // A_pad = roundup(A, 16): SIMT k-chunk and 2 x UMMA_K(tf32)=8
 
 inline int pad_atoms(int a) { return (a + kAtomPad - 1) / kAtomPad * kAtomPad; }
@@ -47,14 +49,15 @@ struct CandLists {
 
 // ---- launch wrappers (defined in the .cu files) -----------------------------------
 cudaError_t launch_pack_frames(const float *raw, const double *mass_norm, long long n, int A, int A_pad,
-                               float *planes, float *hi, float *lo, void *bh, void *bm, float *G, double *cen,
-                               cudaStream_t st);
+                               float *planes, float *hi, float *lo, void *bh, void *bm, void *fh, void *fl, float *G,
+                               double *cen, cudaStream_t st);
 
 cudaError_t launch_rms_sweep_simt(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                   const FrameSetView &ref, int do_fit, CandLists<float> cl, cudaStream_t st);
 
 // tcgen05 sweep (rms_tc.cu).  *_hi / *_lo: TF32 split planes, same [n][3][A_pad] layout as planes.
-// mode: 1 = 3xTF32 (hi/lo fp32 planes), 2 = 1xTF32 (hi only), 3 = 3xBF16 (bh/bm bf16 planes).
+// mode: 1 = 3xTF32 (hi/lo fp32 planes), 2 = 1xTF32 (hi only), 3 = 3xBF16 (bh/bm bf16 planes),
+//       4 = 3xFP16 (fh/fl), 5 = 2xFP16 (fit fh only, reference fh/fl).
 // cl.H must be rms_tc_lists_per_segment() * n_seg (reference segments x column groups).
 cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *fit_hi, const void *fit_lo,
                                 long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,

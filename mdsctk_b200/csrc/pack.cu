@@ -5,9 +5,11 @@
 // layout of the contraction: AoS float[n][A][3] (nm) -> planes float[n][3][A_pad] holding
 // sqrt(m_a/M) * (x_a - c), G = sum (m_a/M)|x_a - c|^2, and the FP64 centroid for the re-score.
 // plus the TF32 hi/lo split planes of the tensor-core sweep.
-// One warp per frame; HBM-bound: 12*A bytes read + 36*A_pad written per frame.
+// plus the BF16 and FP16 split planes.  One warp per frame; HBM-bound: 12*A bytes read +
+// 60*A_pad written per frame.
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace mdsctk {
 
@@ -23,7 +25,8 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
                                                           long long n, int A, int A_pad,
                                                           float *__restrict__ planes, float *__restrict__ hi,
                                                           float *__restrict__ lo, __nv_bfloat16 *__restrict__ bh,
-                                                          __nv_bfloat16 *__restrict__ bm, float *__restrict__ G,
+                                                          __nv_bfloat16 *__restrict__ bm, __half *__restrict__ fh,
+                                                          __half *__restrict__ fl, float *__restrict__ G,
                                                           double *__restrict__ cen)
 {
     const int lane = threadIdx.x & 31;
@@ -73,6 +76,15 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
                 bm[pbase + d * A_pad + a] = __float2bfloat16_rn(o[d] - __bfloat162float(h));
             }
         }
+        if (fh) {  // FP16 split of kRmsHalfScale * x: fh + fl carries 22 bits (fl is exact in fp32 before rounding)
+            const float o[3] = {ox * kRmsHalfScale, oy * kRmsHalfScale, oz * kRmsHalfScale};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const __half h = __float2half_rn(o[d]);
+                fh[pbase + d * A_pad + a] = h;
+                fl[pbase + d * A_pad + a] = __float2half_rn(o[d] - __half2float(h));
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
@@ -83,13 +95,14 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
 }
 
 cudaError_t launch_pack_frames(const float *raw, const double *wnorm, long long n, int A, int A_pad, float *planes,
-                               float *hi, float *lo, void *bh, void *bm, float *G, double *cen, cudaStream_t st)
+                               float *hi, float *lo, void *bh, void *bm, void *fh, void *fl, float *G, double *cen, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
     const int warps = 8;
     const unsigned grid = (unsigned)((n + warps - 1) / warps);
     pack_frames_kernel<<<grid, warps * 32, 0, st>>>(raw, wnorm, n, A, A_pad, planes, hi, lo, static_cast<__nv_bfloat16 *>(bh),
-                                                    static_cast<__nv_bfloat16 *>(bm), G, cen);
+                                                    static_cast<__nv_bfloat16 *>(bm), static_cast<__half *>(fh),
+                                                    static_cast<__half *>(fl), G, cen);
     return cudaGetLastError();
 }
 

@@ -21,6 +21,10 @@
 //                  3xBF16: x ~= h + m (bf16), D += Ah*Bh + Ah*Bm + Am*Bh   kind::f16,  K=16, 32 atoms/stage
 //                  3xTF32: x ~= h + l (tf32), D += Ah*Bh + Ah*Bl + Al*Bh   kind::tf32, K=8,  16 atoms/stage
 //                  1xTF32: D += Ah*Bh only (coarse filter).
+//                  3xFP16: as 3xBF16 on an fp16 split of 64 x (22 bits kept instead of 16)
+//                  2xFP16: D += Ah*Bh + Ah*Bl, fit operand rounded to fp16 (11 bits): two MMAs and
+//                          half the fit-operand traffic; its noise is linear in the reference frame,
+//                          so near neighbours of a row share it (the certificate only needs the spread)
 //   accumulators TMEM of each CTA: its 128 fit rows x 3 regions of 144 fp32 columns (432 of 512);
 //                TMEM lane = fit frame, so an epilogue thread reads the nine S values of ITS fit row
 //                with tcgen05.ld (no shuffles), bounds RMSD^2 from below (Frobenius bound, then QCP
@@ -45,23 +49,35 @@ namespace tc {
 constexpr int TQ = 128;                       // fit frames per CTA
 constexpr int TR = 48;                        // reference frames per pass (24 loaded by each CTA)
 constexpr int TRH = TR / 2;
-constexpr int NST = 3;
 constexpr int ROW_BYTES = 64;                 // one operand row per stage (SWIZZLE_64B)
 constexpr int UMMA_M = 2 * TQ;                // 256 across the pair
 constexpr int UMMA_N = 3 * TR;                // 144
 constexpr int A_TILE = TQ * ROW_BYTES;        // 8192 B : one plane of the CTA's fit tile
 constexpr int A_PART = 3 * A_TILE;            // 24576 B: x|y|z planes of one split part
 constexpr int B_PART = 3 * TRH * ROW_BYTES;   // 4608 B : this CTA's 72 of the 144 reference operand rows
-constexpr int OFF_AHI = 0;
-constexpr int OFF_ALO = A_PART;
-constexpr int OFF_BHI = 2 * A_PART;
-constexpr int OFF_BLO = 2 * A_PART + B_PART;
-constexpr int STAGE_BYTES = 2 * A_PART + 2 * B_PART;   // 58368
+constexpr int MAX_NST = 6;
+constexpr int STATIC_SMEM = 20 * 1024;        // bound on the kernel's static shared memory (checked at launch)
+
+// MODE: 1 = 3xTF32, 2 = 1xTF32, 3 = 3xBF16, 4 = 3xFP16, 5 = 2xFP16 (fit operand: hi part only)
+template <int MODE> struct Mode {
+    static constexpr bool K16 = MODE >= 3;                         // 16-bit operands: K = 16 per MMA, 32 atoms per stage
+    static constexpr int FMT = MODE == 3 ? 1 : (MODE >= 4 ? 0 : 2); // instruction-descriptor operand format
+    static constexpr bool A_LO = MODE == 1 || MODE == 3 || MODE == 4;
+    static constexpr bool B_LO = MODE != 2;
+    static constexpr int OFF_AHI = 0;
+    static constexpr int OFF_ALO = A_PART;
+    static constexpr int OFF_BHI = (A_LO ? 2 : 1) * A_PART;
+    static constexpr int OFF_BLO = OFF_BHI + B_PART;
+    static constexpr int STAGE_BYTES = OFF_BHI + (B_LO ? 2 : 1) * B_PART;   // 58368 / 33792 / 29184
+    static constexpr int NST_FIT = (227 * 1024 - STATIC_SMEM - 1024) / STAGE_BYTES;
+    static constexpr int NST = NST_FIT < MAX_NST ? NST_FIT : MAX_NST;       // 3 / 6 / 6
+    static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;             // + alignment slack
+    static constexpr float SCALE = MODE >= 4 ? kRmsHalfScale * kRmsHalfScale : 1.0f;   // accumulators hold SCALE * S
+};
 constexpr int SUBS = 4;                       // epilogue warps per TMEM lane quarter
 constexpr int EPI_WARPS = 4 * SUBS;           // 16
 constexpr int NTHR = 64 + EPI_WARPS * 32;     // 576
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;   // + alignment slack
 constexpr int SUBW = TR / SUBS;               // 12 reference columns per epilogue warp
 constexpr int EB = 4;                         // pairs per lane and epilogue batch
 constexpr int MERGE_EVERY = 4;                // passes between quarter-wide list merges (power of two)
@@ -257,7 +273,9 @@ struct TcArgs {
     long long *prof;            // MDSCTK_TC_PROF=1: [grid][8] clock sums (see launch_rms_sweep_tc)
 };
 
-// MODE: 1 = 3xTF32, 2 = 1xTF32, 3 = 3xBF16.  Launched as clusters of 2 CTAs.
+// Launched as clusters of 2 CTAs.  With the FP16 modes everything downstream of the accumulators
+// (E0, thresholds, Newton iterates) is kept in units of SCALE nm^2 and converted when a candidate
+// is stored.
 template <int MODE>
 __global__ void __launch_bounds__(tc::NTHR, 1)
 rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
@@ -265,15 +283,19 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     TcArgs a)
 {
     using namespace tc;
-    constexpr bool BF16 = MODE == 3;
-    constexpr bool SPLIT = MODE != 2;
+    using MD = Mode<MODE>;
+    constexpr bool BF16 = MD::K16;                     // 16-bit operand kinds (bf16 / fp16) share kind::f16
+    constexpr bool A_LO = MD::A_LO, B_LO = MD::B_LO;
+    constexpr int NST = MD::NST, STAGE_BYTES = MD::STAGE_BYTES;
+    constexpr int OFF_AHI = MD::OFF_AHI, OFF_ALO = MD::OFF_ALO, OFF_BHI = MD::OFF_BHI, OFF_BLO = MD::OFF_BLO;
+    constexpr float SC = MD::SCALE, INV_SC = 1.0f / MD::SCALE;
     constexpr int KC = BF16 ? 32 : 16;                 // atoms per stage (64-byte rows)
     constexpr int KSTEPS = 2;                          // UMMA_K = 32 bytes; two per 64-byte row
-    constexpr uint32_t IDESC = umma_idesc(BF16 ? 1 : 2, UMMA_M, UMMA_N);
-    constexpr uint32_t STAGE_TX = 2u * (SPLIT ? 2 : 1) * (A_PART + B_PART);   // both CTAs' bytes land on the leader's barrier
+    constexpr uint32_t IDESC = umma_idesc(MD::FMT, UMMA_M, UMMA_N);
+    constexpr uint32_t STAGE_TX = 2u * STAGE_BYTES;    // both CTAs' bytes land on the leader's barrier
 
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_tmem_full, bar_tmem_empty;
+    __shared__ __align__(8) uint64_t bar_full[MAX_NST], bar_empty[MAX_NST], bar_tmem_full, bar_tmem_empty;
     __shared__ uint32_t s_tmem_base;
     __shared__ unsigned s_hist[EPI_WARPS][256];
     __shared__ int s_cnt[EPI_WARPS][32];
@@ -356,10 +378,8 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                             // one box = 64 bytes of atoms x rows frames x 3 planes, landing as [plane][frame][atoms]
                             tma_load_3d_2sm(st + OFF_AHI, &map_q_hi, full_leader, kc * KC, q0, 0, pol_a);
                             tma_load_3d_2sm(st + OFF_BHI, &map_r_hi, full_leader, kc * KC, r0, 0, pol_b);
-                            if constexpr (SPLIT) {
-                                tma_load_3d_2sm(st + OFF_ALO, &map_q_lo, full_leader, kc * KC, q0, 0, pol_a);
-                                tma_load_3d_2sm(st + OFF_BLO, &map_r_lo, full_leader, kc * KC, r0, 0, pol_b);
-                            }
+                            if constexpr (A_LO) tma_load_3d_2sm(st + OFF_ALO, &map_q_lo, full_leader, kc * KC, q0, 0, pol_a);
+                            if constexpr (B_LO) tma_load_3d_2sm(st + OFF_BLO, &map_r_lo, full_leader, kc * KC, r0, 0, pol_b);
                         }
                     }
                     __syncwarp();
@@ -410,9 +430,9 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                                     const uint32_t d = tmem_u + p * UMMA_N;
                                     const uint64_t ahi = umma_desc_sw64(sa + OFF_AHI + p * A_TILE + koff);
                                     tc_mma2<BF16>(d, ahi, bhi, IDESC, (kc | ks) != 0);
-                                    if constexpr (SPLIT) {
+                                    if constexpr (B_LO) tc_mma2<BF16>(d, ahi, blo, IDESC, 1);
+                                    if constexpr (A_LO) {
                                         const uint64_t alo = umma_desc_sw64(sa + OFF_ALO + p * A_TILE + koff);
-                                        tc_mma2<BF16>(d, ahi, blo, IDESC, 1);
                                         tc_mma2<BF16>(d, alo, bhi, IDESC, 1);
                                     }
                                 }
@@ -473,8 +493,9 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     d2 = fmaxf(2.0f * (e0 - x1), 0.0f);
                 } else {
                     QcpCoef c; c.c2 = q_c2[lane]; c.c1 = q_c1[lane]; c.c0 = q_c0[lane];
-                    d2 = qcp_refine(c, e0, e0, x1, tau_r);
+                    d2 = qcp_refine(c, e0, e0, x1, SC * tau_r);
                 }
+                d2 *= INV_SC;                         // accumulator units -> nm^2 (exact power of two)
                 if (d2 < tau_r) {
                     const int pos = atomicAdd(&wcnt[l], 1);
                     if (pos < SUB_APP) {
@@ -556,7 +577,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             const long long row0 = qt * UMMA_M + rank * TQ;      // first fit row of this CTA within the query range
             const long long qrow = row0 + row_in_tile;
             const bool qvalid = qrow < a.n_q;
-            const float hgq = 0.5f * a.q_G[a.q_begin + (qvalid ? qrow : a.n_q - 1)];
+            const float hgq = (0.5f * SC) * a.q_G[a.q_begin + (qvalid ? qrow : a.n_q - 1)];   // accumulator units
             lbase0 = ((size_t)(row0 + quarter * 32) * a.cl.H + seg) * a.cl.cap;
             wcnt[lane] = 0;
             if (sub == 0) {
@@ -578,7 +599,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 tc_fence_after();
                 const long long tp1 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                 long long tp2 = tp1;
-                const float tau = *reinterpret_cast<volatile float *>(&s_tau[row_in_tile]);
+                const float tau = SC * *reinterpret_cast<volatile float *>(&s_tau[row_in_tile]);   // accumulator units
                 const float htau = 0.5f * tau;
                 const float ge[SUBW] = {gv[0].x, gv[0].y, gv[0].z, gv[0].w, gv[1].x, gv[1].y, gv[1].z, gv[1].w,
                                         gv[2].x, gv[2].y, gv[2].z, gv[2].w};
@@ -602,11 +623,11 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                         for (int c = 0; c < 9; ++c)
 #pragma unroll
                             for (int j = 0; j < EB; ++j)
-                                a.debug_tile[(size_t)row_in_tile * (9 * TR) + c * TR + sub * SUBW + h + j] = sv[c][j];
+                                a.debug_tile[(size_t)row_in_tile * (9 * TR) + c * TR + sub * SUBW + h + j] = sv[c][j] * INV_SC;
                     }
                     float e0[EB];
 #pragma unroll
-                    for (int j = 0; j < EB; ++j) e0[j] = fmaf(0.5f, ge[h + j], hgq);
+                    for (int j = 0; j < EB; ++j) e0[j] = fmaf(0.5f * SC, ge[h + j], hgq);
                     if (a.dbg & 1) {
                         float acc = 0.f;
 #pragma unroll
@@ -699,16 +720,18 @@ static EncodeTiledFn get_encode()
 
 // planes[n][3][A_pad] as a 3-D tensor ordered (atom, frame, plane); box = 64 bytes of atoms x `rows`
 // frames x 3 planes, so one TMA op lands the three plane tiles back to back as [plane][frame][atoms].
-static bool make_plane_map(CUtensorMap *m, const void *planes, long long n, int A_pad, int rows, bool bf16)
+static bool make_plane_map(CUtensorMap *m, const void *planes, long long n, int A_pad, int rows, int mode)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
-    const int esz = bf16 ? 2 : 4;
+    const int esz = mode >= 3 ? 2 : 4;
+    const CUtensorMapDataType dt = mode == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : (mode >= 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
     cuuint64_t dims[3] = {(cuuint64_t)A_pad, (cuuint64_t)n, 3};
     cuuint64_t strides[2] = {(cuuint64_t)A_pad * 3 * esz, (cuuint64_t)A_pad * esz};
     cuuint32_t box[3] = {(cuuint32_t)(tc::ROW_BYTES / esz), (cuuint32_t)rows, 3};
     cuuint32_t estr[3] = {1, 1, 1};
-    return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(planes),
+    return enc(m, dt, 3, const_cast<void *>(planes),
                dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -740,14 +763,18 @@ template <int M>
 static cudaError_t launch_tc_mode(const CUtensorMap &mq_hi, const CUtensorMap &mq_lo, const CUtensorMap &mr_hi,
                                   const CUtensorMap &mr_lo, const TcArgs &a, long long n_items, int n_sms, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(rms_sweep_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(rms_sweep_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Mode<M>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, rms_sweep_tc_kernel<M>);
+    if (e == cudaSuccess && fa.sharedSizeBytes > (size_t)tc::STATIC_SMEM) e = cudaErrorInvalidConfiguration;
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(tc::NTHR); cfg.dynamicSmemBytes = tc::SMEM_BYTES; cfg.stream = st;
+    cfg.blockDim = dim3(tc::NTHR); cfg.dynamicSmemBytes = tc::Mode<M>::SMEM_BYTES; cfg.stream = st;
     int max_pairs = n_sms / 2;
     cfg.gridDim = dim3((unsigned)(max_pairs * 2));
     int q = 0;
@@ -766,12 +793,11 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
 {
     if (n_fit <= 0) return cudaSuccess;
     if (cl.H != n_seg || cl.cap < cl.keep + tc::SUBS * tc::SUB_APP) return cudaErrorInvalidValue;
-    const bool bf16 = mode == 3;
     CUtensorMap mq_hi, mq_lo, mr_hi, mr_lo;
-    if (!make_plane_map(&mq_hi, fit_hi, fit.n, fit.A_pad, tc::TQ, bf16) ||
-        !make_plane_map(&mq_lo, fit_lo, fit.n, fit.A_pad, tc::TQ, bf16) ||
-        !make_plane_map(&mr_hi, ref_hi, ref.n, ref.A_pad, tc::TRH, bf16) ||
-        !make_plane_map(&mr_lo, ref_lo, ref.n, ref.A_pad, tc::TRH, bf16))
+    if (!make_plane_map(&mq_hi, fit_hi, fit.n, fit.A_pad, tc::TQ, mode) ||
+        !make_plane_map(&mq_lo, fit_lo, fit.n, fit.A_pad, tc::TQ, mode) ||
+        !make_plane_map(&mr_hi, ref_hi, ref.n, ref.A_pad, tc::TRH, mode) ||
+        !make_plane_map(&mr_lo, ref_lo, ref.n, ref.A_pad, tc::TRH, mode))
         return cudaErrorInvalidValue;
     TcArgs a;
     a.q_G = fit.G; a.r_G = ref.G; a.q_begin = fit_begin; a.n_q = n_fit; a.n_r = ref.n;
@@ -795,6 +821,8 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
     case 1: e = launch_tc_mode<1>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
     case 2: e = launch_tc_mode<2>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
     case 3: e = launch_tc_mode<3>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
+    case 4: e = launch_tc_mode<4>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
+    case 5: e = launch_tc_mode<5>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
     default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

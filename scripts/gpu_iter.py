@@ -14,16 +14,19 @@ k1 = int(os.environ.get("ITER_K1", "33"))
 xyz = synth.traj_frames(n, 300, int(os.environ.get("ITER_BASINS", "16")))
 mass = synth.traj_masses(300)
 ctx = mdsctk_b200.KnnContext(0)
-ctx.set_option("rms_kernel", int(os.environ.get("ITER_KERNEL", "3")))
 ctx.rms_set_reference(xyz, mass)
-for dbg in os.environ.get("ITER_DBG", "0 1").split():
+for spec in os.environ.get("ITER_DBG", "0 1").split():
+    kern, _, dbg = spec.rpartition(":")
+    kern = int(kern) if kern else int(os.environ.get("ITER_KERNEL", "3"))
+    ctx.set_option("rms_kernel", kern)
     os.environ["MDSCTK_TC_DEBUG"] = dbg
     try:
         for rep in range(int(os.environ.get("ITER_REPS", "2"))):
             ctx.rms_query(k1, fetch=False)
         st = ctx.stats()
-        print("dbg", dbg, {k: (round(st[k], 3) if isinstance(st[k], float) else st[k]) for k in
-                           ("ms_sweep", "ms_rescore", "ms_fallback", "fallback_rows", "lists_per_row", "k_keep", "max_filter_spread")},
+        print("kernel", kern, "dbg", dbg, {k: (round(st[k], 3) if isinstance(st[k], float) else st[k]) for k in
+                           ("ms_sweep", "ms_rescore", "ms_fallback", "fallback_rows", "lists_per_row", "k_keep", "rescored_max")},
+              "spread %.2e err %.2e eps %.2e" % (st["max_filter_spread"], st["max_filter_err"], st["cert_eps"]),
               "pairs/s %.3e" % (n * n / (st["ms_sweep"] + st["ms_rescore"] + st["ms_fallback"]) * 1e3), flush=True)
     except Exception as e:  # noqa: BLE001
         print("dbg", dbg, "FAILED", e, flush=True)

@@ -170,7 +170,11 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
     }
     __syncthreads();
 
-    const double eps = a.eps_scale * 0.5 * (gq + (double)a.g_ref_max);
+    // Noise bound: eps_scale * E0 of the pair.  A pair that could still enter the top k1 has
+    // RMSD^2 <= d2_k + margin, and RMSD >= |sqrt(G_q) - sqrt(G_r)| (both frames centred), so its
+    // G_r <= (sqrt(G_q) + sqrt(d2_k + margin))^2 -- usually far below the largest G of the set.
+    const double eps_max = a.eps_scale * 0.5 * (gq + (double)a.g_ref_max);
+    double eps = eps_max;
     int done = 0;
     bool certified = false;
     while (done < total) {
@@ -225,8 +229,13 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
             const double spread = dec(s_emax) - dec(s_emin);
             const float a_next = done < total ? fminf(u_apx[done], tau_row) : tau_row;
             bool ok = done >= k1;
+            if (ok) {
+                const double dk_nm = s_d[k1 - 1] * 0.1;                       // exact k1-th distance, nm
+                const double reach = sqrt(gq) + sqrt(dk_nm * dk_nm + 4.0 * eps_max);
+                eps = a.eps_scale * 0.5 * (gq + fmin((double)a.g_ref_max, reach * reach));
+            }
             if (ok && a_next != kInfF)  // a_next == inf: nothing was ever dropped, every pair has been re-scored
-                ok = 0.5 * spread <= eps && (double)__uint_as_float(s_dtil) + 2.0 * eps < (double)a_next;
+                ok = 0.5 * spread <= eps_max && (double)__uint_as_float(s_dtil) + 2.0 * eps < (double)a_next;
             s_ok = ok ? 1 : 0;
         }
         __syncthreads();

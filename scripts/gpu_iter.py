@@ -11,9 +11,14 @@ from mdsctk_b200 import synth
 
 n = int(os.environ.get("ITER_N", "100000"))
 k1 = int(os.environ.get("ITER_K1", "33"))
-xyz = synth.traj_frames(n, 300, int(os.environ.get("ITER_BASINS", "16")))
+xyz = synth.traj_frames(n, 300, int(os.environ.get("ITER_BASINS", "16")), int(os.environ.get("ITER_SEED", "20260117")))
+rows = int(os.environ.get("ITER_ROWS", "0"))
+if os.environ.get("ITER_SLACK"):
+    pass
 mass = synth.traj_masses(300)
 ctx = mdsctk_b200.KnnContext(0)
+if os.environ.get("ITER_SLACK"):
+    ctx.set_option("slack", int(os.environ["ITER_SLACK"]))
 ctx.rms_set_reference(xyz, mass)
 for spec in os.environ.get("ITER_DBG", "0 1").split():
     kern, _, dbg = spec.rpartition(":")
@@ -22,12 +27,12 @@ for spec in os.environ.get("ITER_DBG", "0 1").split():
     os.environ["MDSCTK_TC_DEBUG"] = dbg
     try:
         for rep in range(int(os.environ.get("ITER_REPS", "2"))):
-            ctx.rms_query(k1, fetch=False)
+            ctx.rms_query(k1, fetch=False, fit_range=(int(os.environ.get("ITER_ROW0", "0")), rows) if rows else None)
         st = ctx.stats()
         print("kernel", kern, "dbg", dbg, {k: (round(st[k], 3) if isinstance(st[k], float) else st[k]) for k in
                            ("ms_sweep", "ms_rescore", "ms_fallback", "fallback_rows", "lists_per_row", "k_keep", "rescored_max")},
               "spread %.2e err %.2e eps %.2e" % (st["max_filter_spread"], st["max_filter_err"], st["cert_eps"]),
-              "pairs/s %.3e" % (n * n / (st["ms_sweep"] + st["ms_rescore"] + st["ms_fallback"]) * 1e3), flush=True)
+              "pairs/s %.3e" % ((rows or n) * n / (st["ms_sweep"] + st["ms_rescore"] + st["ms_fallback"]) * 1e3), flush=True)
     except Exception as e:  # noqa: BLE001
         print("dbg", dbg, "FAILED", e, flush=True)
         break

@@ -109,6 +109,13 @@ struct mdsctk_knn_ctx {
     long long dn_ref = 0;
     int ddim = 0;
     bool have_dref = false, dstats_dirty = true;
+    // tensor-core filter state of the vector path (data_tc.cu)
+    DevBuf dt_ref_hi, dt_ref_lo, dt_ref_norm, dt_fit_hi, dt_fit_lo, dt_fit_norm;
+    DevBuf fb_rows, fb_key, fb_idx, fb_cnt, fb_tau, fb_dist, fb_oidx;
+    bool dpack_dirty = true;
+    double dt_scale = 1.0, dt_ref_maxabs = 0.0;
+    float dt_rnorm_max = 0.f;
+    int data_kernel = -1;      // -1 auto, 0 exact FP64 sweep, 1 tensor-core filter + exact re-score
     // scratch + results
     DevBuf cand_key, cand_idx, cand_cnt, cand_tau, flags, bad_rows, scalars, rows_buf;
     DevBuf out_dist, out_idx, debug_tile, row_tau;
@@ -332,6 +339,137 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
     return 0;
 }
 
+// Euclidean knn_data through the tensor-core filter (data_tc.cu): pack -> sweep -> exact FP64 re-score
+// with certificate -> exact FP64 sweep of the rows that could not be certified.
+int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1,
+                double *out_dist, int *out_idx)
+{
+    mdsctk_knn_stats &S = ctx->stats;
+    const int dim = ctx->ddim, D_pad = data_tc_pad_dim(dim);
+    const long long n_ref = ctx->dn_ref;
+    CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
+    ctx->tm.start(ctx->st);
+    if (ctx->dpack_dirty) {
+        CK(launch_data_maxabs(ctx->d_ref.as<double>(), (size_t)n_ref * dim, ctx->scalars.as<double>(), ctx->st), "maxabs");
+        CK(cudaMemcpyAsync(&ctx->dt_ref_maxabs, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, ctx->st), "D2H maxabs");
+        CK(cudaStreamSynchronize(ctx->st), "sync maxabs");
+        // power-of-two scale that puts the largest reference value near 1024 (fp16 keeps 11 bits below it)
+        int e = 0;
+        if (ctx->dt_ref_maxabs > 0.0 && std::isfinite(ctx->dt_ref_maxabs)) e = 10 - (int)std::ceil(std::log2(ctx->dt_ref_maxabs));
+        e = std::max(-100, std::min(100, e));
+        ctx->dt_scale = std::ldexp(1.0, e);
+        CK(ctx->dt_ref_hi.reserve((size_t)n_ref * D_pad * 2), "cudaMalloc(ref hi)");
+        CK(ctx->dt_ref_lo.reserve((size_t)n_ref * D_pad * 2), "cudaMalloc(ref lo)");
+        CK(ctx->dt_ref_norm.reserve((size_t)(n_ref + 512) * 4), "cudaMalloc(ref norm)");
+        CK(cudaMemsetAsync(ctx->dt_ref_norm.p, 0, (size_t)(n_ref + 512) * 4, ctx->st), "memset ref norm");
+        CK(launch_data_pack(ctx->d_ref.as<double>(), n_ref, dim, D_pad, ctx->dt_scale, ctx->dt_ref_hi.p, ctx->dt_ref_lo.p,
+                            ctx->dt_ref_norm.as<float>(), ctx->st), "data_pack(ref)");
+        CK(launch_max_float(ctx->dt_ref_norm.as<float>(), n_ref, ctx->scalars.as<float>() + 4, ctx->st), "max(norm)");
+        CK(cudaMemcpyAsync(&ctx->dt_rnorm_max, ctx->scalars.as<float>() + 4, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H max(norm)");
+        CK(cudaStreamSynchronize(ctx->st), "sync max(norm)");
+        ctx->dpack_dirty = false;
+        S.launches += 3;
+    }
+    const void *fit_hi, *fit_lo;
+    const float *fit_norm;
+    if (fit_is_ref) {
+        fit_hi = ctx->dt_ref_hi.as<uint16_t>() + (size_t)fit_begin * D_pad;
+        fit_lo = ctx->dt_ref_lo.as<uint16_t>() + (size_t)fit_begin * D_pad;
+        fit_norm = ctx->dt_ref_norm.as<float>() + fit_begin;
+    } else {
+        double fit_max = 0.0;
+        CK(launch_data_maxabs(d_fit, (size_t)n_fit * dim, ctx->scalars.as<double>(), ctx->st), "maxabs(fit)");
+        CK(cudaMemcpyAsync(&fit_max, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, ctx->st), "D2H maxabs");
+        CK(cudaStreamSynchronize(ctx->st), "sync maxabs");
+        if (!(fit_max * ctx->dt_scale < 3.0e4)) return 1;   // would overflow fp16: the caller takes the exact path
+        CK(ctx->dt_fit_hi.reserve((size_t)n_fit * D_pad * 2), "cudaMalloc(fit hi)");
+        CK(ctx->dt_fit_lo.reserve((size_t)n_fit * D_pad * 2), "cudaMalloc(fit lo)");
+        CK(ctx->dt_fit_norm.reserve((size_t)(n_fit + 512) * 4), "cudaMalloc(fit norm)");
+        CK(launch_data_pack(d_fit, n_fit, dim, D_pad, ctx->dt_scale, ctx->dt_fit_hi.p, ctx->dt_fit_lo.p,
+                            ctx->dt_fit_norm.as<float>(), ctx->st), "data_pack(fit)");
+        fit_hi = ctx->dt_fit_hi.p; fit_lo = ctx->dt_fit_lo.p; fit_norm = ctx->dt_fit_norm.as<float>();
+        S.launches += 2;
+    }
+    S.ms_pack += ctx->tm.stop(ctx->st);
+
+    const long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(32, k1 / 2);
+    const int keep = (int)(((long long)k1 + slack + 7) / 8 * 8);
+    const int cap = data_tc_list_stride(keep);
+    const int n_seg = data_tc_choose_segments(n_fit, n_ref, ctx->n_sms);
+    S.k_keep = keep; S.lists_per_row = n_seg;
+    if ((size_t)dim * 8 + (size_t)keep * n_seg * 2 * 28 > 200 * 1024) return 1;   // re-score working set: exact path instead
+    CandLists<float> cl;
+    CK(ctx->cand_key.reserve((size_t)n_fit * n_seg * cap * 4), "cudaMalloc(cand_key)");
+    CK(ctx->cand_idx.reserve((size_t)n_fit * n_seg * cap * 4), "cudaMalloc(cand_idx)");
+    CK(ctx->cand_cnt.reserve((size_t)n_fit * n_seg * 4), "cudaMalloc(cand_cnt)");
+    CK(ctx->cand_tau.reserve((size_t)n_fit * n_seg * 8), "cudaMalloc(cand_tau)");
+    CK(ctx->flags.reserve((size_t)n_fit * 4), "cudaMalloc(flags)");
+    CK(ctx->bad_rows.reserve((size_t)n_fit * 4), "cudaMalloc(bad_rows)");
+    CK(ctx->row_tau.reserve((size_t)n_fit * 4), "cudaMalloc(row_tau)");
+    CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
+    CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
+    ctx->out_rows = n_fit; ctx->out_k1 = k1;
+    cl.key = ctx->cand_key.as<float>(); cl.idx = ctx->cand_idx.as<int>(); cl.cnt = ctx->cand_cnt.as<int>();
+    cl.tau = ctx->cand_tau.as<float>(); cl.cap = cap; cl.keep = keep; cl.H = n_seg;
+    CK(cudaMemsetAsync(ctx->scalars.p, 0, 64, ctx->st), "memset scalars");
+    double *d_err = ctx->scalars.as<double>() + 1;
+    int *d_nbad = ctx->scalars.as<int>() + 8;
+
+    ctx->tm.start(ctx->st);
+    CK(launch_fill_u32(ctx->row_tau.p, (size_t)n_fit, 0x7f800000u, ctx->st), "fill row_tau");
+    CK(launch_data_sweep_tc(fit_hi, fit_lo, fit_norm, n_fit, fit_is_ref ? fit_begin : -1, ctx->dt_ref_hi.p, ctx->dt_ref_lo.p,
+                            ctx->dt_ref_norm.as<float>(), n_ref, D_pad, ctx->dt_scale, n_seg, cl, ctx->row_tau.as<float>(),
+                            ctx->n_sms, ctx->st), "data_sweep_tc");
+    S.ms_sweep = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "data tensor sweep kernel");
+    S.launches += 2;
+
+    // filter noise: fp32 accumulation of 3 * dim products and the three-term key, relative to |x|^2 + |y|^2
+    // (measured half-spread at dim 512: 2.1e-6; the certificate re-checks the observed spread on every row)
+    const double eps_rel = 2.0e-6 * std::sqrt((double)std::max(dim, 64) / 64.0) * (double)ctx->cert_scale_ppm * 1e-6;
+    S.cert_eps = eps_rel * 2.0 * (double)ctx->dt_rnorm_max / (ctx->dt_scale * ctx->dt_scale);
+    ctx->tm.start(ctx->st);
+    CK(launch_data_rescore(d_fit, ctx->d_ref.as<double>(), n_fit, dim, k1, cl, eps_rel, fit_norm, ctx->dt_scale,
+                           ctx->dt_rnorm_max, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(), d_err,
+                           d_nbad, ctx->bad_rows.as<int>(), ctx->st), "data_rescore");
+    struct { double pad, err, spread, done_max; int nbad; } host_sc;
+    CK(cudaMemcpyAsync(&host_sc, ctx->scalars.p, sizeof(host_sc), cudaMemcpyDeviceToHost, ctx->st), "D2H scalars");
+    S.ms_rescore = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "data rescore kernel");
+    S.launches += 1;
+    S.max_filter_err = host_sc.err; S.max_filter_spread = host_sc.spread; S.rescored_max = (int)host_sc.done_max;
+    S.fallback_rows = host_sc.nbad;
+
+    if (host_sc.nbad > 0) {     // exact FP64 sweep of the uncertified rows (gathered), results scattered back
+        ctx->tm.start(ctx->st);
+        const int nb = host_sc.nbad;
+        const long long fslack = 8;
+        const int fkeep = (int)(((long long)k1 + fslack + 7) / 8 * 8);
+        const int fcap = (fkeep + 160 + 31) / 32 * 32;
+        CK(ctx->fb_rows.reserve((size_t)nb * dim * 8), "cudaMalloc(fb_rows)");
+        CK(ctx->fb_key.reserve((size_t)nb * fcap * 8), "cudaMalloc(fb_key)");
+        CK(ctx->fb_idx.reserve((size_t)nb * fcap * 4), "cudaMalloc(fb_idx)");
+        CK(ctx->fb_cnt.reserve((size_t)nb * 4), "cudaMalloc(fb_cnt)");
+        CK(ctx->fb_tau.reserve((size_t)nb * 8), "cudaMalloc(fb_tau)");
+        CK(ctx->fb_dist.reserve((size_t)nb * k1 * 8), "cudaMalloc(fb_dist)");
+        CK(ctx->fb_oidx.reserve((size_t)nb * k1 * 4), "cudaMalloc(fb_oidx)");
+        CK(launch_data_gather_rows(d_fit, ctx->bad_rows.as<int>(), nb, dim, ctx->fb_rows.as<double>(), ctx->st), "gather rows");
+        CandLists<double> fl;
+        fl.key = ctx->fb_key.as<double>(); fl.idx = ctx->fb_idx.as<int>(); fl.cnt = ctx->fb_cnt.as<int>();
+        fl.tau = ctx->fb_tau.as<double>(); fl.cap = fcap; fl.keep = fkeep; fl.H = 1;
+        CK(launch_data_sweep(ctx->fb_rows.as<double>(), nullptr, nb, ctx->d_ref.as<double>(), nullptr, n_ref, dim,
+                             MDSCTK_KNN_EUCLIDEAN, fl, ctx->st), "data_sweep(fallback)");
+        CK(launch_data_finalize(fl, nb, k1, ctx->fb_dist.as<double>(), ctx->fb_oidx.as<int>(), ctx->st), "data_finalize(fallback)");
+        CK(launch_data_scatter_out(ctx->fb_dist.as<double>(), ctx->fb_oidx.as<int>(), ctx->bad_rows.as<int>(), nb, k1,
+                                   ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->st), "scatter rows");
+        S.ms_fallback = ctx->tm.stop(ctx->st);
+        CK(cudaGetLastError(), "data fallback kernels");
+        S.launches += 4;
+    }
+    if (out_dist || out_idx) return mdsctk_knn_fetch(ctx, out_dist, out_idx);
+    return 0;
+}
+
 int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1,
              int metric, double *out_dist, int *out_idx)
 {
@@ -344,6 +482,15 @@ int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long lon
     S.ms_sweep = S.ms_rescore = S.ms_fallback = S.ms_download = 0;
     S.pairs = n_fit * ctx->dn_ref; S.launches = 0; S.fallback_rows = 0; S.max_filter_err = 0; S.cert_eps = 0;
     const int dim = ctx->ddim;
+    S.max_filter_spread = 0; S.rescored_max = 0; S.lists_per_row = 1;
+    // tensor-core filter: Euclidean metric; by default only where the contraction is worth staging
+    const bool want_tc = metric == MDSCTK_KNN_EUCLIDEAN &&
+                         (ctx->data_kernel == 1 ||
+                          (ctx->data_kernel < 0 && dim >= 8 && (double)n_fit * (double)ctx->dn_ref >= 2.5e7));
+    if (want_tc) {
+        const int rc = data_run_tc(ctx, d_fit, fit_is_ref, fit_begin, n_fit, k1, out_dist, out_idx);
+        if (rc != 1) return rc;        // 1: not applicable to this input -> exact sweep below
+    }
     const double *fit_stats = nullptr, *ref_stats = nullptr;
     if (metric == MDSCTK_KNN_CORRELATION) {
         if (ctx->dstats_dirty) {
@@ -470,6 +617,9 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
     } else if (!strcmp(key, "cert_scale_ppm")) {
         if (value < 0) return fail(ctx, MDSCTK_KNN_EINVAL, "cert_scale_ppm must be >= 0");
         ctx->cert_scale_ppm = value;
+    } else if (!strcmp(key, "data_kernel")) {
+        if (value < -1 || value > 1) return fail(ctx, MDSCTK_KNN_EINVAL, "data_kernel must be -1 (auto), 0 (exact) or 1 (tensor)");
+        ctx->data_kernel = (int)value;
     } else if (!strcmp(key, "debug_tile")) {
         ctx->debug_tile_on = value != 0;
     } else {
@@ -604,7 +754,7 @@ int mdsctk_knn_data_alloc_reference(mdsctk_knn_ctx *ctx, long long n_total, int 
     Bind b(ctx);
     ctx->have_dref = false;
     CK(ctx->d_ref.reserve((size_t)n_total * dim * 8), "cudaMalloc(reference rows)");
-    ctx->dn_ref = n_total; ctx->ddim = dim; ctx->have_dref = true; ctx->dstats_dirty = true;
+    ctx->dn_ref = n_total; ctx->ddim = dim; ctx->have_dref = true; ctx->dstats_dirty = true; ctx->dpack_dirty = true;
     ctx->stats.ms_upload = ctx->stats.ms_pack = 0;
     return 0;
 }
@@ -617,6 +767,7 @@ int mdsctk_knn_data_upload_shard(mdsctk_knn_ctx *ctx, const double *rows, long l
         return fail(ctx, MDSCTK_KNN_EINVAL, "shard outside the allocated reference set");
     Bind b(ctx);
     ctx->dstats_dirty = true;
+    ctx->dpack_dirty = true;
     if (n_rows == 0) return 0;
     ctx->tm.start(ctx->st);
     CK(cudaMemcpyAsync(ctx->d_ref.as<double>() + (size_t)row_offset * ctx->ddim, rows, (size_t)n_rows * ctx->ddim * 8,
@@ -635,6 +786,7 @@ int mdsctk_knn_data_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n
     dev_ptrs[0] = ctx->d_ref.p;
     bytes_per_row[0] = (size_t)ctx->ddim * 8;
     ctx->dstats_dirty = true;
+    ctx->dpack_dirty = true;
     return 0;
 }
 

@@ -79,10 +79,6 @@ __device__ __forceinline__ void load_fit_frame(double *wq, const float *raw_q, c
     }
 }
 
-__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v)
-{
-    atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
-}
 
 struct RescoreArgs {
     FrameSetView fit, ref;

@@ -34,6 +34,7 @@
 #include "common.cuh"
 #include "qcp.cuh"
 #include "select.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>
 #include <cstdio>
@@ -83,184 +84,6 @@ constexpr int EB = 4;                         // pairs per lane and epilogue bat
 constexpr int MERGE_EVERY = 4;                // passes between quarter-wide list merges (power of two)
 constexpr int SUB_APP = 2 * MERGE_EVERY * SUBW;   // 96: private append area per epilogue warp and row
 }  // namespace tc
-
-// ---------------------------------------------------------------- PTX wrappers ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, not hang the GPU.  try_wait suspends the thread in
-// hardware for up to the hint (ns) per poll, so the loop costs few issue slots.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag)
-{
-    uint32_t polls = 0;
-    while (true) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
-            : "memory");
-        if (ok) return;
-        if (++polls > 400000u) {
-            printf("rms_sweep_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x,
-                   parity);
-            __trap();
-        }
-    }
-}
-// Latency-critical variant for the MMA issuer: plain try_wait polling (no suspend hint).
-__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity, int tag)
-{
-    uint32_t polls = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++polls > 200000000u) {
-            printf("rms_sweep_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void quarter_sync(int quarter)
-{
-    asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-// CTA-pair copy: lands in THIS CTA's shared memory, completes on the mbarrier `bar_cluster_addr`
-// (a shared::cluster address; the leader's "full" barrier for both CTAs of the pair).  `policy` is
-// an L2 eviction-priority descriptor (kEvictLast for the fit tile, re-read every pass).
-constexpr uint64_t kEvictNormal = 0x1000000000000000ull, kEvictFirst = 0x12F0000000000000ull, kEvictLast = 0x14F0000000000000ull;
-__device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1,
-                                                int c2, uint64_t policy)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-        : "memory");
-}
-// shared::cluster address of the same variable in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank)
-{
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
-{
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-}
-// one lane of a converged warp (the others fall through); keeps the operands of the guarded
-// instruction in uniform registers instead of a per-lane "waterfall" loop
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// pair MMA bookkeeping: arrives on the mbarrier at the same offset in every CTA of `mask` once the
-// cta_group::2 MMAs issued so far are done
-__device__ __forceinline__ void tc_commit2_mc(uint64_t *bar, uint16_t mask)
-{
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"(mask)
-        : "memory");
-}
-// D[256 x N] (+)= A[256 x K] * B[N x K]^T over the CTA pair; descriptors are shared-memory offsets
-// valid in both CTAs, d_tmem likewise
-template <bool BF16>
-__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
-{
-    if constexpr (BF16) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-            : "memory");
-    }
-}
-// four consecutive accumulator columns of this thread's TMEM lane -> v[c][0..3] (valid after tc_wait_ld)
-__device__ __forceinline__ void tc_ld4(uint32_t taddr, float (&v)[9][4], int c)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v[c][0]), "=f"(v[c][1]), "=f"(v[c][2]), "=f"(v[c][3])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_64B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x 64 B = 512 B)
-//   [46,48) version=1 | [61,64) layout type 4 = SWIZZLE_64B
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr)
-{
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A/B format at [7,10)/[10,13)
-// (BF16 = 1, TF32 = 2), both K-major, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N)
-{
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 struct TcArgs {
     const float *q_G, *r_G;
@@ -700,29 +523,11 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 }
 
 // ---------------------------------------------------------------- host side ----
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-            qres != cudaDriverEntryPointSuccess)
-            return nullptr;
-        fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
 // planes[n][3][A_pad] as a 3-D tensor ordered (atom, frame, plane); box = 64 bytes of atoms x `rows`
 // frames x 3 planes, so one TMA op lands the three plane tiles back to back as [plane][frame][atoms].
 static bool make_plane_map(CUtensorMap *m, const void *planes, long long n, int A_pad, int rows, int mode)
 {
-    EncodeTiledFn enc = get_encode();
+    EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) return false;
     const int esz = mode >= 3 ? 2 : 4;
     const CUtensorMapDataType dt = mode == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16

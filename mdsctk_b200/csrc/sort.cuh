@@ -32,6 +32,12 @@ __device__ inline void block_bitonic_sort(double *d, int *ix, int n)
     }
 }
 
+// atomicMax on a non-negative double (its bit pattern orders like an unsigned integer)
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v)
+{
+    atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
 __device__ __forceinline__ int next_pow2(int v)
 {
     int p = 1;

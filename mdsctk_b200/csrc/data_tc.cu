@@ -471,7 +471,7 @@ struct DataRescoreArgs {
     double *err_stats;
 };
 
-constexpr int DRESCORE_ROUND = 64;
+constexpr int DRESCORE_ROUND = 128;   // upper bound of a round (one candidate per thread)
 
 __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
 {
@@ -526,7 +526,8 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
     int done = 0;
     bool certified = false;
     while (done < total) {
-        const int nb = min(DRESCORE_ROUND, total - done);
+        // first round: just enough candidates to fill the k-list; then 32 more at a time
+        const int nb = min(done == 0 ? min(DRESCORE_ROUND, (k1 + 31) / 32 * 32) : 32, total - done);
         if (threadIdx.x < nb) {
             const double *rv = a.ref + (size_t)u_i[done + threadIdx.x] * D;
             double sum = 0.0;

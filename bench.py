@@ -132,6 +132,24 @@ def cpu_baseline_sample(wl, rows=None):
                       f"rows x first {n_ref} reference frames of the same synthetic trajectory, k={wl['k']}, {dt:.1f} s"}
 
 
+def knn_data_sample(ctx):
+    """Second tool on the path (BASELINE.json config 5, reduced to fit the default run): Euclidean
+    knn_data on synthetic phi-psi sin/cos rows, k=64, through the same context; not part of `value`."""
+    from mdsctk_b200 import synth
+    n, dim, k1 = int(os.environ.get("BENCH_DATA_ROWS", 100_000)), 512, 65
+    rows = synth.phipsi_rows(n, dim, 64)
+    ctx.data_set_reference(rows)
+    for _ in range(2):
+        ctx.data_query(k1, fetch=False)
+    st = ctx.stats()
+    tot = st["ms_sweep"] + st["ms_rescore"] + st["ms_fallback"]
+    return {"metric": "knn_data Euclidean row pairs/sec (all-pairs kNN)", "value": n * n / tot * 1e3, "unit": "pairs/s",
+            "workload": f"synthetic phi-psi sin/cos rows {n} x {dim}, k=64 (C5 shape at reduced row count), 1 GPU",
+            "kernel": "data_sweep_tc_kernel (tcgen05 cta_group::2, 3xFP16 split) + exact FP64 re-score, bit-identical output",
+            "sweep_ms": st["ms_sweep"], "rescore_ms": st["ms_rescore"], "fallback_rows": st["fallback_rows"],
+            "sweep_tflops_algorithmic": n * n * 2 * dim / st["ms_sweep"] * 1e3 / 1e12}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the reference itself cannot be
     built here: needs libgromacs/Boost/BDB/ARPACK) on the host cores, bounded sample per step."""
@@ -329,6 +347,10 @@ def main():
                          "sweep_ms_per_step": sweep_ms / args.steps, "post_ms_per_step": post_ms / args.steps},
             "cpu_baseline": cpu_baseline_sample(wl),
         }
+        # SURVEY.md section 8d quotes the contraction roofline against the dense TF32 rate (= half the bf16 rate)
+        line["roofline"]["frac_of_tf32_rate"] = sweep_tflops / (peaks["tflops"] / 2.0) if st["rms_kernel"] >= 3 else None
+        if world == 1 and os.environ.get("BENCH_KNN_DATA", "1") == "1":
+            line["secondary"] = knn_data_sample(ctx)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

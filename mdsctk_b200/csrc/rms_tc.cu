@@ -416,7 +416,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 #pragma unroll
                 for (int j = 0; j < SUBW / 4; ++j) gv[j] = __ldg(reinterpret_cast<const float4 *>(a.r_G + min(rb, a.n_r & ~3LL)) + j);
                 const long long tp0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
-                if (lane == 0) mbar_wait(&bar_tmem_full, tph, 4);
+                if (lane == 0) { if (a.dbg & 128) mbar_wait_spin(&bar_tmem_full, tph, 4); else mbar_wait(&bar_tmem_full, tph, 4); }
                 tph ^= 1;
                 __syncwarp();
                 tc_fence_after();

@@ -140,6 +140,17 @@ int mdsctk_knn_data_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n
 int mdsctk_knn_data_query_range(mdsctk_knn_ctx *ctx, long long fit_begin, long long n_fit, int k1, int metric,
                                 double *out_dist, int *out_idx);
 
+/* ---- consumer of the kNN files: symmetric CSC matrix (make_sysparse.cpp:245-329) ----------------
+ * idx / dist: host, row-major [n][maxk] exactly as indices.dat / distances.dat hold them; only the
+ * first k entries of every row are used (make_sysparse's -n / --output-knn, make_sysparse.cpp:93-103).
+ * Edge (min(i,j), max(i,j)) -> distance; when both endpoints list each other the value written from
+ * the larger endpoint wins (the reference's Db::put overwrites in row order); self edges are dropped.
+ * build: fills pcol[n+1] (host) and *nnz; fetch: irow[nnz], val[nnz] (host), rows ascending per column --
+ * together the arrays make_sysparse writes after the leading int n (make_sysparse.cpp:310-329). */
+int mdsctk_knn_csc_build_sym(mdsctk_knn_ctx *ctx, const int *idx, const double *dist, long long n, int maxk, int k,
+                             int *pcol, long long *nnz);
+int mdsctk_knn_csc_fetch(mdsctk_knn_ctx *ctx, int *irow, double *val);
+
 /* Diagnostic: after set_option("debug_tile", 1) a tensor-core RMSD query also captures the raw
  * TMEM accumulators of (fit tile 0, reference tile 0): out[128][9][48] floats, S_ab of fit row q
  * against reference j at out[q][3*a+b][j]. */

@@ -116,6 +116,9 @@ struct mdsctk_knn_ctx {
     double dt_scale = 1.0, dt_ref_maxabs = 0.0;
     float dt_rnorm_max = 0.f;
     int data_kernel = -1;      // -1 auto, 0 exact FP64 sweep, 1 tensor-core filter + exact re-score
+    // CSC builder state (csc.cu)
+    DevBuf c_idx, c_dist, c_ints, c_key, c_val, c_irow, c_oval;
+    long long c_nnz = -1;
     // scratch + results
     DevBuf cand_key, cand_idx, cand_cnt, cand_tau, flags, bad_rows, scalars, rows_buf;
     DevBuf out_dist, out_idx, debug_tile, row_tau;
@@ -826,6 +829,69 @@ int mdsctk_knn_data_query(mdsctk_knn_ctx *ctx, const double *fit_rows, long long
        "H2D fit rows");
     ctx->stats.ms_upload += ctx->tm.stop(ctx->st);
     return data_run(ctx, ctx->d_fit.as<double>(), false, 0, n_fit, k1, metric, out_dist, out_idx);
+}
+
+/* ---------------------------------------------------------------- CSC builder ---- */
+int mdsctk_knn_csc_build_sym(mdsctk_knn_ctx *ctx, const int *idx, const double *dist, long long n, int maxk, int k,
+                             int *pcol, long long *nnz)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (!idx || !dist || !pcol || !nnz || n <= 0 || maxk <= 0 || k < 0 || k > maxk)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "csc_build_sym: bad arguments (need 0 <= k <= maxk, n > 0)");
+    if ((double)n * (double)std::max(k, 1) >= 2147483647.0)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "csc_build_sym: n*k must stay below 2^31 (int offsets, as in the reference)");
+    Bind b(ctx);
+    mdsctk_knn_stats &S = ctx->stats;
+    S.ms_upload = S.ms_sweep = S.ms_download = 0; S.launches = 0;
+    ctx->c_nnz = -1;
+    const size_t ne = (size_t)n * maxk, nk = (size_t)n * std::max(k, 1);
+    const size_t nscan = (size_t)n / 1024 + (size_t)n / (1024 * 1024) + 16;
+    CK(ctx->c_idx.reserve(ne * 4), "cudaMalloc(csc idx)");
+    CK(ctx->c_dist.reserve(ne * 8), "cudaMalloc(csc dist)");
+    CK(ctx->c_ints.reserve(((size_t)(n + 1) * 5 + nscan) * 4), "cudaMalloc(csc counters)");
+    CK(ctx->c_key.reserve(nk * 8), "cudaMalloc(csc keys)");
+    CK(ctx->c_val.reserve(nk * 8), "cudaMalloc(csc vals)");
+    CK(ctx->c_irow.reserve(nk * 4), "cudaMalloc(csc irow)");
+    CK(ctx->c_oval.reserve(nk * 8), "cudaMalloc(csc val)");
+    ctx->tm.start(ctx->st);
+    CK(cudaMemcpyAsync(ctx->c_idx.p, idx, ne * 4, cudaMemcpyHostToDevice, ctx->st), "H2D indices");
+    CK(cudaMemcpyAsync(ctx->c_dist.p, dist, ne * 8, cudaMemcpyHostToDevice, ctx->st), "H2D distances");
+    S.ms_upload = ctx->tm.stop(ctx->st);
+    int *ints = ctx->c_ints.as<int>();
+    int *cnt = ints, *cur = ints + (n + 1), *off = ints + 2 * (n + 1), *fin = ints + 3 * (n + 1), *d_pcol = ints + 4 * (n + 1);
+    int *scan_tmp = ints + 5 * (n + 1);
+    ctx->tm.start(ctx->st);
+    if (k > 0) {
+        CK(launch_csc_build_sym(ctx->c_idx.as<int>(), ctx->c_dist.as<double>(), n, maxk, k, cnt, cur, off, fin, d_pcol, scan_tmp,
+                                ctx->c_key.as<unsigned long long>(), ctx->c_val.as<double>(), ctx->c_irow.as<int>(),
+                                ctx->c_oval.as<double>(), ctx->st), "csc_build_sym");
+        S.launches = 11;
+    } else {
+        CK(cudaMemsetAsync(d_pcol, 0, (size_t)(n + 1) * 4, ctx->st), "memset pcol");
+    }
+    S.ms_sweep = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "csc kernels");
+    ctx->tm.start(ctx->st);
+    CK(cudaMemcpyAsync(pcol, d_pcol, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->st), "D2H pcol");
+    S.ms_download = ctx->tm.stop(ctx->st);
+    ctx->c_nnz = pcol[n];
+    *nnz = ctx->c_nnz;
+    S.pairs = (long long)n * k;
+    return 0;
+}
+
+int mdsctk_knn_csc_fetch(mdsctk_knn_ctx *ctx, int *irow, double *val)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (ctx->c_nnz < 0) return fail(ctx, MDSCTK_KNN_ESTATE, "csc_fetch: no matrix built");
+    if (ctx->c_nnz == 0) return 0;
+    if (!irow || !val) return fail(ctx, MDSCTK_KNN_EINVAL, "csc_fetch: NULL output");
+    Bind b(ctx);
+    ctx->tm.start(ctx->st);
+    CK(cudaMemcpyAsync(irow, ctx->c_irow.p, (size_t)ctx->c_nnz * 4, cudaMemcpyDeviceToHost, ctx->st), "D2H irow");
+    CK(cudaMemcpyAsync(val, ctx->c_oval.p, (size_t)ctx->c_nnz * 8, cudaMemcpyDeviceToHost, ctx->st), "D2H val");
+    ctx->stats.ms_download += ctx->tm.stop(ctx->st);
+    return 0;
 }
 
 int mdsctk_knn_debug_fetch_tile(mdsctk_knn_ctx *ctx, float *out)

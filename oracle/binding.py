@@ -48,6 +48,8 @@ def lib():
         L.oracle_rms_rows.argtypes = [C.c_int, C.c_int, fp, fp, C.c_longlong, fp, C.c_longlong,
                                       C.c_int, C.c_int, dp]
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_make_sysparse.argtypes = [ip, dp, C.c_longlong, C.c_int, C.c_int, ip, ip, dp]
+        L.oracle_make_sysparse.restype = C.c_longlong
         _LIB = L
     return _LIB
 
@@ -163,3 +165,19 @@ def knn_data(ref, k, fit=None, metric=0, nthreads=0):
     if rc != 0:
         raise RuntimeError(f"oracle_knn_data -> {rc}")
     return dist, idx
+
+
+def make_sysparse(idx, dist, k=None):
+    """(pcol[n+1], irow[nnz], val[nnz]) of the symmetric CSC matrix make_sysparse writes."""
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    dist = np.ascontiguousarray(dist, dtype=np.float64)
+    n, maxk = idx.shape
+    k = maxk if k is None else k
+    pcol = np.zeros(n + 1, dtype=np.int32)
+    irow = np.zeros(max(1, n * k), dtype=np.int32)
+    val = np.zeros(max(1, n * k), dtype=np.float64)
+    nnz = lib().oracle_make_sysparse(idx.ctypes.data_as(C.POINTER(C.c_int)), _d(dist), n, maxk, k,
+                                     pcol.ctypes.data_as(C.POINTER(C.c_int)), irow.ctypes.data_as(C.POINTER(C.c_int)), _d(val))
+    if nnz < 0:
+        raise ValueError("oracle_make_sysparse failed")
+    return pcol, irow[:nnz].copy(), val[:nnz].copy()

@@ -86,6 +86,10 @@ int oracle_rms_rows(int mode, int natoms, const float *mass,
 
 int oracle_max_threads(void);
 
+/* make_sysparse (make_sysparse.cpp:245-329): symmetric CSC from the kNN files; returns nnz (csc.c). */
+long long oracle_make_sysparse(const int *idx, const double *dist, long long n, int maxk, int k, int *pcol, int *irow,
+                               double *val);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,6 +149,11 @@ int mdsctk_knn_data_query_range(mdsctk_knn_ctx *ctx, long long fit_begin, long l
  * together the arrays make_sysparse writes after the leading int n (make_sysparse.cpp:310-329). */
 int mdsctk_knn_csc_build_sym(mdsctk_knn_ctx *ctx, const int *idx, const double *dist, long long n, int maxk, int k,
                              int *pcol, long long *nnz);
+/* General (non-symmetric) CSC matrix, make_gesparse.cpp:246-275: column i holds row i's entries (self entries
+ * included, the last duplicate wins); with symmetric != 0 (make_gesparse -s) entry (j, i) <- d(i, j) is added
+ * wherever row j does not list i itself (the first such entry sticks).  Same outputs as build_sym. */
+int mdsctk_knn_csc_build_general(mdsctk_knn_ctx *ctx, const int *idx, const double *dist, long long n, int maxk, int k,
+                                 int symmetric, int *pcol, long long *nnz);
 int mdsctk_knn_csc_fetch(mdsctk_knn_ctx *ctx, int *irow, double *val);
 
 /* Diagnostic: after set_option("debug_tile", 1) a tensor-core RMSD query also captures the raw

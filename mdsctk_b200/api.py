@@ -24,7 +24,7 @@ SYMBOLS = [
     "mdsctk_knn_data_set_reference", "mdsctk_knn_data_query", "mdsctk_knn_data_alloc_reference",
     "mdsctk_knn_data_upload_shard", "mdsctk_knn_data_reference_arrays", "mdsctk_knn_data_query_range",
     "mdsctk_knn_fetch", "mdsctk_knn_rms_rows", "mdsctk_knn_timer_start", "mdsctk_knn_timer_stop",
-    "mdsctk_knn_debug_fetch_tile", "mdsctk_knn_csc_build_sym", "mdsctk_knn_csc_fetch",
+    "mdsctk_knn_debug_fetch_tile", "mdsctk_knn_csc_build_sym", "mdsctk_knn_csc_build_general", "mdsctk_knn_csc_fetch",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library():
     L.mdsctk_knn_debug_fetch_tile.argtypes = [vp, fp]
     L.mdsctk_knn_timer_stop.argtypes = [vp, dp]
     L.mdsctk_knn_csc_build_sym.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, ip, C.POINTER(ll)]
+    L.mdsctk_knn_csc_build_general.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_fetch.argtypes = [vp, ip, dp]
     _LIB = L
     return L
@@ -235,7 +236,11 @@ class KnnContext:
         self._ck(rc, "data_query")
         return dist, idx
 
-    def csc_build_sym(self, idx, dist, k=None):
+    def csc_build_general(self, idx, dist, k=None, symmetric=False):
+        """General CSC matrix of the kNN lists, as make_gesparse [-s] writes it."""
+        return self.csc_build_sym(idx, dist, k, _mode=2 if symmetric else 1)
+
+    def csc_build_sym(self, idx, dist, k=None, _mode=0):
         """Symmetric CSC matrix of the kNN lists, as make_sysparse writes it: (pcol[n+1], irow[nnz], val[nnz])."""
         idx = np.ascontiguousarray(idx, dtype=np.int32)
         dist = np.ascontiguousarray(dist, dtype=np.float64)
@@ -243,8 +248,13 @@ class KnnContext:
         k = maxk if k is None else k
         pcol = np.empty(n + 1, dtype=np.int32)
         nnz = C.c_longlong(0)
-        self._ck(self._L.mdsctk_knn_csc_build_sym(self._h, _ptr(idx, C.c_int), _ptr(dist, C.c_double), n, maxk, k,
-                                                  _ptr(pcol, C.c_int), C.byref(nnz)), "csc_build_sym")
+        if _mode == 0:
+            rc = self._L.mdsctk_knn_csc_build_sym(self._h, _ptr(idx, C.c_int), _ptr(dist, C.c_double), n, maxk, k,
+                                                  _ptr(pcol, C.c_int), C.byref(nnz))
+        else:
+            rc = self._L.mdsctk_knn_csc_build_general(self._h, _ptr(idx, C.c_int), _ptr(dist, C.c_double), n, maxk, k,
+                                                      1 if _mode == 2 else 0, _ptr(pcol, C.c_int), C.byref(nnz))
+        self._ck(rc, "csc_build")
         irow = np.empty(nnz.value, dtype=np.int32)
         val = np.empty(nnz.value, dtype=np.float64)
         self._ck(self._L.mdsctk_knn_csc_fetch(self._h, _ptr(irow, C.c_int), _ptr(val, C.c_double)), "csc_fetch")

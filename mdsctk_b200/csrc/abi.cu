@@ -832,19 +832,35 @@ int mdsctk_knn_data_query(mdsctk_knn_ctx *ctx, const double *fit_rows, long long
 }
 
 /* ---------------------------------------------------------------- CSC builder ---- */
+static int csc_build(mdsctk_knn_ctx *ctx, int mode, const int *idx, const double *dist, long long n, int maxk, int k, int *pcol,
+                     long long *nnz);
+
 int mdsctk_knn_csc_build_sym(mdsctk_knn_ctx *ctx, const int *idx, const double *dist, long long n, int maxk, int k,
                              int *pcol, long long *nnz)
+{
+    return csc_build(ctx, 0, idx, dist, n, maxk, k, pcol, nnz);
+}
+
+int mdsctk_knn_csc_build_general(mdsctk_knn_ctx *ctx, const int *idx, const double *dist, long long n, int maxk, int k,
+                                 int symmetric, int *pcol, long long *nnz)
+{
+    return csc_build(ctx, symmetric ? 2 : 1, idx, dist, n, maxk, k, pcol, nnz);
+}
+
+static int csc_build(mdsctk_knn_ctx *ctx, int mode, const int *idx, const double *dist, long long n, int maxk, int k, int *pcol,
+                     long long *nnz)
 {
     if (!ctx) return MDSCTK_KNN_EINVAL;
     if (!idx || !dist || !pcol || !nnz || n <= 0 || maxk <= 0 || k < 0 || k > maxk)
         return fail(ctx, MDSCTK_KNN_EINVAL, "csc_build_sym: bad arguments (need 0 <= k <= maxk, n > 0)");
-    if ((double)n * (double)std::max(k, 1) >= 2147483647.0)
-        return fail(ctx, MDSCTK_KNN_EINVAL, "csc_build_sym: n*k must stay below 2^31 (int offsets, as in the reference)");
+    const int fan = mode == 2 ? 2 : 1;          // entries a kNN item can produce
+    if ((double)n * (double)std::max(k, 1) * fan >= 2147483647.0)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "csc_build: the entry count must stay below 2^31 (int offsets, as in the reference)");
     Bind b(ctx);
     mdsctk_knn_stats &S = ctx->stats;
     S.ms_upload = S.ms_sweep = S.ms_download = 0; S.launches = 0;
     ctx->c_nnz = -1;
-    const size_t ne = (size_t)n * maxk, nk = (size_t)n * std::max(k, 1);
+    const size_t ne = (size_t)n * maxk, nk = (size_t)n * std::max(k, 1) * fan;
     const size_t nscan = (size_t)n / 1024 + (size_t)n / (1024 * 1024) + 16;
     CK(ctx->c_idx.reserve(ne * 4), "cudaMalloc(csc idx)");
     CK(ctx->c_dist.reserve(ne * 8), "cudaMalloc(csc dist)");
@@ -862,9 +878,9 @@ int mdsctk_knn_csc_build_sym(mdsctk_knn_ctx *ctx, const int *idx, const double *
     int *scan_tmp = ints + 5 * (n + 1);
     ctx->tm.start(ctx->st);
     if (k > 0) {
-        CK(launch_csc_build_sym(ctx->c_idx.as<int>(), ctx->c_dist.as<double>(), n, maxk, k, cnt, cur, off, fin, d_pcol, scan_tmp,
+        CK(launch_csc_build(mode, ctx->c_idx.as<int>(), ctx->c_dist.as<double>(), n, maxk, k, cnt, cur, off, fin, d_pcol, scan_tmp,
                                 ctx->c_key.as<unsigned long long>(), ctx->c_val.as<double>(), ctx->c_irow.as<int>(),
-                                ctx->c_oval.as<double>(), ctx->st), "csc_build_sym");
+                                ctx->c_oval.as<double>(), ctx->st), "csc_build");
         S.launches = 11;
     } else {
         CK(cudaMemsetAsync(d_pcol, 0, (size_t)(n + 1) * 4, ctx->st), "memset pcol");

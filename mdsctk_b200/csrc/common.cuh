@@ -115,9 +115,10 @@ cudaError_t launch_data_scatter_out(const double *d_src, const int *i_src, const
                                     int *i_dst, cudaStream_t st);
 
 // Symmetric CSC matrix from kNN lists (csc.cu; replaces make_sysparse.cpp:245-329).
-cudaError_t launch_csc_build_sym(const int *d_idx, const double *d_dist, long long n, int maxk, int k, int *cnt, int *cur,
-                                 int *off, int *fin, int *pcol, int *scan_tmp, unsigned long long *seg_key, double *seg_val,
-                                 int *irow, double *val, cudaStream_t st);
+// mode 0 make_sysparse, 1 make_gesparse, 2 make_gesparse -s
+cudaError_t launch_csc_build(int mode, const int *d_idx, const double *d_dist, long long n, int maxk, int k, int *cnt, int *cur,
+                             int *off, int *fin, int *pcol, int *scan_tmp, unsigned long long *seg_key, double *seg_val,
+                             int *irow, double *val, cudaStream_t st);
 
 cudaError_t launch_max_float(const float *v, long long n, float *out, cudaStream_t st);
 cudaError_t launch_fill_u32(void *p, size_t n, uint32_t v, cudaStream_t st);

@@ -1,4 +1,4 @@
-// csc.cu -- symmetric CSC matrix from the kNN lists on the GPU (the consumer make_sysparse).
+// csc.cu -- CSC matrices from the kNN lists on the GPU (the consumers make_sysparse / make_gesparse).
 //
 // Replaces make_sysparse.cpp:245-329: the reference inserts, row by row, the edge
 // (min(i,j), max(i,j)) -> distance of the first k entries of every kNN row into an on-disk
@@ -24,16 +24,24 @@ constexpr int SEG_CAP = 512;          // entries a warp sorts in shared memory
 constexpr int WARPS = 4;
 }  // namespace csc
 
-__global__ void csc_count_kernel(const int *__restrict__ idx, long long n, int maxk, int k, int *__restrict__ cnt)
+// mode 0: make_sysparse (edge (min,max), larger endpoint's value wins)
+// mode 1: make_gesparse (column = the listing row, every entry kept, last duplicate wins)
+// mode 2: make_gesparse -s (additionally (j, i) <- d(i, j) where row j does not list i; first such entry wins)
+__global__ void csc_count_kernel(const int *__restrict__ idx, long long n, int maxk, int k, int mode, int *__restrict__ cnt)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * k) return;
     const long long i = t / k;
     const int x = (int)(t - i * k);
     const int j = idx[i * maxk + x];
-    if (j == (int)i) return;
-    const int c = j < (int)i ? j : (int)i;
-    if (c >= 0 && c < n) atomicAdd(&cnt[c], 1);
+    if (mode == 0) {
+        if (j == (int)i) return;
+        const int c = j < (int)i ? j : (int)i;
+        if (c >= 0 && c < n) atomicAdd(&cnt[c], 1);
+    } else {
+        atomicAdd(&cnt[i], 1);
+        if (mode == 2 && j != (int)i && j >= 0 && j < n) atomicAdd(&cnt[j], 1);
+    }
 }
 
 // ---- exclusive scan of int[n] (values and total fit in int: nnz < 2^31 as in the reference's int pcol) ----
@@ -87,8 +95,10 @@ static cudaError_t exclusive_scan(const int *in, int *out, long long n, int *tmp
     return cudaGetLastError();
 }
 
+// Segment entry: key = (row index `to`) << 32 | priority; per `to` the entry with the LARGEST priority is the one
+// the reference's B-tree holds at the end (make_sysparse.cpp:245-277, make_gesparse.cpp:246-275).
 __global__ void csc_scatter_kernel(const int *__restrict__ idx, const double *__restrict__ dist, long long n, int maxk,
-                                   int k, const int *__restrict__ off, int *__restrict__ cur,
+                                   int k, int mode, const int *__restrict__ off, int *__restrict__ cur,
                                    unsigned long long *__restrict__ seg_key, double *__restrict__ seg_val)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,14 +106,23 @@ __global__ void csc_scatter_kernel(const int *__restrict__ idx, const double *__
     const long long i = t / k;
     const int x = (int)(t - i * k);
     const int j = idx[i * maxk + x];
-    if (j == (int)i) return;
-    const bool rev = j < (int)i;                 // written from the larger endpoint: processed later, wins
-    const int c = rev ? j : (int)i, r = rev ? (int)i : j;
-    if (c < 0 || c >= n) return;
-    const int pos = off[c] + atomicAdd(&cur[c], 1);
-    // (to, insertion order within the edge): to in the high word, then the `rev` bit, then the entry number
-    seg_key[pos] = ((unsigned long long)(unsigned)r << 32) | ((unsigned long long)(rev ? 1u : 0u) << 31) | (unsigned)x;
-    seg_val[pos] = dist[i * maxk + x];
+    const double d = dist[i * maxk + x];
+    auto emit = [&](int c, int r, unsigned prio) {
+        const int pos = off[c] + atomicAdd(&cur[c], 1);
+        seg_key[pos] = ((unsigned long long)(unsigned)r << 32) | prio;
+        seg_val[pos] = d;
+    };
+    if (mode == 0) {
+        if (j == (int)i) return;
+        const bool rev = j < (int)i;             // written from the larger endpoint: processed later, overwrites
+        const int c = rev ? j : (int)i, r = rev ? (int)i : j;
+        if (c < 0 || c >= n) return;
+        emit(c, r, (rev ? 0x80000000u : 0u) | (unsigned)x);          // later entries of a row overwrite earlier ones
+    } else {
+        emit((int)i, j, 0x80000000u | (unsigned)x);                  // direct put: always overwrites, last duplicate wins
+        // symmetric fill: written only while (j, i) is absent, so the first attempt sticks unless row j lists i itself
+        if (mode == 2 && j != (int)i && j >= 0 && j < n) emit(j, (int)i, (unsigned)(maxk - 1 - x));
+    }
 }
 
 // Bitonic sort of n (any length) 64-bit keys + payload, ascending.  "Flip" formulation: every
@@ -200,11 +219,11 @@ __global__ void csc_compact_kernel(const int *__restrict__ off, const int *__res
 
 // Device-side driver.  d_idx [n][maxk], d_dist [n][maxk]; work buffers sized by the caller:
 //   cnt, cur, off, fin, pcol: n + 1 ints each; scan_tmp: n/1024 + n/1024^2 + 8 ints;
-//   seg_key / seg_val: n * k entries; irow / val: n * k entries (upper bound of nnz).
+//   seg_key / seg_val, irow / val: n * k entries (2 n k for mode 2), the upper bound of nnz.
 // *nnz_host is valid after the stream has been synchronised by the caller's copy of pcol[n].
-cudaError_t launch_csc_build_sym(const int *d_idx, const double *d_dist, long long n, int maxk, int k, int *cnt, int *cur,
-                                 int *off, int *fin, int *pcol, int *scan_tmp, unsigned long long *seg_key, double *seg_val,
-                                 int *irow, double *val, cudaStream_t st)
+cudaError_t launch_csc_build(int mode, const int *d_idx, const double *d_dist, long long n, int maxk, int k, int *cnt, int *cur,
+                             int *off, int *fin, int *pcol, int *scan_tmp, unsigned long long *seg_key, double *seg_val,
+                             int *irow, double *val, cudaStream_t st)
 {
     if (n <= 0 || k <= 0) return cudaSuccess;
     cudaError_t e;
@@ -213,9 +232,9 @@ cudaError_t launch_csc_build_sym(const int *d_idx, const double *d_dist, long lo
     if ((e = cudaMemsetAsync(fin, 0, (size_t)(n + 1) * 4, st)) != cudaSuccess) return e;
     const long long total = n * k;
     const unsigned grid = (unsigned)((total + 255) / 256);
-    csc_count_kernel<<<grid, 256, 0, st>>>(d_idx, n, maxk, k, cnt);
+    csc_count_kernel<<<grid, 256, 0, st>>>(d_idx, n, maxk, k, mode, cnt);
     if ((e = exclusive_scan(cnt, off, n + 1, scan_tmp, st)) != cudaSuccess) return e;
-    csc_scatter_kernel<<<grid, 256, 0, st>>>(d_idx, d_dist, n, maxk, k, off, cur, seg_key, seg_val);
+    csc_scatter_kernel<<<grid, 256, 0, st>>>(d_idx, d_dist, n, maxk, k, mode, off, cur, seg_key, seg_val);
     csc_resolve_kernel<<<(unsigned)((n + csc::WARPS - 1) / csc::WARPS), csc::WARPS * 32, 0, st>>>(off, n, seg_key, seg_val, fin);
     if ((e = exclusive_scan(fin, pcol, n + 1, scan_tmp, st)) != cudaSuccess) return e;
     csc_compact_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(off, pcol, n, seg_key, seg_val, irow, val);

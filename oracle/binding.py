@@ -50,6 +50,8 @@ def lib():
         L.oracle_max_threads.restype = C.c_int
         L.oracle_make_sysparse.argtypes = [ip, dp, C.c_longlong, C.c_int, C.c_int, ip, ip, dp]
         L.oracle_make_sysparse.restype = C.c_longlong
+        L.oracle_make_gesparse.argtypes = [ip, dp, C.c_longlong, C.c_int, C.c_int, C.c_int, ip, ip, dp]
+        L.oracle_make_gesparse.restype = C.c_longlong
         _LIB = L
     return _LIB
 
@@ -180,4 +182,21 @@ def make_sysparse(idx, dist, k=None):
                                      pcol.ctypes.data_as(C.POINTER(C.c_int)), irow.ctypes.data_as(C.POINTER(C.c_int)), _d(val))
     if nnz < 0:
         raise ValueError("oracle_make_sysparse failed")
+    return pcol, irow[:nnz].copy(), val[:nnz].copy()
+
+
+def make_gesparse(idx, dist, k=None, symmetric=False):
+    """(pcol[n+1], irow[nnz], val[nnz]) of the general CSC matrix make_gesparse [-s] writes."""
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    dist = np.ascontiguousarray(dist, dtype=np.float64)
+    n, maxk = idx.shape
+    k = maxk if k is None else k
+    cap = max(1, n * k * (2 if symmetric else 1))
+    pcol = np.zeros(n + 1, dtype=np.int32)
+    irow = np.zeros(cap, dtype=np.int32)
+    val = np.zeros(cap, dtype=np.float64)
+    nnz = lib().oracle_make_gesparse(idx.ctypes.data_as(C.POINTER(C.c_int)), _d(dist), n, maxk, k, int(bool(symmetric)),
+                                     pcol.ctypes.data_as(C.POINTER(C.c_int)), irow.ctypes.data_as(C.POINTER(C.c_int)), _d(val))
+    if nnz < 0:
+        raise ValueError("oracle_make_gesparse failed")
     return pcol, irow[:nnz].copy(), val[:nnz].copy()

@@ -59,3 +59,51 @@ long long oracle_make_sysparse(const int *idx, const double *dist, long long n, 
     free(e);
     return nnz;
 }
+
+/* make_gesparse.cpp:246-275: for the first k entries of row i, in order:
+ *   put((i, j) -> d)                                   -- always, overwriting
+ *   with -s: if (j, i) is absent, put((j, i) -> d)     -- db.get(...) == DB_NOTFOUND
+ * then the same (from, to) walk.  The B-tree is simulated per key: the events of a key are replayed in
+ * chronological order with exactly those put / put-if-absent semantics.  `order` doubles as the flag:
+ * even = direct put, odd = fill attempt. */
+long long oracle_make_gesparse(const int *idx, const double *dist, long long n, int maxk, int k, int symmetric, int *pcol,
+                               int *irow, double *val)
+{
+    if (n < 0 || k < 0 || k > maxk) return -1;
+    const long long cap = n * k * (symmetric ? 2 : 1);
+    csc_edge *e = (csc_edge *)malloc(sizeof(csc_edge) * (size_t)(cap > 0 ? cap : 1));
+    if (!e) return -1;
+    long long m = 0;
+    for (long long i = 0; i < n; i++)
+        for (int x = 0; x < k; x++) {
+            const int j = idx[i * maxk + x];
+            e[m].from = (int)i; e[m].to = j; e[m].order = 2 * (i * maxk + x); e[m].d = dist[i * maxk + x];
+            m++;
+            if (symmetric) {
+                e[m].from = j; e[m].to = (int)i; e[m].order = 2 * (i * maxk + x) + 1; e[m].d = dist[i * maxk + x];
+                m++;
+            }
+        }
+    qsort(e, (size_t)m, sizeof(csc_edge), cmp_edge);
+    long long nnz = 0;
+    memset(pcol, 0, sizeof(int) * (size_t)(n + 1));
+    for (long long a = 0; a < m;) {
+        long long b = a;
+        int present = 0;
+        double v = 0.0;
+        for (; b < m && e[b].from == e[a].from && e[b].to == e[a].to; b++) {
+            if ((e[b].order & 1) == 0) { present = 1; v = e[b].d; }          /* put: overwrite */
+            else if (!present) { present = 1; v = e[b].d; }                   /* fill: only while absent */
+        }
+        if (present && e[a].from >= 0 && e[a].from < n) {
+            irow[nnz] = e[a].to;
+            val[nnz] = v;
+            pcol[e[a].from + 1]++;
+            nnz++;
+        }
+        a = b;
+    }
+    for (long long c = 0; c < n; c++) pcol[c + 1] += pcol[c];
+    free(e);
+    return nnz;
+}

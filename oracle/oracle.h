@@ -87,6 +87,9 @@ int oracle_rms_rows(int mode, int natoms, const float *mass,
 int oracle_max_threads(void);
 
 /* make_sysparse (make_sysparse.cpp:245-329): symmetric CSC from the kNN files; returns nnz (csc.c). */
+/* make_gesparse [-s] (make_gesparse.cpp:246-333): general CSC; returns nnz (capacity n*k, or 2*n*k with symmetric) */
+long long oracle_make_gesparse(const int *idx, const double *dist, long long n, int maxk, int k, int symmetric, int *pcol,
+                               int *irow, double *val);
 long long oracle_make_sysparse(const int *idx, const double *dist, long long n, int maxk, int k, int *pcol, int *irow,
                                double *val);
 

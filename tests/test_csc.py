@@ -39,6 +39,24 @@ def reference_semantics(idx, dist, k):
         np.array([db[kk] for kk in keys], dtype=np.float64)
 
 
+def reference_semantics_general(idx, dist, k, symmetric):
+    """make_gesparse.cpp:246-275 as a dict: put always; with -s put the transposed entry only while it is absent."""
+    n = idx.shape[0]
+    db = {}
+    for i in range(n):
+        for x in range(k):
+            j = int(idx[i, x])
+            db[(i, j)] = dist[i, x]
+            if symmetric and (j, i) not in db:
+                db[(j, i)] = dist[i, x]
+    keys = [kk for kk in sorted(db) if 0 <= kk[0] < n]
+    pcol = np.zeros(n + 1, dtype=np.int32)
+    for (f, _t) in keys:
+        pcol[f + 1] += 1
+    return np.cumsum(pcol, dtype=np.int32), np.array([t for _f, t in keys], dtype=np.int32), \
+        np.array([db[kk] for kk in keys], dtype=np.float64)
+
+
 def random_lists(rng, n, maxk, dup=False, hub=False):
     idx = np.empty((n, maxk), dtype=np.int32)
     for i in range(n):
@@ -67,6 +85,18 @@ def test_oracle_matches_reference_semantics():
             assert np.array_equal(g, w)
 
 
+def test_gesparse_oracle_matches_reference_semantics():
+    from oracle import binding as ob
+    rng = np.random.default_rng(3)
+    for n, maxk, k, dup in ((40, 5, 5, False), (90, 8, 3, True), (150, 10, 10, True)):
+        idx, dist = random_lists(rng, n, maxk, dup=dup)
+        for sym in (False, True):
+            got = ob.make_gesparse(idx, dist, k, symmetric=sym)
+            want = reference_semantics_general(idx, dist, k, sym)
+            for g, w in zip(got, want):
+                assert np.array_equal(g, w), (n, maxk, k, dup, sym)
+
+
 def test_make_sysparse_cli_contract(tmp_path):
     def run(*args):
         p = subprocess.run([os.path.join(BIN, "make_sysparse"), *args], capture_output=True, text=True, cwd=tmp_path)
@@ -82,6 +112,10 @@ def test_make_sysparse_cli_contract(tmp_path):
     rc, out = run("-k", "5")
     assert rc == 255 and "Could not open file: distances.dat" in out      # :140-146
     assert "knn =            5" in out and "output-knn =     5" in out and "output-file =    distances.ssm" in out
+    p = subprocess.run([os.path.join(BIN, "make_gesparse"), "-h"], capture_output=True, text=True, cwd=tmp_path)
+    assert p.returncode == 1 and "usage: make_gesparse [options]" in p.stdout and "--symmetric" in p.stdout   # make_gesparse.cpp:66-76
+    p = subprocess.run([os.path.join(BIN, "make_gesparse"), "-k", "4"], capture_output=True, text=True, cwd=tmp_path)
+    assert p.returncode == 255 and "output-file =    distances.gsm" in p.stdout
 
 
 @pytest.mark.gpu
@@ -102,6 +136,11 @@ def test_gpu_builder_matches_oracle():
             want = ob.make_sysparse(idx, dist, k)
             for g, w, name in zip(got, want, ("pcol", "irow", "val")):
                 assert np.array_equal(g, w), (n, maxk, k, dup, hub, name)
+            for sym in (False, True):
+                got = ctx.csc_build_general(idx, dist, k, symmetric=sym)
+                want = ob.make_gesparse(idx, dist, k, symmetric=sym)
+                for g, w, name in zip(got, want, ("pcol", "irow", "val")):
+                    assert np.array_equal(g, w), ("general", sym, n, maxk, k, dup, hub, name)
         # k = 0: empty matrix
         pcol, irow, val = ctx.csc_build_sym(idx, dist, 0)
         assert not pcol.any() and irow.size == 0 and val.size == 0
@@ -134,3 +173,15 @@ def test_make_sysparse_tool_end_to_end(tmp_path):
         for c in (0, 1, n // 2, n - 2):
             r = irow[pcol[c]:pcol[c + 1]]
             assert (r > c).all() and (np.diff(r) > 0).all()
+        for flag, sym in (((), False), (("-s",), True)):
+            p = subprocess.run([os.path.join(BIN, "make_gesparse"), "-k", "100", "-n", str(k), *flag], capture_output=True,
+                               text=True, cwd=tmp_path)
+            assert p.returncode == 0, p.stdout
+            raw = (tmp_path / "distances.gsm").read_bytes()
+            n = int(np.frombuffer(raw, dtype=np.int32, count=1)[0])
+            pcol = np.frombuffer(raw, dtype=np.int32, count=n + 1, offset=4)
+            nnz = int(pcol[-1])
+            irow = np.frombuffer(raw, dtype=np.int32, count=nnz, offset=4 + 4 * (n + 1))
+            val = np.frombuffer(raw, dtype=np.float64, count=nnz, offset=4 + 4 * (n + 1) + 4 * nnz)
+            want = ob.make_gesparse(idx, dist, k, symmetric=sym)
+            assert np.array_equal(pcol, want[0]) and np.array_equal(irow, want[1]) and np.array_equal(val, want[2])

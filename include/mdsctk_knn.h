@@ -156,6 +156,15 @@ int mdsctk_knn_csc_build_general(mdsctk_knn_ctx *ctx, const int *idx, const doub
                                  int symmetric, int *pcol, long long *nnz);
 int mdsctk_knn_csc_fetch(mdsctk_knn_ctx *ctx, int *irow, double *val);
 
+/* ---- producers of knn_data's input: backbone phi/psi angles and their sin/cos embedding -------------
+ * xyz: host, float[n_frames][n_atoms][3] (nm), backbone atoms N-CA-C only, one chain
+ * (bb_xtc_to_phipsi.cpp:106-122).  T = 2*(n_atoms/3) - 2 angles per frame (radians, torsion() of
+ * mdsctk.cpp:643-676 in float, widened to double).  phipsi: host double[n_frames][T] or NULL;
+ * sincos: host double[n_frames][2T] (sin, cos interleaved, angles_to_sincos.cpp:107-118) or NULL. */
+int mdsctk_knn_phipsi(mdsctk_knn_ctx *ctx, const float *xyz, long long n_frames, int n_atoms, double *phipsi, double *sincos);
+/* angles: host double[n]; out: host double[2n] = sin, cos interleaved (angles_to_sincos.cpp:107-118). */
+int mdsctk_knn_sincos(mdsctk_knn_ctx *ctx, const double *angles, long long n, double *out);
+
 /* Diagnostic: after set_option("debug_tile", 1) a tensor-core RMSD query also captures the raw
  * TMEM accumulators of (fit tile 0, reference tile 0): out[128][9][48] floats, S_ab of fit row q
  * against reference j at out[q][3*a+b][j]. */

@@ -25,6 +25,7 @@ SYMBOLS = [
     "mdsctk_knn_data_upload_shard", "mdsctk_knn_data_reference_arrays", "mdsctk_knn_data_query_range",
     "mdsctk_knn_fetch", "mdsctk_knn_rms_rows", "mdsctk_knn_timer_start", "mdsctk_knn_timer_stop",
     "mdsctk_knn_debug_fetch_tile", "mdsctk_knn_csc_build_sym", "mdsctk_knn_csc_build_general", "mdsctk_knn_csc_fetch",
+    "mdsctk_knn_phipsi", "mdsctk_knn_sincos",
 ]
 
 
@@ -88,6 +89,8 @@ def load_library():
     L.mdsctk_knn_csc_build_sym.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_build_general.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_fetch.argtypes = [vp, ip, dp]
+    L.mdsctk_knn_phipsi.argtypes = [vp, fp, ll, C.c_int, dp, dp]
+    L.mdsctk_knn_sincos.argtypes = [vp, dp, ll, dp]
     _LIB = L
     return L
 
@@ -235,6 +238,23 @@ class KnnContext:
                                                _ptr(dist, C.c_double), _ptr(idx, C.c_int))
         self._ck(rc, "data_query")
         return dist, idx
+
+    def phipsi(self, xyz, want_angles=True, want_sincos=True):
+        """Backbone torsions (bb_xtc_to_phipsi) and their sin/cos embedding (angles_to_sincos) of N-CA-C frames."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        n, a = xyz.shape[0], xyz.shape[1]
+        t = 2 * (a // 3) - 2
+        ang = np.empty((n, t), dtype=np.float64) if want_angles else None
+        sc = np.empty((n, 2 * t), dtype=np.float64) if want_sincos else None
+        self._ck(self._L.mdsctk_knn_phipsi(self._h, _ptr(xyz, C.c_float), n, a, _ptr(ang, C.c_double), _ptr(sc, C.c_double)),
+                 "phipsi")
+        return ang, sc
+
+    def sincos(self, angles):
+        angles = np.ascontiguousarray(angles, dtype=np.float64)
+        out = np.empty(angles.size * 2, dtype=np.float64)
+        self._ck(self._L.mdsctk_knn_sincos(self._h, _ptr(angles, C.c_double), angles.size, _ptr(out, C.c_double)), "sincos")
+        return out
 
     def csc_build_general(self, idx, dist, k=None, symmetric=False):
         """General CSC matrix of the kNN lists, as make_gesparse [-s] writes it."""

@@ -118,6 +118,7 @@ struct mdsctk_knn_ctx {
     int data_kernel = -1;      // -1 auto, 0 exact FP64 sweep, 1 tensor-core filter + exact re-score
     // CSC builder state (csc.cu)
     DevBuf c_idx, c_dist, c_ints, c_key, c_val, c_irow, c_oval;
+    DevBuf f_in, f_ang, f_sc;   // featuriser buffers
     long long c_nnz = -1;
     // scratch + results
     DevBuf cand_key, cand_idx, cand_cnt, cand_tau, flags, bad_rows, scalars, rows_buf;
@@ -907,6 +908,50 @@ int mdsctk_knn_csc_fetch(mdsctk_knn_ctx *ctx, int *irow, double *val)
     CK(cudaMemcpyAsync(irow, ctx->c_irow.p, (size_t)ctx->c_nnz * 4, cudaMemcpyDeviceToHost, ctx->st), "D2H irow");
     CK(cudaMemcpyAsync(val, ctx->c_oval.p, (size_t)ctx->c_nnz * 8, cudaMemcpyDeviceToHost, ctx->st), "D2H val");
     ctx->stats.ms_download += ctx->tm.stop(ctx->st);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- featurisers ---- */
+int mdsctk_knn_phipsi(mdsctk_knn_ctx *ctx, const float *xyz, long long n_frames, int n_atoms, double *phipsi, double *sincos)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    const int T = 2 * (n_atoms / 3) - 2;
+    if (!xyz || n_frames <= 0 || n_atoms < 6 || T <= 0 || (!phipsi && !sincos))
+        return fail(ctx, MDSCTK_KNN_EINVAL, "phipsi: need frames of at least 6 backbone atoms and an output");
+    Bind b(ctx);
+    mdsctk_knn_stats &S = ctx->stats;
+    S.ms_upload = S.ms_sweep = S.ms_download = 0; S.launches = 1;
+    const size_t na = (size_t)n_frames * T;
+    CK(ctx->f_in.reserve((size_t)n_frames * n_atoms * 12), "cudaMalloc(frames)");
+    if (phipsi) CK(ctx->f_ang.reserve(na * 8), "cudaMalloc(angles)");
+    if (sincos) CK(ctx->f_sc.reserve(na * 16), "cudaMalloc(sincos)");
+    ctx->tm.start(ctx->st);
+    CK(cudaMemcpyAsync(ctx->f_in.p, xyz, (size_t)n_frames * n_atoms * 12, cudaMemcpyHostToDevice, ctx->st), "H2D frames");
+    S.ms_upload = ctx->tm.stop(ctx->st);
+    ctx->tm.start(ctx->st);
+    CK(launch_phipsi(ctx->f_in.as<float>(), n_frames, n_atoms, phipsi ? ctx->f_ang.as<double>() : nullptr,
+                     sincos ? ctx->f_sc.as<double>() : nullptr, ctx->st), "phipsi");
+    S.ms_sweep = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "phipsi kernel");
+    ctx->tm.start(ctx->st);
+    if (phipsi) CK(cudaMemcpyAsync(phipsi, ctx->f_ang.p, na * 8, cudaMemcpyDeviceToHost, ctx->st), "D2H angles");
+    if (sincos) CK(cudaMemcpyAsync(sincos, ctx->f_sc.p, na * 16, cudaMemcpyDeviceToHost, ctx->st), "D2H sincos");
+    S.ms_download = ctx->tm.stop(ctx->st);
+    S.pairs = (long long)na;
+    return 0;
+}
+
+int mdsctk_knn_sincos(mdsctk_knn_ctx *ctx, const double *angles, long long n, double *out)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (!angles || !out || n <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "sincos: bad arguments");
+    Bind b(ctx);
+    CK(ctx->f_ang.reserve((size_t)n * 8), "cudaMalloc(angles)");
+    CK(ctx->f_sc.reserve((size_t)n * 16), "cudaMalloc(sincos)");
+    CK(cudaMemcpyAsync(ctx->f_ang.p, angles, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->st), "H2D angles");
+    CK(launch_sincos(ctx->f_ang.as<double>(), n, ctx->f_sc.as<double>(), ctx->st), "sincos");
+    CK(cudaMemcpyAsync(out, ctx->f_sc.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->st), "D2H sincos");
+    CK(cudaStreamSynchronize(ctx->st), "sync sincos");
     return 0;
 }
 

@@ -120,6 +120,10 @@ cudaError_t launch_csc_build(int mode, const int *d_idx, const double *d_dist, l
                              int *off, int *fin, int *pcol, int *scan_tmp, unsigned long long *seg_key, double *seg_val,
                              int *irow, double *val, cudaStream_t st);
 
+// Featurisers (featurize.cu): backbone torsions and the sin/cos embedding.
+cudaError_t launch_phipsi(const float *xyz, long long n, int A, double *phipsi, double *sincos, cudaStream_t st);
+cudaError_t launch_sincos(const double *angles, long long n, double *out, cudaStream_t st);
+
 cudaError_t launch_max_float(const float *v, long long n, float *out, cudaStream_t st);
 cudaError_t launch_fill_u32(void *p, size_t n, uint32_t v, cudaStream_t st);
 

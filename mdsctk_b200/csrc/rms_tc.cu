@@ -586,6 +586,7 @@ static cudaError_t launch_tc_mode(const CUtensorMap &mq_hi, const CUtensorMap &m
     if (cudaOccupancyMaxActiveClusters(&q, rms_sweep_tc_kernel<M>, &cfg) == cudaSuccess && q > 0 && q < max_pairs)
         max_pairs = q;                              // a GPC with an odd SM count cannot host every pair
     (void)cudaGetLastError();
+    if (const char *mp = getenv("MDSCTK_TC_MAX_PAIRS")) { const int v = atoi(mp); if (v > 0 && v < max_pairs) max_pairs = v; }   // experiments
     const long long n_pairs = n_items < max_pairs ? n_items : max_pairs;
     cfg.gridDim = dim3((unsigned)(n_pairs * 2));
     return cudaLaunchKernelEx(&cfg, rms_sweep_tc_kernel<M>, mq_hi, mq_lo, mr_hi, mr_lo, a);

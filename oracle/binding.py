@@ -52,6 +52,10 @@ def lib():
         L.oracle_make_sysparse.restype = C.c_longlong
         L.oracle_make_gesparse.argtypes = [ip, dp, C.c_longlong, C.c_int, C.c_int, C.c_int, ip, ip, dp]
         L.oracle_make_gesparse.restype = C.c_longlong
+        L.oracle_phipsi.argtypes = [fp, C.c_longlong, C.c_int, dp]
+        L.oracle_phipsi.restype = None
+        L.oracle_sincos.argtypes = [dp, C.c_longlong, dp]
+        L.oracle_sincos.restype = None
         _LIB = L
     return _LIB
 
@@ -200,3 +204,19 @@ def make_gesparse(idx, dist, k=None, symmetric=False):
     if nnz < 0:
         raise ValueError("oracle_make_gesparse failed")
     return pcol, irow[:nnz].copy(), val[:nnz].copy()
+
+
+def phipsi(xyz):
+    """double[n][2*(A/3)-2] backbone torsions of N-CA-C frames, as bb_xtc_to_phipsi writes them."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    n, a = xyz.shape[0], xyz.shape[1]
+    out = np.empty((n, 2 * (a // 3) - 2), dtype=np.float64)
+    lib().oracle_phipsi(_f(xyz), n, a, _d(out))
+    return out
+
+
+def sincos(angles):
+    angles = np.ascontiguousarray(angles, dtype=np.float64)
+    out = np.empty(angles.size * 2, dtype=np.float64)
+    lib().oracle_sincos(_d(angles), angles.size, _d(out))
+    return out

@@ -87,6 +87,11 @@ int oracle_rms_rows(int mode, int natoms, const float *mass,
 int oracle_max_threads(void);
 
 /* make_sysparse (make_sysparse.cpp:245-329): symmetric CSC from the kNN files; returns nnz (csc.c). */
+/* bb_xtc_to_phipsi / angles_to_sincos (featurize.c) */
+float oracle_torsion(const float *pos1, const float *pos2, const float *pos3, const float *pos4);
+void oracle_phipsi(const float *xyz, long long n, int natoms, double *phipsi);
+void oracle_sincos(const double *angles, long long n, double *out);
+
 /* make_gesparse [-s] (make_gesparse.cpp:246-333): general CSC; returns nnz (capacity n*k, or 2*n*k with symmetric) */
 long long oracle_make_gesparse(const int *idx, const double *dist, long long n, int maxk, int k, int symmetric, int *pcol,
                                int *irow, double *val);

@@ -140,6 +140,10 @@ int mdsctk_knn_data_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n
 int mdsctk_knn_data_query_range(mdsctk_knn_ctx *ctx, long long fit_begin, long long n_fit, int k1, int metric,
                                 double *out_dist, int *out_idx);
 
+/* knn_data --sort false (knn_data.cpp:198-216): the full rows of distances, out[n_fit][n_reference] (host),
+ * in reference order, same arithmetic as the queries.  fit_rows == NULL: the reference rows themselves. */
+int mdsctk_knn_data_rows(mdsctk_knn_ctx *ctx, const double *fit_rows, long long n_fit, int metric, double *out);
+
 /* ---- consumer of the kNN files: symmetric CSC matrix (make_sysparse.cpp:245-329) ----------------
  * idx / dist: host, row-major [n][maxk] exactly as indices.dat / distances.dat hold them; only the
  * first k entries of every row are used (make_sysparse's -n / --output-knn, make_sysparse.cpp:93-103).

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mdsctk_knn_data_upload_shard", "mdsctk_knn_data_reference_arrays", "mdsctk_knn_data_query_range",
     "mdsctk_knn_fetch", "mdsctk_knn_rms_rows", "mdsctk_knn_timer_start", "mdsctk_knn_timer_stop",
     "mdsctk_knn_debug_fetch_tile", "mdsctk_knn_csc_build_sym", "mdsctk_knn_csc_build_general", "mdsctk_knn_csc_fetch",
-    "mdsctk_knn_phipsi", "mdsctk_knn_sincos",
+    "mdsctk_knn_phipsi", "mdsctk_knn_sincos", "mdsctk_knn_data_rows",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library():
     L.mdsctk_knn_csc_build_sym.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_build_general.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_fetch.argtypes = [vp, ip, dp]
+    L.mdsctk_knn_data_rows.argtypes = [vp, dp, ll, C.c_int, dp]
     L.mdsctk_knn_phipsi.argtypes = [vp, fp, ll, C.c_int, dp, dp]
     L.mdsctk_knn_sincos.argtypes = [vp, dp, ll, dp]
     _LIB = L
@@ -238,6 +239,17 @@ class KnnContext:
                                                _ptr(dist, C.c_double), _ptr(idx, C.c_int))
         self._ck(rc, "data_query")
         return dist, idx
+
+    def data_rows(self, fit=None, metric=EUCLIDEAN):
+        """Full distance rows [n_fit, n_reference] (knn_data --sort false)."""
+        n_fit = self._dn_ref
+        if fit is not None:
+            fit = np.ascontiguousarray(fit, dtype=np.float64)
+            n_fit = fit.shape[0]
+        out = np.empty((n_fit, self._dn_ref), dtype=np.float64)
+        self._ck(self._L.mdsctk_knn_data_rows(self._h, _ptr(fit, C.c_double), n_fit, int(metric), _ptr(out, C.c_double)),
+                 "data_rows")
+        return out
 
     def phipsi(self, xyz, want_angles=True, want_sincos=True):
         """Backbone torsions (bb_xtc_to_phipsi) and their sin/cos embedding (angles_to_sincos) of N-CA-C frames."""

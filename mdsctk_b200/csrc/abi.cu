@@ -832,6 +832,48 @@ int mdsctk_knn_data_query(mdsctk_knn_ctx *ctx, const double *fit_rows, long long
     return data_run(ctx, ctx->d_fit.as<double>(), false, 0, n_fit, k1, metric, out_dist, out_idx);
 }
 
+int mdsctk_knn_data_rows(mdsctk_knn_ctx *ctx, const double *fit_rows, long long n_fit, int metric, double *out)
+{
+    if (!ctx || !out) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_dref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
+    if (metric != MDSCTK_KNN_EUCLIDEAN && metric != MDSCTK_KNN_CORRELATION) return fail(ctx, MDSCTK_KNN_EINVAL, "unknown metric");
+    if (!fit_rows && n_fit != ctx->dn_ref) return fail(ctx, MDSCTK_KNN_EINVAL, "fit_rows == NULL requires n_fit == n_reference");
+    if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
+    Bind b(ctx);
+    const int dim = ctx->ddim;
+    const long long n_ref = ctx->dn_ref;
+    const double *d_fit = ctx->d_ref.as<double>();
+    if (fit_rows) {
+        CK(ctx->d_fit.reserve((size_t)n_fit * dim * 8), "cudaMalloc(fit rows)");
+        CK(cudaMemcpyAsync(ctx->d_fit.p, fit_rows, (size_t)n_fit * dim * 8, cudaMemcpyHostToDevice, ctx->st), "H2D fit rows");
+        d_fit = ctx->d_fit.as<double>();
+    }
+    const double *fit_stats = nullptr, *ref_stats = nullptr;
+    if (metric == MDSCTK_KNN_CORRELATION) {
+        CK(ctx->d_ref_stats.reserve((size_t)n_ref * 16), "cudaMalloc(ref_stats)");
+        CK(launch_data_rowstats(ctx->d_ref.as<double>(), n_ref, dim, ctx->d_ref_stats.as<double>(), ctx->st), "data_rowstats");
+        ctx->dstats_dirty = false;
+        ref_stats = fit_stats = ctx->d_ref_stats.as<double>();
+        if (fit_rows) {
+            CK(ctx->d_fit_stats.reserve((size_t)n_fit * 16), "cudaMalloc(fit_stats)");
+            CK(launch_data_rowstats(d_fit, n_fit, dim, ctx->d_fit_stats.as<double>(), ctx->st), "data_rowstats");
+            fit_stats = ctx->d_fit_stats.as<double>();
+        }
+    }
+    const size_t row_bytes = (size_t)n_ref * 8;
+    const long long chunk = (long long)std::max<size_t>(1, std::min<size_t>((size_t)n_fit, ((size_t)256 << 20) / row_bytes));
+    CK(ctx->rows_buf.reserve((size_t)chunk * row_bytes), "cudaMalloc(rows_buf)");
+    for (long long off = 0; off < n_fit; off += chunk) {
+        const long long nr = std::min<long long>(chunk, n_fit - off);
+        CK(launch_data_exact_rows(d_fit + (size_t)off * dim, fit_stats ? fit_stats + 2 * off : nullptr, nr, ctx->d_ref.as<double>(),
+                                  ref_stats, n_ref, dim, metric, ctx->rows_buf.as<double>(), ctx->st), "data_exact_rows");
+        CK(cudaMemcpyAsync(out + (size_t)off * n_ref, ctx->rows_buf.p, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, ctx->st),
+           "D2H rows");
+        CK(cudaStreamSynchronize(ctx->st), "sync rows");
+    }
+    return 0;
+}
+
 /* ---------------------------------------------------------------- CSC builder ---- */
 static int csc_build(mdsctk_knn_ctx *ctx, int mode, const int *idx, const double *dist, long long n, int maxk, int k, int *pcol,
                      long long *nnz);

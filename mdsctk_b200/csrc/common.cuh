@@ -92,6 +92,8 @@ cudaError_t launch_data_rowstats(const double *rows, long long n, int dim, doubl
 cudaError_t launch_data_sweep(const double *fit, const double *fit_stats, long long n_fit, const double *ref,
                               const double *ref_stats, long long n_ref, int dim, int metric,
                               CandLists<double> cl, cudaStream_t st);
+cudaError_t launch_data_exact_rows(const double *fit, const double *fit_stats, long long n_fit, const double *ref,
+                                   const double *ref_stats, long long n_ref, int dim, int metric, double *out, cudaStream_t st);
 cudaError_t launch_data_finalize(CandLists<double> cl, long long n_fit, int k1, double *out_dist, int *out_idx,
                                  cudaStream_t st);
 

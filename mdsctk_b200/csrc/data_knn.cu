@@ -195,6 +195,40 @@ cudaError_t launch_data_sweep(const double *fit, const double *fit_stats, long l
     return cudaGetLastError();
 }
 
+// ---- full distance rows (knn_data --sort false, knn_data.cpp:198-216): one thread per pair ----------
+__global__ void data_exact_rows_kernel(const double *__restrict__ fit, const double *__restrict__ fit_stats, long long n_fit,
+                                       const double *__restrict__ ref, const double *__restrict__ ref_stats, long long n_ref,
+                                       int dim, int metric, double *__restrict__ out)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = blockIdx.y;
+    if (r >= n_ref || f >= n_fit) return;
+    const double *fv = fit + (size_t)f * dim, *rv = ref + (size_t)r * dim;
+    double acc = 0.0;
+    if (metric == 0) {
+        for (int x = 0; x < dim; ++x) {
+            const double d = __dsub_rn(fv[x], rv[x]);
+            acc = __dadd_rn(acc, __dmul_rn(d, d));
+        }
+    } else {
+        const double fm = fit_stats[2 * f], fs = fit_stats[2 * f + 1], rm = ref_stats[2 * r], rs = ref_stats[2 * r + 1];
+        for (int x = 0; x < dim; ++x) acc = __dadd_rn(acc, __dmul_rn(__dsub_rn(fv[x], fm), __dsub_rn(rv[x], rm)));
+        const double den = __dmul_rn(__dmul_rn(__dsub_rn((double)dim, 1.0), fs), rs);
+        acc = __ddiv_rn(__dsub_rn(1.0, __ddiv_rn(acc, den)), 2.0);
+        if (acc < 0.0) acc = 0.0;
+    }
+    out[(size_t)f * n_ref + r] = sqrt(acc);
+}
+
+cudaError_t launch_data_exact_rows(const double *fit, const double *fit_stats, long long n_fit, const double *ref,
+                                   const double *ref_stats, long long n_ref, int dim, int metric, double *out, cudaStream_t st)
+{
+    if (n_fit <= 0 || n_ref <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((n_ref + 127) / 128), (unsigned)n_fit);
+    data_exact_rows_kernel<<<grid, 128, 0, st>>>(fit, fit_stats, n_fit, ref, ref_stats, n_ref, dim, metric, out);
+    return cudaGetLastError();
+}
+
 // ---- final (distance, index) sort of the survivors; distance = sqrt(key) --------------------
 __global__ void __launch_bounds__(128) data_finalize_kernel(CandLists<double> cl, int k1, int P, double *out_dist,
                                                             int *out_idx)

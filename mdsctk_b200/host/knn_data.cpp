@@ -110,7 +110,6 @@ int main(int argc, char *argv[])
     std::cout << "done." << std::endl;
     std::cout << "Number of fitting coordinates: " << n_fit << std::endl;
     if (n_ref <= 0 || n_fit <= 0) { std::cout << "ERROR: empty input" << std::endl; return 3; }
-    if (!sort) { std::cout << "ERROR: --sort false (full distance matrix) is not supported by this build" << std::endl; return 6; }
 
     std::ofstream distances(d_filename.c_str(), std::ios::binary | std::ios::trunc);
     std::ofstream indices(i_filename.c_str(), std::ios::binary | std::ios::trunc);
@@ -132,12 +131,37 @@ int main(int argc, char *argv[])
             return 5;
         }
     }
+    const int metric = corr ? MDSCTK_KNN_CORRELATION : MDSCTK_KNN_EUCLIDEAN;
+    if (!sort) {
+        // full rows in reference order (knn_data.cpp:198-216).  The reference writes its never-filled index
+        // vector here (undefined behaviour); this build writes the identity permutation, like knn_rms.
+        const long long rows = std::max<long long>(1, std::min<long long>(n_fit, (64LL << 20) / (n_ref * 8)));
+        std::vector<double> buf((size_t)rows * n_ref);
+        std::vector<int> ident((size_t)n_ref);
+        for (long long j = 0; j < n_ref; ++j) ident[(size_t)j] = (int)j;
+        int rc = 0;
+        for (long long f = 0; f < n_fit && rc == 0; f += rows) {
+            const long long n = std::min(rows, n_fit - f);
+            const double *fr = (same ? ref.data() : fit.data()) + (size_t)f * vector_size;
+            if (mdsctk_knn_data_rows(ctx[0], fr, n, metric, buf.data()) != 0) {
+                std::cout << "ERROR: " << mdsctk_knn_last_error(ctx[0]) << std::endl;
+                rc = 5;
+                break;
+            }
+            for (long long r = 0; r < n; ++r) {
+                distances.write(reinterpret_cast<const char *>(&buf[(size_t)r * n_ref]), (std::streamsize)(sizeof(double) * n_ref));
+                indices.write(reinterpret_cast<const char *>(ident.data()), (std::streamsize)(sizeof(int) * n_ref));
+            }
+        }
+        std::cout << std::endl << std::endl;
+        for (auto *c : ctx) mdsctk_knn_destroy(c);
+        return rc;
+    }
     std::vector<double> dist((size_t)n_fit * k1);
     std::vector<int> idx((size_t)n_fit * k1);
     std::vector<std::thread> pool;
     std::vector<int> status(ngpus, 0);
     const long long shard = (n_fit + ngpus - 1) / ngpus;
-    const int metric = corr ? MDSCTK_KNN_CORRELATION : MDSCTK_KNN_EUCLIDEAN;
     for (int g = 0; g < ngpus; ++g) {
         pool.emplace_back([&, g]() {
             const long long b = std::min(n_fit, g * shard), n = std::min(shard, n_fit - b);

@@ -180,6 +180,29 @@ def test_knn_data_wide_rows(ctx):
     assert np.array_equal(idx, i) and np.array_equal(dist, d)
 
 
+def test_knn_data_full_rows_sort_false(ctx, tmp_path):
+    """knn_data --sort false (knn_data.cpp:198-216): full rows, bit-identical to the oracle's distance functions."""
+    import subprocess
+    from oracle import binding as ob
+    L = ob.lib()
+    sw = load_pts("swissroll.pts", 3)[:60]
+    fit = load_pts("swissroll-outofsample.pts", 3)[:25]
+    ctx.data_set_reference(sw)
+    for metric, fn in ((0, L.oracle_euclidean_distance), (1, L.oracle_correlation_distance)):
+        for f in (None, fit):
+            rows = ctx.data_rows(f, metric=metric)
+            q = sw if f is None else f
+            want = np.array([[fn(3, ob._d(np.ascontiguousarray(a)), ob._d(np.ascontiguousarray(b))) for b in sw] for a in q])
+            assert rows.shape == want.shape and np.array_equal(rows, want), (metric, f is None)
+    sw.tofile(tmp_path / "ref.pts")
+    tool = os.path.join(os.path.dirname(os.path.dirname(GOLDEN)), "mdsctk_b200", "bin", "knn_data")
+    p = subprocess.run([tool, "-v", "3", "-s", "false", "-r", "ref.pts"], capture_output=True, text=True, cwd=tmp_path)
+    assert p.returncode == 0, p.stdout
+    d = np.fromfile(tmp_path / "distances.dat", dtype=np.float64).reshape(60, 60)
+    i = np.fromfile(tmp_path / "indices.dat", dtype=np.int32).reshape(60, 60)
+    assert np.array_equal(d, ctx.data_rows(None, metric=0)) and (i == np.arange(60)[None, :]).all()
+
+
 def test_errors_are_reported_not_thrown(ctx, trpcage):
     import mdsctk_b200
     xyz, mass = trpcage

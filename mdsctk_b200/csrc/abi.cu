@@ -401,7 +401,7 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
     const int cap = data_tc_list_stride(keep);
     const int n_seg = data_tc_choose_segments(n_fit, n_ref, ctx->n_sms);
     S.k_keep = keep; S.lists_per_row = n_seg;
-    if ((size_t)dim * 8 + (size_t)keep * n_seg * 2 * 28 > 200 * 1024) return 1;   // re-score working set: exact path instead
+    if ((size_t)dim * 8 + (size_t)keep * n_seg * 2 * 28 > 170 * 1024) return 1;   // re-score working set: exact path instead
     CandLists<float> cl;
     CK(ctx->cand_key.reserve((size_t)n_fit * n_seg * cap * 4), "cudaMalloc(cand_key)");
     CK(ctx->cand_idx.reserve((size_t)n_fit * n_seg * cap * 4), "cudaMalloc(cand_idx)");

@@ -472,6 +472,7 @@ struct DataRescoreArgs {
 };
 
 constexpr int DRESCORE_ROUND = 128;   // upper bound of a round (one candidate per thread)
+constexpr int DCHUNK = 32;            // dims staged per step: [128][33] doubles = 33 KB of shared memory
 
 __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
 {
@@ -483,12 +484,14 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
     int *s_i = reinterpret_cast<int *>(u_key + P);           // [P]
     int *u_i = s_i + P;                                      // [P]
     float *u_apx = reinterpret_cast<float *>(u_i + P);       // [P]
+    double *s_chunk = reinterpret_cast<double *>(dsm + (((size_t)D * 8 + (size_t)P * 28 + 15) & ~(size_t)15));   // [128][DCHUNK + 1]
     __shared__ int s_total, s_ok;
     __shared__ float s_taumin;
     __shared__ unsigned s_dtil;
     __shared__ unsigned long long s_emin, s_emax;
 
     const long long q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int x = threadIdx.x; x < D; x += blockDim.x) fq[x] = a.fit[(size_t)q * D + x];
     const double kInfD = __longlong_as_double(0x7ff0000000000000LL);
     const float kInfF = __uint_as_float(0x7f800000u);
@@ -528,13 +531,26 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
     while (done < total) {
         // first round: just enough candidates to fill the k-list; then 32 more at a time
         const int nb = min(done == 0 ? min(DRESCORE_ROUND, (k1 + 31) / 32 * 32) : 32, total - done);
-        if (threadIdx.x < nb) {
-            const double *rv = a.ref + (size_t)u_i[done + threadIdx.x] * D;
-            double sum = 0.0;
-            for (int x = 0; x < D; ++x) {
-                const double d = __dsub_rn(fq[x], rv[x]);
-                sum = __dadd_rn(sum, __dmul_rn(d, d));
+        // candidate rows are staged through shared memory in chunks of DCHUNK dims with coalesced loads
+        // (a warp per candidate); thread c then adds its candidate's terms in the reference's order
+        double sum = 0.0;
+        for (int x0 = 0; x0 < D; x0 += DCHUNK) {
+            const int w = min(DCHUNK, D - x0);
+            for (int c = warp; c < nb; c += 4) {
+                const double *rv = a.ref + (size_t)u_i[done + c] * D + x0;
+                for (int x = lane; x < w; x += 32) s_chunk[c * (DCHUNK + 1) + x] = rv[x];
             }
+            __syncthreads();
+            if (threadIdx.x < nb) {
+                const double *rc = s_chunk + threadIdx.x * (DCHUNK + 1);
+                for (int x = 0; x < w; ++x) {
+                    const double d = __dsub_rn(fq[x0 + x], rc[x]);
+                    sum = __dadd_rn(sum, __dmul_rn(d, d));
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < nb) {
             u_key[done + threadIdx.x] = sum;
             const double err = (double)u_apx[done + threadIdx.x] - sum;
             unsigned long long bits = (unsigned long long)__double_as_longlong(err);
@@ -544,10 +560,12 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
         }
         __syncthreads();
         done += nb;
-        for (int i = threadIdx.x; i < Pr; i += blockDim.x) { s_d[i] = u_key[i]; s_i[i] = u_i[i]; }
+        int Ps = 32;                       // only the re-scored prefix carries finite keys
+        while (Ps < done) Ps <<= 1;
+        for (int i = threadIdx.x; i < Ps; i += blockDim.x) { s_d[i] = u_key[i]; s_i[i] = u_i[i]; }
         if (threadIdx.x == 0) s_dtil = 0u;
         __syncthreads();
-        block_bitonic_sort(s_d, s_i, Pr);
+        block_bitonic_sort(s_d, s_i, Ps);
         if (done >= k1) {
             const double dk = s_d[k1 - 1];
             const int ik = s_i[k1 - 1];
@@ -613,7 +631,7 @@ cudaError_t launch_data_rescore(const double *fit, const double *ref, long long 
     int P = 32;
     while (P < cl.keep * cl.H) P <<= 1;
     a.P = P;
-    const size_t smem = (size_t)dim * 8 + (size_t)P * 28;
+    const size_t smem = (((size_t)dim * 8 + (size_t)P * 28 + 15) & ~(size_t)15) + (size_t)DRESCORE_ROUND * (DCHUNK + 1) * 8;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(data_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -204,10 +204,12 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
         __syncthreads();
         done += nb;
         // ---- 2. order + certificate ----------------------------------------------------------------
-        for (int i = threadIdx.x; i < Pr; i += blockDim.x) { s_d[i] = u_dist[i]; s_i[i] = u_i[i]; }
+        int Ps = 32;                       // only the re-scored prefix carries finite keys
+        while (Ps < done) Ps <<= 1;
+        for (int i = threadIdx.x; i < Ps; i += blockDim.x) { s_d[i] = u_dist[i]; s_i[i] = u_i[i]; }
         if (threadIdx.x == 0) s_dtil = 0u;
         __syncthreads();
-        block_bitonic_sort(s_d, s_i, Pr);
+        block_bitonic_sort(s_d, s_i, Ps);
         if (done >= k1) {
             const double dk = s_d[k1 - 1];
             const int ik = s_i[k1 - 1];

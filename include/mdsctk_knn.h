@@ -59,7 +59,7 @@ enum {
     MDSCTK_KNN_RMS_TC_3XTF32 = 1,  /* tcgen05 kind::tf32, hi/lo operand split (3 MMAs)              */
     MDSCTK_KNN_RMS_TC_1XTF32 = 2,  /* tcgen05 kind::tf32, hi only (coarse filter)                   */
     MDSCTK_KNN_RMS_TC_3XBF16 = 3,  /* tcgen05 kind::f16 on bf16 hi/mid operand split (3 MMAs)       */
-    MDSCTK_KNN_RMS_TC_3XFP16 = 4,  /* tcgen05 kind::f16 on fp16 hi/lo split of 64x (3 MMAs, 22 bits) */
+    MDSCTK_KNN_RMS_TC_3XFP16 = 4,  /* tcgen05 kind::f16 on fp16 hi/lo split of 64x (3 MMAs, 22 bits): DEFAULT */
     MDSCTK_KNN_RMS_TC_2XFP16 = 5   /* fit operand fp16 hi only, reference hi/lo (2 MMAs)            */
 };
 

@@ -11,6 +11,8 @@
 //                        exact FP64 full rows + exact selection for rows whose certificate
 //                        failed (and the diagnostic mdsctk_knn_rms_rows entry point).
 #include "common.cuh"
+
+#include <algorithm>
 #include "sort.cuh"
 
 namespace mdsctk {
@@ -294,6 +296,7 @@ struct ExactRowsArgs {
     const double *wnorm;
     int do_fit;
     double *out;  // [n_rows][n_ref] d^2 in nm^2
+    long long ref_block0;
 };
 
 __global__ void __launch_bounds__(128) rms_exact_rows_kernel(ExactRowsArgs a)
@@ -301,14 +304,16 @@ __global__ void __launch_bounds__(128) rms_exact_rows_kernel(ExactRowsArgs a)
     extern __shared__ __align__(16) unsigned char dsm[];
     double *wq = reinterpret_cast<double *>(dsm);
     const int A = a.fit.A;
-    const int row = blockIdx.y;
+    // rows vary fastest across the grid: the blocks that share a block of reference frames run together, so
+    // the frames come from L2 for all but the first row (a row alone streams the whole raw set from HBM)
+    const int row = blockIdx.x;
     const long long qf = a.fit_begin + (a.row_ids ? a.row_ids[row] : row);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double *cen_q = a.fit.cen + 4 * qf;
     load_fit_frame(wq, a.fit.raw + (size_t)qf * A * 3, cen_q, a.wnorm, A);
     __syncthreads();
     const double gq = cen_q[3];
-    const long long base = ((long long)blockIdx.x * 4 + warp) * 32;
+    const long long base = ((a.ref_block0 + (long long)blockIdx.y) * 4 + warp) * 32;
     if (base >= a.ref.n) return;
     const int nb = (int)min((long long)32, a.ref.n - base);
     double S[9];
@@ -342,8 +347,13 @@ cudaError_t launch_rms_exact_rows(const FrameSetView &fit, const int *row_ids, l
     const size_t smem = (size_t)fit.A * 3 * 8;
     cudaError_t e = cudaFuncSetAttribute(rms_exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((unsigned)((ref.n + 127) / 128), (unsigned)n_rows);
-    rms_exact_rows_kernel<<<grid, 128, smem, st>>>(a);
+    const long long ref_blocks = (ref.n + 127) / 128;
+    for (long long b0 = 0; b0 < ref_blocks; b0 += 65535) {      // gridDim.y limit
+        ExactRowsArgs c = a;
+        c.ref_block0 = b0;
+        dim3 grid((unsigned)n_rows, (unsigned)std::min<long long>(65535, ref_blocks - b0));
+        rms_exact_rows_kernel<<<grid, 128, smem, st>>>(c);
+    }
     return cudaGetLastError();
 }
 

@@ -17,6 +17,8 @@ if os.environ.get("ITER_SLACK"):
     pass
 mass = synth.traj_masses(300)
 ctx = mdsctk_b200.KnnContext(0)
+if os.environ.get("ITER_CERT_PPM"):
+    ctx.set_option("cert_scale_ppm", int(os.environ["ITER_CERT_PPM"]))
 if os.environ.get("ITER_SLACK"):
     ctx.set_option("slack", int(os.environ["ITER_SLACK"]))
 ctx.rms_set_reference(xyz, mass)

@@ -322,7 +322,7 @@ def main():
                 4: "rms_sweep_tc_kernel<4> (tcgen05 cta_group::2 kind::f16, 3xFP16 split contraction + QCP bounds + streaming top-k)",
                 5: "rms_sweep_tc_kernel<5> (tcgen05 cta_group::2 kind::f16, 2xFP16 contraction + QCP bounds + streaming top-k)"}[st["rms_kernel"]]
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_r01b.json")
+        tp = os.path.join(ROOT, "profiles", "traffic_r01c.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(str(st["rms_kernel"]))
         line = {

@@ -52,6 +52,8 @@ def lib():
         L.oracle_make_sysparse.restype = C.c_longlong
         L.oracle_make_gesparse.argtypes = [ip, dp, C.c_longlong, C.c_int, C.c_int, C.c_int, ip, ip, dp]
         L.oracle_make_gesparse.restype = C.c_longlong
+        lp = C.POINTER(C.c_longlong)
+        L.oracle_knn_data_sparse.argtypes = [lp, ip, dp, C.c_longlong, lp, ip, dp, C.c_longlong, C.c_int, dp, ip]
         L.oracle_phipsi.argtypes = [fp, C.c_longlong, C.c_int, dp]
         L.oracle_phipsi.restype = None
         L.oracle_sincos.argtypes = [dp, C.c_longlong, dp]
@@ -220,3 +222,29 @@ def sincos(angles):
     out = np.empty(angles.size * 2, dtype=np.float64)
     lib().oracle_sincos(_d(angles), angles.size, _d(out))
     return out
+
+
+def _csr(vectors):
+    """[(idx int array, val double array), ...] -> offsets, indices, values."""
+    off = np.zeros(len(vectors) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(i) for i, _ in vectors])
+    idx = np.concatenate([np.asarray(i, dtype=np.int32) for i, _ in vectors]) if len(vectors) else np.zeros(0, np.int32)
+    val = np.concatenate([np.asarray(v, dtype=np.float64) for _, v in vectors]) if len(vectors) else np.zeros(0)
+    return off, np.ascontiguousarray(idx, dtype=np.int32), np.ascontiguousarray(val, dtype=np.float64)
+
+
+def knn_data_sparse(ref, k, fit=None):
+    """What knn_data_sparse writes for sparse vectors given as [(indices, values), ...]."""
+    fit = ref if fit is None else fit
+    ro, ri, rv = _csr(ref)
+    fo, fi, fv = _csr(fit)
+    k = min(k, len(ref) - 1)
+    dist = np.empty((len(fit), k), dtype=np.float64)
+    idx = np.empty((len(fit), k), dtype=np.int32)
+    lp = C.POINTER(C.c_longlong)
+    rc = lib().oracle_knn_data_sparse(ro.ctypes.data_as(lp), ri.ctypes.data_as(C.POINTER(C.c_int)), _d(rv), len(ref),
+                                      fo.ctypes.data_as(lp), fi.ctypes.data_as(C.POINTER(C.c_int)), _d(fv), len(fit), k,
+                                      _d(dist), idx.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc != 0:
+        raise ValueError("oracle_knn_data_sparse failed")
+    return dist, idx

@@ -198,3 +198,50 @@ int oracle_knn_data(int metric, int dim, const double *ref, long long n_ref, con
     }
     return 0;
 }
+
+/* euclidean_distance_sparse, mdsctk.cpp:362-386: merge of two ascending index lists; a dimension present in
+ * one vector only contributes its square, terms are added in ascending index order. */
+double oracle_euclidean_distance_sparse(int ref_size, const int *ref_index, const double *ref_data, int fit_size,
+                                        const int *fit_index, const double *fit_data)
+{
+    double value = 0.0;
+    int ref = 0, fit = 0;
+    for (ref = 0; ref < ref_size; ref++) {
+        while (fit < fit_size && fit_index[fit] < ref_index[ref]) {
+            value += (fit_data[fit] * fit_data[fit]);
+            fit++;
+        }
+        if (fit < fit_size && ref_index[ref] == fit_index[fit]) {
+            value += ((ref_data[ref] - fit_data[fit]) * (ref_data[ref] - fit_data[fit]));
+            fit++;
+        } else {
+            value += (ref_data[ref] * ref_data[ref]);
+        }
+    }
+    for (; fit < fit_size; fit++) value += (fit_data[fit] * fit_data[fit]);
+    return sqrt(value);
+}
+
+/* knn_data_sparse.cpp:195-262 row loop on CSR-style inputs: vector v = entries [off[v], off[v+1]). */
+int oracle_knn_data_sparse(const long long *ref_off, const int *ref_idx, const double *ref_val, long long n_ref,
+                           const long long *fit_off, const int *fit_idx, const double *fit_val, long long n_fit, int k,
+                           double *out_dist, int *out_idx)
+{
+    if (k < 0 || k > n_ref - 1) return -2;
+    const int k1 = k + 1;
+    double *row = (double *)malloc(sizeof(double) * (size_t)n_ref);
+    cand *heap = (cand *)malloc(sizeof(cand) * (size_t)k1);
+    for (long long f = 0; f < n_fit; f++) {
+        for (long long r = 0; r < n_ref; r++)
+            row[r] = oracle_euclidean_distance_sparse((int)(ref_off[r + 1] - ref_off[r]), ref_idx + ref_off[r], ref_val + ref_off[r],
+                                                      (int)(fit_off[f + 1] - fit_off[f]), fit_idx + fit_off[f], fit_val + fit_off[f]);
+        select_smallest(row, n_ref, k1, heap);
+        for (int j = 0; j < k; j++) {
+            out_dist[(size_t)f * k + j] = heap[j + 1].v;
+            out_idx[(size_t)f * k + j] = heap[j + 1].i;
+        }
+    }
+    free(row);
+    free(heap);
+    return 0;
+}

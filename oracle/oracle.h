@@ -87,6 +87,13 @@ int oracle_rms_rows(int mode, int natoms, const float *mass,
 int oracle_max_threads(void);
 
 /* make_sysparse (make_sysparse.cpp:245-329): symmetric CSC from the kNN files; returns nnz (csc.c). */
+/* knn_data_sparse (mdsctk.cpp:362-386, knn_data_sparse.cpp:195-262); vectors in CSR form */
+double oracle_euclidean_distance_sparse(int ref_size, const int *ref_index, const double *ref_data, int fit_size,
+                                        const int *fit_index, const double *fit_data);
+int oracle_knn_data_sparse(const long long *ref_off, const int *ref_idx, const double *ref_val, long long n_ref,
+                           const long long *fit_off, const int *fit_idx, const double *fit_val, long long n_fit, int k,
+                           double *out_dist, int *out_idx);
+
 /* bb_xtc_to_phipsi / angles_to_sincos (featurize.c) */
 float oracle_torsion(const float *pos1, const float *pos2, const float *pos3, const float *pos4);
 void oracle_phipsi(const float *xyz, long long n, int natoms, double *phipsi);

@@ -31,6 +31,9 @@ for spec in os.environ.get("ITER_DBG", "0 1").split():
         for rep in range(int(os.environ.get("ITER_REPS", "2"))):
             ctx.rms_query(k1, fetch=False, fit_range=(int(os.environ.get("ITER_ROW0", "0")), rows) if rows else None)
         st = ctx.stats()
+        import time as _t
+        ctx.timer_start(); ctx.rms_query(k1, fetch=False, fit_range=(int(os.environ.get("ITER_ROW0", "0")), rows) if rows else None); tot_ms = ctx.timer_stop()
+        print("step_ms %.2f" % tot_ms, end=" ")
         print("kernel", kern, "dbg", dbg, {k: (round(st[k], 3) if isinstance(st[k], float) else st[k]) for k in
                            ("ms_sweep", "ms_rescore", "ms_fallback", "fallback_rows", "lists_per_row", "k_keep", "rescored_max")},
               "spread %.2e err %.2e eps %.2e" % (st["max_filter_spread"], st["max_filter_err"], st["cert_eps"]),

@@ -160,6 +160,19 @@ int mdsctk_knn_csc_build_general(mdsctk_knn_ctx *ctx, const int *idx, const doub
                                  int symmetric, int *pcol, long long *nnz);
 int mdsctk_knn_csc_fetch(mdsctk_knn_ctx *ctx, int *irow, double *val);
 
+/* ---- spectral stage: auto_decomp_sparse.cpp:150-236 / decomp_sparse ------------------------------------
+ * pcol[n+1], irow[nnz], val[nnz]: host, the symmetric CSC matrix as make_sysparse writes it (strict upper
+ * triangle).  k_sigma > 0: the values are distances; they are turned into Gaussian affinities with per-frame
+ * sigmas (mean of the first k_sigma values of a frame in CSC traversal order) and normalised D^-1/2 W D^-1/2
+ * (auto_decomp_sparse.cpp:150-198); k_sigma <= 0 and sigma > 0: one global sigma (decomp_sparse.cpp:150-175);
+ * both <= 0: the matrix is decomposed as given.
+ * Output: the nev algebraically largest eigenvalues, LARGEST FIRST (the order the tool writes them),
+ * evecs[nev][n] (unit vectors; the sign of an eigenvector is arbitrary, as with ARPACK), residuals[nev] =
+ * |A z - d z| / |d|, the average sigma, and the number of converged pairs.  ARPACK (runARPACK,
+ * mdsctk.cpp:857-924) is replaced by a thick-restart Lanczos with the same basis size ncv = 10*nev+1. */
+int mdsctk_knn_spectral_decomp(mdsctk_knn_ctx *ctx, int n, const int *pcol, const int *irow, const double *val, int k_sigma,
+                               double sigma, int nev, double *evals, double *evecs, double *residuals, double *avg_sigma, int *n_converged);
+
 /* ---- producers of knn_data's input: backbone phi/psi angles and their sin/cos embedding -------------
  * xyz: host, float[n_frames][n_atoms][3] (nm), backbone atoms N-CA-C only, one chain
  * (bb_xtc_to_phipsi.cpp:106-122).  T = 2*(n_atoms/3) - 2 angles per frame (radians, torsion() of

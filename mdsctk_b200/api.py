@@ -25,7 +25,7 @@ SYMBOLS = [
     "mdsctk_knn_data_upload_shard", "mdsctk_knn_data_reference_arrays", "mdsctk_knn_data_query_range",
     "mdsctk_knn_fetch", "mdsctk_knn_rms_rows", "mdsctk_knn_timer_start", "mdsctk_knn_timer_stop",
     "mdsctk_knn_debug_fetch_tile", "mdsctk_knn_csc_build_sym", "mdsctk_knn_csc_build_general", "mdsctk_knn_csc_fetch",
-    "mdsctk_knn_phipsi", "mdsctk_knn_sincos", "mdsctk_knn_data_rows",
+    "mdsctk_knn_phipsi", "mdsctk_knn_sincos", "mdsctk_knn_data_rows", "mdsctk_knn_spectral_decomp",
 ]
 
 
@@ -90,6 +90,7 @@ def load_library():
     L.mdsctk_knn_csc_build_general.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_fetch.argtypes = [vp, ip, dp]
     L.mdsctk_knn_data_rows.argtypes = [vp, dp, ll, C.c_int, dp]
+    L.mdsctk_knn_spectral_decomp.argtypes = [vp, C.c_int, ip, ip, dp, C.c_int, C.c_double, C.c_int, dp, dp, dp, dp, ip]
     L.mdsctk_knn_phipsi.argtypes = [vp, fp, ll, C.c_int, dp, dp]
     L.mdsctk_knn_sincos.argtypes = [vp, dp, ll, dp]
     _LIB = L
@@ -250,6 +251,20 @@ class KnnContext:
         self._ck(self._L.mdsctk_knn_data_rows(self._h, _ptr(fit, C.c_double), n_fit, int(metric), _ptr(out, C.c_double)),
                  "data_rows")
         return out
+
+    def spectral_decomp(self, pcol, irow, val, nev, k_sigma=0, sigma=0.0):
+        """auto_decomp_sparse (k_sigma > 0) / decomp_sparse (k_sigma = 0): (evals[nev] largest first, evecs[nev, n],
+        residuals[nev], average sigma, converged pairs)."""
+        pcol = np.ascontiguousarray(pcol, dtype=np.int32)
+        irow = np.ascontiguousarray(irow, dtype=np.int32)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        n = pcol.size - 1
+        ev, vec, res = np.empty(nev), np.empty((nev, n)), np.empty(nev)
+        avg, nconv = C.c_double(0.0), C.c_int(0)
+        self._ck(self._L.mdsctk_knn_spectral_decomp(self._h, n, _ptr(pcol, C.c_int), _ptr(irow, C.c_int), _ptr(val, C.c_double),
+                                                    int(k_sigma), float(sigma), int(nev), _ptr(ev, C.c_double), _ptr(vec, C.c_double),
+                                                    _ptr(res, C.c_double), C.byref(avg), C.byref(nconv)), "spectral_decomp")
+        return ev, vec, res, avg.value, nconv.value
 
     def phipsi(self, xyz, want_angles=True, want_sincos=True):
         """Backbone torsions (bb_xtc_to_phipsi) and their sin/cos embedding (angles_to_sincos) of N-CA-C frames."""

@@ -67,7 +67,7 @@ def build_tools(force=False):
     mk = os.path.join(HOST, "Makefile")
     if os.path.exists(mk):
         subprocess.check_call(["make", "-s", "-C", HOST] + (["-B"] if force else []))
-    return [os.path.join(PKG, "bin", t) for t in ("knn_rms", "knn_data", "flatten_xtc", "make_sysparse", "make_gesparse", "bb_xtc_to_phipsi", "angles_to_sincos", "knn_data_sparse")]
+    return [os.path.join(PKG, "bin", t) for t in ("knn_rms", "knn_data", "flatten_xtc", "make_sysparse", "make_gesparse", "bb_xtc_to_phipsi", "angles_to_sincos", "knn_data_sparse", "auto_decomp_sparse", "decomp_sparse")]
 
 
 def build_all(force=False, verbose=False):

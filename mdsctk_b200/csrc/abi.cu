@@ -121,6 +121,7 @@ struct mdsctk_knn_ctx {
     // CSC builder state (csc.cu)
     DevBuf c_idx, c_dist, c_ints, c_key, c_val, c_irow, c_oval;
     DevBuf f_in, f_ang, f_sc;   // featuriser buffers
+    DevBuf s_int, s_val, s_vec, s_basis, s_rot, s_small, s_evec;   // spectral stage
     long long c_nnz = -1;
     // scratch + results
     DevBuf cand_key, cand_idx, cand_cnt, cand_tau, flags, bad_rows, scalars, rows_buf;
@@ -952,6 +953,66 @@ int mdsctk_knn_csc_fetch(mdsctk_knn_ctx *ctx, int *irow, double *val)
     CK(cudaMemcpyAsync(irow, ctx->c_irow.p, (size_t)ctx->c_nnz * 4, cudaMemcpyDeviceToHost, ctx->st), "D2H irow");
     CK(cudaMemcpyAsync(val, ctx->c_oval.p, (size_t)ctx->c_nnz * 8, cudaMemcpyDeviceToHost, ctx->st), "D2H val");
     ctx->stats.ms_download += ctx->tm.stop(ctx->st);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- spectral stage ---- */
+int mdsctk_knn_spectral_decomp(mdsctk_knn_ctx *ctx, int n, const int *pcol, const int *irow, const double *val, int k_sigma,
+                               double sigma, int nev, double *evals, double *evecs, double *residuals, double *avg_sigma, int *n_converged)
+{
+    if (!ctx) return MDSCTK_KNN_EINVAL;
+    if (!pcol || !irow || !val || !evals || !evecs || !residuals || n < 2 || nev < 1 || nev >= n)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "spectral_decomp: need n >= 2, 1 <= nev < n and non-NULL arrays");
+    const int nnz = pcol[n];
+    if (nnz < 0) return fail(ctx, MDSCTK_KNN_EINVAL, "spectral_decomp: bad pcol");
+    Bind b(ctx);
+    mdsctk_knn_stats &S = ctx->stats;
+    S.ms_upload = S.ms_pack = S.ms_sweep = S.ms_download = 0; S.launches = 0;
+    const int ncv = std::min(n, 10 * nev + 1);                       // runARPACK, mdsctk.cpp:869
+    const size_t nscan = (size_t)n / 1024 + (size_t)n / (1024 * 1024) + 16;
+    // ints: pcol (n+1) | irow (nnz) | ptr (n+1) | n_as_row (n+1) | cur (n+1) | scan_tmp | adj_other (2nnz) | adj_pos (2nnz)
+    CK(ctx->s_int.reserve(((size_t)4 * (n + 1) + nscan + (size_t)5 * std::max(nnz, 1)) * 4), "cudaMalloc(spectral ints)");
+    CK(ctx->s_val.reserve((size_t)std::max(nnz, 1) * 8), "cudaMalloc(spectral values)");
+    CK(ctx->s_vec.reserve((size_t)2 * n * 8), "cudaMalloc(sigma, dinv)");
+    CK(ctx->s_basis.reserve((size_t)(ncv + 1) * n * 8), "cudaMalloc(Lanczos basis)");
+    CK(ctx->s_rot.reserve((size_t)ncv * n * 8), "cudaMalloc(rotation scratch)");
+    CK(ctx->s_small.reserve(((size_t)(296 + 2) * (ncv + 1) + (size_t)ncv * ncv) * 8), "cudaMalloc(small)");
+    CK(ctx->s_evec.reserve((size_t)nev * n * 8), "cudaMalloc(eigenvectors)");
+    int *d_pcol = ctx->s_int.as<int>(), *d_irow = d_pcol + (n + 1), *d_ptr = d_irow + std::max(nnz, 1), *d_asrow = d_ptr + (n + 1);
+    int *d_cur = d_asrow + (n + 1), *d_scan = d_cur + (n + 1), *d_other = d_scan + nscan, *d_pos = d_other + 2 * (size_t)std::max(nnz, 1);
+    double *d_M = ctx->s_val.as<double>(), *d_sigma = ctx->s_vec.as<double>(), *d_dinv = d_sigma + n;
+    ctx->tm.start(ctx->st);
+    CK(cudaMemcpyAsync(d_pcol, pcol, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->st), "H2D pcol");
+    CK(cudaMemcpyAsync(d_irow, irow, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->st), "H2D irow");
+    CK(cudaMemcpyAsync(d_M, val, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->st), "H2D values");
+    S.ms_upload = ctx->tm.stop(ctx->st);
+    ctx->tm.start(ctx->st);
+    CK(launch_spectral_adjacency(n, nnz, d_pcol, d_irow, d_ptr, d_asrow, d_cur, d_scan, d_other, d_pos, exclusive_scan, ctx->st),
+       "spectral adjacency");
+    double avg = 0.0;
+    if (k_sigma > 0 || sigma > 0.0) {
+        CK(launch_spectral_affinity(n, d_pcol, d_irow, d_ptr, d_pos, k_sigma, sigma, d_M, d_sigma, d_dinv, ctx->st), "spectral affinity");
+        std::vector<double> hs((size_t)n);
+        CK(cudaMemcpyAsync(hs.data(), d_sigma, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->st), "D2H sigma");
+        CK(cudaStreamSynchronize(ctx->st), "sync sigma");
+        for (int i = 0; i < n; ++i) avg += hs[(size_t)i];       // auto_decomp_sparse.cpp:199-201
+        avg /= (double)n;
+    }
+    if (avg_sigma) *avg_sigma = avg;
+    S.ms_pack = ctx->tm.stop(ctx->st);
+    CK(cudaGetLastError(), "spectral affinity kernels");
+    ctx->tm.start(ctx->st);
+    int nconv = 0, nrestart = 0, nspmv = 0;
+    CK(spectral_lanczos(n, d_ptr, d_other, d_pos, d_M, nev, ncv, 100 * nev, 1e-13, ctx->s_basis.as<double>(), ctx->s_rot.as<double>(),
+                        ctx->s_small.as<double>(), evals, ctx->s_evec.as<double>(), residuals, &nconv, &nrestart, &nspmv, ctx->st),
+       "spectral_lanczos");
+    S.ms_sweep = ctx->tm.stop(ctx->st);
+    if (n_converged) *n_converged = nconv;
+    S.launches = nspmv; S.rescored_max = nrestart;
+    ctx->tm.start(ctx->st);
+    CK(cudaMemcpyAsync(evecs, ctx->s_evec.p, (size_t)nev * n * 8, cudaMemcpyDeviceToHost, ctx->st), "D2H eigenvectors");
+    S.ms_download = ctx->tm.stop(ctx->st);
+    S.pairs = (long long)nnz;
     return 0;
 }
 

@@ -122,6 +122,21 @@ cudaError_t launch_csc_build(int mode, const int *d_idx, const double *d_dist, l
                              int *off, int *fin, int *pcol, int *scan_tmp, unsigned long long *seg_key, double *seg_val,
                              int *irow, double *val, cudaStream_t st);
 
+// out[i] = sum in[0..i) (csc.cu); out may alias in; tmp: n/1024 + n/1024^2 + 8 ints
+cudaError_t exclusive_scan(const int *in, int *out, long long n, int *tmp, cudaStream_t st);
+
+// Spectral stage (spectral.cu; replaces auto_decomp_sparse.cpp:150-198 and runARPACK, mdsctk.cpp:857-924).
+cudaError_t launch_spectral_adjacency(int n, int nnz, const int *pcol, const int *irow, int *deg_ptr, int *n_as_row, int *cur,
+                                      int *scan_tmp, int *adj_other, int *adj_pos,
+                                      cudaError_t (*scan)(const int *, int *, long long, int *, cudaStream_t), cudaStream_t st);
+cudaError_t launch_spectral_affinity(int n, const int *pcol, const int *irow, const int *ptr, const int *adj_pos, int k_a, double sigma0, double *M,
+                                     double *sigma, double *dinv, cudaStream_t st);
+cudaError_t launch_spectral_spmv(int n, const int *ptr, const int *adj_other, const int *adj_pos, const double *M, const double *x,
+                                 double *y, cudaStream_t st);
+cudaError_t spectral_lanczos(int n, const int *ptr, const int *adj_other, const int *adj_pos, const double *M, int nev, int ncv,
+                             int max_restarts, double tol, double *V, double *W, double *small, double *evals, double *d_evecs,
+                             double *residuals, int *n_conv, int *n_restart, int *n_spmv, cudaStream_t st);
+
 // Featurisers (featurize.cu): backbone torsions and the sin/cos embedding.
 cudaError_t launch_phipsi(const float *xyz, long long n, int A, double *phipsi, double *sincos, cudaStream_t st);
 cudaError_t launch_sincos(const double *angles, long long n, double *out, cudaStream_t st);

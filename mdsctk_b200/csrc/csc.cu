@@ -82,7 +82,7 @@ __global__ void scan_add_kernel(int *__restrict__ out, const int *__restrict__ b
 }
 
 // out[i] = sum of in[0..i), out may alias in; tmp: two levels of block sums (ceil(n/1024) + ceil(n/1024^2) + 2 ints)
-static cudaError_t exclusive_scan(const int *in, int *out, long long n, int *tmp, cudaStream_t st)
+cudaError_t exclusive_scan(const int *in, int *out, long long n, int *tmp, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
     const long long nb = (n + csc::SCAN_BLOCK - 1) / csc::SCAN_BLOCK;

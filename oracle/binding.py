@@ -54,6 +54,9 @@ def lib():
         L.oracle_make_gesparse.restype = C.c_longlong
         lp = C.POINTER(C.c_longlong)
         L.oracle_knn_data_sparse.argtypes = [lp, ip, dp, C.c_longlong, lp, ip, dp, C.c_longlong, C.c_int, dp, ip]
+        L.oracle_affinity.argtypes = [C.c_int, ip, ip, dp, C.c_int]
+        L.oracle_affinity.restype = C.c_double
+        L.oracle_sym_eigs_largest.argtypes = [C.c_int, ip, ip, dp, C.c_int, dp, dp, dp]
         L.oracle_phipsi.argtypes = [fp, C.c_longlong, C.c_int, dp]
         L.oracle_phipsi.restype = None
         L.oracle_sincos.argtypes = [dp, C.c_longlong, dp]
@@ -248,3 +251,28 @@ def knn_data_sparse(ref, k, fit=None):
     if rc != 0:
         raise ValueError("oracle_knn_data_sparse failed")
     return dist, idx
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def affinity(pcol, irow, val, k_a):
+    """Normalised affinities of auto_decomp_sparse's affinity stage: (values, average sigma)."""
+    pcol = np.ascontiguousarray(pcol, dtype=np.int32)
+    irow = np.ascontiguousarray(irow, dtype=np.int32)
+    m = np.array(val, dtype=np.float64, copy=True)
+    avg = lib().oracle_affinity(len(pcol) - 1, _i(pcol), _i(irow), _d(m), k_a)
+    return m, avg
+
+
+def sym_eigs_largest(pcol, irow, val, nev):
+    """(evals[nev] descending, evecs[nev, n], residuals[nev]) of the symmetric upper-CSC matrix (dense Jacobi)."""
+    pcol = np.ascontiguousarray(pcol, dtype=np.int32)
+    irow = np.ascontiguousarray(irow, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    n = len(pcol) - 1
+    ev, vec, res = np.empty(nev), np.empty((nev, n)), np.empty(nev)
+    if lib().oracle_sym_eigs_largest(n, _i(pcol), _i(irow), _d(val), nev, _d(ev), _d(vec), _d(res)) != 0:
+        raise ValueError("oracle_sym_eigs_largest failed")
+    return ev, vec, res

@@ -87,6 +87,12 @@ int oracle_rms_rows(int mode, int natoms, const float *mass,
 int oracle_max_threads(void);
 
 /* make_sysparse (make_sysparse.cpp:245-329): symmetric CSC from the kNN files; returns nnz (csc.c). */
+/* auto_decomp_sparse (spectral.c): affinity stage, sp_dsymv, dense eigen-solve standing in for ARPACK */
+double oracle_affinity(int n, const int *pcol, const int *irow, double *M, int k_a);
+void oracle_sp_dsymv(int n, const int *irow, const int *pcol, const double *A, const double *v, double *w);
+int oracle_sym_eigs_largest(int n, const int *pcol, const int *irow, const double *M, int nev, double *evals, double *evecs,
+                            double *residuals);
+
 /* knn_data_sparse (mdsctk.cpp:362-386, knn_data_sparse.cpp:195-262); vectors in CSR form */
 double oracle_euclidean_distance_sparse(int ref_size, const int *ref_index, const double *ref_data, int fit_size,
                                         const int *fit_index, const double *fit_data);

@@ -23,6 +23,7 @@
 #include "tc_ptx.cuh"
 
 #include <cuda_fp16.h>
+#include <algorithm>
 #include <cstdlib>
 
 namespace mdsctk {
@@ -461,7 +462,7 @@ cudaError_t launch_data_sweep_tc(const void *fit_hi, const void *fit_lo, const f
 struct DataRescoreArgs {
     const double *fit, *ref;          // fit rows of this query (row 0 = fit row 0), reference rows
     long long n_fit;
-    int dim, k1, P;
+    int dim, k1, P, round0;           // round0: candidates of the first round = min(128, roundup32(k1))
     CandLists<float> cl;
     double eps_rel;                   // noise bound of the filter as a fraction of (|x|^2 + |y|^2)
     const float *q_norm;              // scaled norms; inv_scale2 converts
@@ -472,7 +473,7 @@ struct DataRescoreArgs {
 };
 
 constexpr int DRESCORE_ROUND = 128;   // upper bound of a round (one candidate per thread)
-constexpr int DCHUNK = 32;            // dims staged per step: [128][33] doubles = 33 KB of shared memory
+constexpr int DCHUNK = 16;            // dims staged per step: [round][17] doubles (13 KB for k = 64)
 
 __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
 {
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
     bool certified = false;
     while (done < total) {
         // first round: just enough candidates to fill the k-list; then 32 more at a time
-        const int nb = min(done == 0 ? min(DRESCORE_ROUND, (k1 + 31) / 32 * 32) : 32, total - done);
+        const int nb = min(done == 0 ? a.round0 : 32, total - done);
         // candidate rows are staged through shared memory in chunks of DCHUNK dims with coalesced loads
         // (a warp per candidate); thread c then adds its candidate's terms in the reference's order
         double sum = 0.0;
@@ -631,7 +632,8 @@ cudaError_t launch_data_rescore(const double *fit, const double *ref, long long 
     int P = 32;
     while (P < cl.keep * cl.H) P <<= 1;
     a.P = P;
-    const size_t smem = (((size_t)dim * 8 + (size_t)P * 28 + 15) & ~(size_t)15) + (size_t)DRESCORE_ROUND * (DCHUNK + 1) * 8;
+    a.round0 = std::min(DRESCORE_ROUND, (k1 + 31) / 32 * 32);
+    const size_t smem = (((size_t)dim * 8 + (size_t)P * 28 + 15) & ~(size_t)15) + (size_t)std::max(a.round0, 32) * (DCHUNK + 1) * 8;
     if (smem > 220 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(data_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

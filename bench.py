@@ -320,7 +320,9 @@ def main():
                 2: "rms_sweep_tc_kernel<2> (tcgen05 kind::tf32, 1xTF32 contraction + QCP + streaming top-k)",
                 3: "rms_sweep_tc_kernel<3> (tcgen05 cta_group::2 kind::f16, 3xBF16 split contraction + QCP bounds + streaming top-k)",
                 4: "rms_sweep_tc_kernel<4> (tcgen05 cta_group::2 kind::f16, 3xFP16 split contraction + QCP bounds + streaming top-k)",
-                5: "rms_sweep_tc_kernel<5> (tcgen05 cta_group::2 kind::f16, 2xFP16 contraction + QCP bounds + streaming top-k)"}[st["rms_kernel"]]
+                5: "rms_sweep_tc_kernel<5> (tcgen05 cta_group::2 kind::f16, 2xFP16 contraction + QCP bounds + streaming top-k)",
+                6: "rms_sweep_tc_kernel<6> (tcgen05 cta_group::2 kind::f16, 1xFP16 contraction + QCP bounds + streaming top-k; "
+                   "FP64 re-score with the rounded-structure triangle bound)"}[st["rms_kernel"]]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic_r01c.json")
         if os.path.exists(tp):
@@ -328,21 +330,22 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "tf32", 2: "tf32", 3: "bf16", 4: "f16", 5: "f16"}[st["rms_kernel"]] + " contraction (fp32 accumulate), f64 re-score",
+            "dtype": {0: "f32", 1: "tf32", 2: "tf32", 3: "bf16", 4: "f16", 5: "f16", 6: "f16"}[st["rms_kernel"]] + " contraction (fp32 accumulate), f64 re-score",
             "data": "synthetic",
             "config": {"workload": wl["name"], "frames": n_total, "atoms": ATOMS, "k": wl["k"],
                        "fit_rows_per_rank_per_step": rows, "parallelism": f"row-sharded x{world}, reference replicated",
                        "l2": "inputs larger than L2 (reference planes %.0f MB + raw %.0f MB vs 126 MB L2)" %
                              (n_total * 3 * 304 * 4 / 1e6, n_total * ATOMS * 12 / 1e6),
                        "kernel": kern, "k_keep": st["k_keep"], "fallback_rows": fallback_rows,
-                       "max_filter_err_nm2": err, "cert_eps_nm2": st["cert_eps"], "allgather_ms": allgather_ms},
+                       "max_filter_err_nm2": err, "cert_eps_nm2": st["cert_eps"], "cert_gres_nm": st["cert_gres"],
+                       "rescored_max": st["rescored_max"], "allgather_ms": allgather_ms},
             "e2e": {"value": world * rows * n_total * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": sweep_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": sweep_tflops / peaks["tflops"], "traffic": traffic,
-                         "mma_per_flop": {0: 1, 2: 1, 5: 2}.get(st["rms_kernel"], 3),
+                         "mma_per_flop": {0: 1, 2: 1, 5: 2, 6: 1}.get(st["rms_kernel"], 3),
                          "kernel": kern.split(" ")[0], "flop_per_pair": FLOP_PER_PAIR, "peak_source": peaks["source"],
                          "sweep_ms_per_step": sweep_ms / args.steps, "post_ms_per_step": post_ms / args.steps},
             "cpu_baseline": cpu_baseline_sample(wl),

@@ -60,7 +60,10 @@ enum {
     MDSCTK_KNN_RMS_TC_1XTF32 = 2,  /* tcgen05 kind::tf32, hi only (coarse filter)                   */
     MDSCTK_KNN_RMS_TC_3XBF16 = 3,  /* tcgen05 kind::f16 on bf16 hi/mid operand split (3 MMAs)       */
     MDSCTK_KNN_RMS_TC_3XFP16 = 4,  /* tcgen05 kind::f16 on fp16 hi/lo split of 64x (3 MMAs, 22 bits): DEFAULT */
-    MDSCTK_KNN_RMS_TC_2XFP16 = 5   /* fit operand fp16 hi only, reference hi/lo (2 MMAs)            */
+    MDSCTK_KNN_RMS_TC_2XFP16 = 5,  /* fit operand fp16 hi only, reference hi/lo (2 MMAs)            */
+    MDSCTK_KNN_RMS_TC_1XFP16 = 6   /* both operands fp16 hi only (1 MMA); exactness comes from the FP64
+                                      re-score, whose certificate bounds the rounding rigorously
+                                      (metric triangle inequality on the rounded structures)       */
 };
 
 typedef struct mdsctk_knn_ctx mdsctk_knn_ctx;
@@ -83,6 +86,7 @@ typedef struct mdsctk_knn_stats {
     int k_keep;            /* candidates kept per row (k1 + slack)                  */
     int lists_per_row;     /* candidate lists per row kept by the sweep             */
     int rescored_max;      /* most candidates any row needed before its certificate held */
+    double cert_gres;      /* 2xFP16 / 1xFP16: largest operand-rounding residual norm of the reference set (nm) */
 } mdsctk_knn_stats;
 
 int mdsctk_knn_abi_version(void);

@@ -7,7 +7,7 @@ has no CPU fallback: importing works anywhere, but creating a context without th
 library or without an sm_100 GPU raises.
 """
 from .api import (KnnContext, KnnError, knn_data, knn_rms, library_path, load_library,  # noqa: F401
-                  RMS_SIMT_FP32, RMS_TC_1XTF32, RMS_TC_2XFP16, RMS_TC_3XBF16, RMS_TC_3XFP16, RMS_TC_3XTF32)
+                  RMS_SIMT_FP32, RMS_TC_1XFP16, RMS_TC_1XTF32, RMS_TC_2XFP16, RMS_TC_3XBF16, RMS_TC_3XFP16, RMS_TC_3XTF32)
 
 __all__ = ["KnnContext", "KnnError", "knn_rms", "knn_data", "load_library", "library_path",
-           "RMS_SIMT_FP32", "RMS_TC_3XTF32", "RMS_TC_1XTF32", "RMS_TC_3XBF16", "RMS_TC_3XFP16", "RMS_TC_2XFP16"]
+           "RMS_SIMT_FP32", "RMS_TC_3XTF32", "RMS_TC_1XTF32", "RMS_TC_3XBF16", "RMS_TC_3XFP16", "RMS_TC_2XFP16", "RMS_TC_1XFP16"]

@@ -13,7 +13,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-RMS_SIMT_FP32, RMS_TC_3XTF32, RMS_TC_1XTF32, RMS_TC_3XBF16, RMS_TC_3XFP16, RMS_TC_2XFP16 = 0, 1, 2, 3, 4, 5
+RMS_SIMT_FP32, RMS_TC_3XTF32, RMS_TC_1XTF32, RMS_TC_3XBF16, RMS_TC_3XFP16, RMS_TC_2XFP16, RMS_TC_1XFP16 = 0, 1, 2, 3, 4, 5, 6
 EUCLIDEAN, CORRELATION = 0, 1
 
 SYMBOLS = [
@@ -39,7 +39,7 @@ class Stats(C.Structure):
                 ("pairs", C.c_longlong), ("launches", C.c_longlong), ("fallback_rows", C.c_longlong),
                 ("sweep_appends", C.c_longlong), ("max_filter_err", C.c_double), ("max_filter_spread", C.c_double),
                 ("cert_eps", C.c_double), ("rms_kernel", C.c_int), ("k_keep", C.c_int), ("lists_per_row", C.c_int),
-                ("rescored_max", C.c_int)]
+                ("rescored_max", C.c_int), ("cert_gres", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -41,13 +41,14 @@ struct DevBuf {
 };
 
 struct FrameSet {
-    DevBuf raw, planes, hi, lo, bh, bm, fh, fl, G, cen;
+    DevBuf raw, planes, hi, lo, bh, bm, fh, fl, G, cen, Gh, G2, gres;
     long long n = 0;
     int A = 0, A_pad = 0;
     FrameSetView view() const
     {
         FrameSetView v;
         v.raw = raw.as<float>(); v.planes = planes.as<float>(); v.G = G.as<float>(); v.cen = cen.as<double>();
+        v.Gh = Gh.as<float>(); v.G2 = G2.as<float>(); v.gres = gres.as<float>();
         v.n = n; v.A = A; v.A_pad = A_pad;
         return v;
     }
@@ -64,12 +65,15 @@ struct FrameSet {
         if ((e = fh.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
         if ((e = fl.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
         if ((e = G.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;  // tensor-core epilogue reads G in 48-wide tiles
+        if ((e = Gh.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;
+        if ((e = G2.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;
+        if ((e = gres.reserve((size_t)n * 8)) != cudaSuccess) return e;
         return cen.reserve((size_t)n * 32);
     }
     void release()
     {
         raw.release(); planes.release(); hi.release(); lo.release(); bh.release(); bm.release(); fh.release(); fl.release(); G.release();
-        cen.release(); n = 0;
+        cen.release(); Gh.release(); G2.release(); gres.release(); n = 0;
     }
 };
 
@@ -106,6 +110,7 @@ struct mdsctk_knn_ctx {
     DevBuf wnorm;  // double[A]
     bool have_ref = false, gmax_dirty = true;
     float g_ref_max = 0.f;
+    float gres_ref_max[2] = {0.f, 0.f};   // largest rounding residual norm of the reference set (1 / 2 fp16 parts)
     // vector state
     DevBuf d_ref, d_fit, d_ref_stats, d_fit_stats;
     long long dn_ref = 0;
@@ -189,7 +194,8 @@ int pack_into(mdsctk_knn_ctx *ctx, FrameSet &fs, const float *xyz, long long off
                           fs.bh.as<uint16_t>() + (size_t)off * 3 * fs.A_pad, fs.bm.as<uint16_t>() + (size_t)off * 3 * fs.A_pad,
                           fs.fh.as<uint16_t>() + (size_t)off * 3 * fs.A_pad, fs.fl.as<uint16_t>() + (size_t)off * 3 * fs.A_pad,
                           fs.G.as<float>() + off,
-                          fs.cen.as<double>() + 4 * off, ctx->st), "pack_frames");
+                          fs.cen.as<double>() + 4 * off, fs.Gh.as<float>() + off, fs.G2.as<float>() + off,
+                          fs.gres.as<float>() + 2 * off, ctx->st), "pack_frames");
     ctx->stats.ms_pack += ctx->tm.stop(ctx->st);
     return 0;
 }
@@ -217,7 +223,10 @@ double default_eps_scale(int rms_kernel, int n_atoms)
     switch (rms_kernel) {
     case MDSCTK_KNN_RMS_TC_1XTF32: return 4e-5 * sa;
     case MDSCTK_KNN_RMS_TC_3XBF16: return 1.5e-5;       // bf16 split residual 2^-18 per product dominates
-    case MDSCTK_KNN_RMS_TC_2XFP16: return 1.2e-4;       // fit operand rounded to 11 bits; measured half-spread 9e-5 E0
+    // the reduced FP16 modes bound the operand rounding separately and rigorously (gres, rms_rescore.cu);
+    // what is left is the same fp32 accumulation noise as 3xFP16 (fewer accumulation steps, if anything)
+    case MDSCTK_KNN_RMS_TC_2XFP16:
+    case MDSCTK_KNN_RMS_TC_1XFP16:
     case MDSCTK_KNN_RMS_TC_3XFP16:
     case MDSCTK_KNN_RMS_TC_3XTF32:
     default: return 5e-7 * sa;
@@ -243,6 +252,11 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
         CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
         CK(launch_max_float(ref.G, ref.n, ctx->scalars.as<float>(), ctx->st), "max(G)");
         CK(cudaMemcpyAsync(&ctx->g_ref_max, ctx->scalars.p, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H max(G)");
+        for (int part = 0; part < 2; ++part) {
+            CK(launch_max_float_strided(ref.gres + part, ref.n, 2, ctx->scalars.as<float>() + 1 + part, ctx->st), "max(gres)");
+            CK(cudaMemcpyAsync(&ctx->gres_ref_max[part], ctx->scalars.as<float>() + 1 + part, 4, cudaMemcpyDeviceToHost, ctx->st),
+               "D2H max(gres)");
+        }
         CK(cudaStreamSynchronize(ctx->st), "sync max(G)");
         ctx->gmax_dirty = false;
     }
@@ -289,7 +303,8 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
             const void *q_hi = fitset.hi.p, *q_lo = fitset.lo.p, *r_hi = ctx->ref.hi.p, *r_lo = ctx->ref.lo.p;
             if (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_3XBF16) {
                 q_hi = fitset.bh.p; q_lo = fitset.bm.p; r_hi = ctx->ref.bh.p; r_lo = ctx->ref.bm.p;
-            } else if (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_3XFP16 || ctx->rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16) {
+            } else if (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_3XFP16 || ctx->rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ||
+                       ctx->rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16) {
                 q_hi = fitset.fh.p; q_lo = fitset.fl.p; r_hi = ctx->ref.fh.p; r_lo = ctx->ref.fl.p;
                 // 64 * sqrt(G) bounds every operand element; fp16 overflows at 65504
                 if (64.0 * std::sqrt((double)ctx->g_ref_max) > 3.0e4)
@@ -310,8 +325,13 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
     const double eps_scale = default_eps_scale(ctx->rms_kernel, ref.A) * (double)ctx->cert_scale_ppm * 1e-6;
     S.cert_eps = eps_scale * 0.5 * (double)ctx->g_ref_max * 2.0;
     ctx->tm.start(ctx->st);
+    // operand-rounding term: 2xFP16 contracts fit fh with reference fh+fl, 1xFP16 fh with fh
+    const int fit_part = (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 || ctx->rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16) ? 0 : -1;
+    const float gres_ref = ctx->rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16 ? ctx->gres_ref_max[0]
+                           : (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ? ctx->gres_ref_max[1] : 0.0f);
+    S.cert_gres = fit_part >= 0 ? (double)gres_ref : 0.0;
     CK(launch_rms_rescore(fit, fit_begin, n_fit, ref, ctx->wnorm.as<double>(), do_fit, cl, k1, eps_scale,
-                          ctx->g_ref_max, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(),
+                          ctx->g_ref_max, fit_part, gres_ref, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(),
                           d_err, d_nbad, ctx->bad_rows.as<int>(), ctx->st), "rms_rescore");
     S.launches += 1;
     struct { double pad, err, spread, done_max; int nbad; } host_sc;
@@ -616,7 +636,7 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
 {
     if (!ctx || !key) return MDSCTK_KNN_EINVAL;
     if (!strcmp(key, "rms_kernel")) {
-        if (value < 0 || value > 5) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel must be 0..5");
+        if (value < 0 || value > 6) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel must be 0..6");
         ctx->rms_kernel = (int)value;
     } else if (!strcmp(key, "slack")) {
         if (value < -1 || value > 1024) return fail(ctx, MDSCTK_KNN_EINVAL, "slack out of range");
@@ -676,8 +696,8 @@ int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_
 {
     if (!ctx || !n_arrays) return MDSCTK_KNN_EINVAL;
     if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
-    *n_arrays = 10;
-    if (max_arrays < 10 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 10 arrays");
+    *n_arrays = 13;
+    if (max_arrays < 13 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 13 arrays");
     dev_ptrs[0] = ctx->ref.raw.p;    bytes_per_frame[0] = (size_t)ctx->ref.A * 12;
     dev_ptrs[1] = ctx->ref.planes.p; bytes_per_frame[1] = (size_t)ctx->ref.A_pad * 12;
     dev_ptrs[2] = ctx->ref.G.p;      bytes_per_frame[2] = 4;
@@ -688,6 +708,9 @@ int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_
     dev_ptrs[7] = ctx->ref.bm.p;     bytes_per_frame[7] = (size_t)ctx->ref.A_pad * 6;
     dev_ptrs[8] = ctx->ref.fh.p;     bytes_per_frame[8] = (size_t)ctx->ref.A_pad * 6;
     dev_ptrs[9] = ctx->ref.fl.p;     bytes_per_frame[9] = (size_t)ctx->ref.A_pad * 6;
+    dev_ptrs[10] = ctx->ref.Gh.p;    bytes_per_frame[10] = 4;
+    dev_ptrs[11] = ctx->ref.G2.p;    bytes_per_frame[11] = 4;
+    dev_ptrs[12] = ctx->ref.gres.p;  bytes_per_frame[12] = 8;
     ctx->gmax_dirty = true;  // the caller is about to overwrite them (all-gather)
     return 0;
 }

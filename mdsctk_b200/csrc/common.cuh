@@ -9,6 +9,9 @@
 //   bh, bm bf16   [n][3][A_pad]    BF16 split of planes: bh = rn_bf16(x), bm = rn_bf16(x - bh)
 //   fh, fl fp16   [n][3][A_pad]    FP16 split of 64*planes: fh = rn_f16(64x), fl = rn_f16(64x - fh)
 //   G      float  [n] (+64 pad)    sum_a (m_a/M) |x_a - c|^2          (fp32 copy for the sweep)
+//   Gh, G2 float  [n] (+64 pad)    |fh/64|^2 and |(fh+fl)/64|^2: norms of the ROUNDED structures the
+//                                  1xFP16 / 2xFP16 sweeps contract (their E0 uses these, not G)
+//   gres   float  [n][2]           residual norms |x - fh/64|, |x - (fh+fl)/64| in nm, rounded up
 //   cen    double [n][4]           mass-weighted centroid (x,y,z) and G in FP64
 // With the weights normalised to sum 1, min-RMSD^2 = G_q + G_r - 2*lambda_max (nm^2).
 #pragma once
@@ -26,6 +29,8 @@ struct FrameSetView {
     const float *raw;     // [n][A][3]
     const float *planes;  // [n][3][A_pad]
     const float *G;       // [n]
+    const float *Gh, *G2; // [n]     norms of the fp16-rounded structures (1 part / 2 parts)
+    const float *gres;    // [n][2]  their distance from the true structure
     const double *cen;    // [n][4]
     long long n;
     int A, A_pad;
@@ -50,14 +55,14 @@ struct CandLists {
 // ---- launch wrappers (defined in the .cu files) -----------------------------------
 cudaError_t launch_pack_frames(const float *raw, const double *mass_norm, long long n, int A, int A_pad,
                                float *planes, float *hi, float *lo, void *bh, void *bm, void *fh, void *fl, float *G,
-                               double *cen, cudaStream_t st);
+                               double *cen, float *Gh, float *G2, float *gres, cudaStream_t st);
 
 cudaError_t launch_rms_sweep_simt(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                   const FrameSetView &ref, int do_fit, CandLists<float> cl, cudaStream_t st);
 
 // tcgen05 sweep (rms_tc.cu).  *_hi / *_lo: TF32 split planes, same [n][3][A_pad] layout as planes.
 // mode: 1 = 3xTF32 (hi/lo fp32 planes), 2 = 1xTF32 (hi only), 3 = 3xBF16 (bh/bm bf16 planes),
-//       4 = 3xFP16 (fh/fl), 5 = 2xFP16 (fit fh only, reference fh/fl).
+//       4 = 3xFP16 (fh/fl), 5 = 2xFP16 (fit fh only, reference fh/fl), 6 = 1xFP16 (fh only).
 // cl.H must be rms_tc_lists_per_segment() * n_seg (reference segments x column groups).
 cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *fit_hi, const void *fit_lo,
                                 long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,
@@ -71,10 +76,13 @@ int rms_tc_list_stride(int keep);
 //   out_dist [n_fit][k1] (Angstrom), out_idx [n_fit][k1], flags[n_fit] (1 = certified),
 //   err_stats: device double[2] = {max |approx - exact| d^2, max per-row spread of (approx - exact)};
 //   n_bad: device int counter of uncertified rows, listed in bad_rows.
+//   fit_part / gres_ref_max: operand-rounding term of the certificate for the 2xFP16 / 1xFP16 sweeps
+//   (fit_part = column of fit.gres the sweep's fit operand corresponds to, -1 = none; gres_ref_max =
+//   largest residual norm of the reference operand), see rms_rescore.cu.
 cudaError_t launch_rms_rescore(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                const FrameSetView &ref, const double *mass_norm, int do_fit,
                                CandLists<float> cl, int k1, double eps_scale, float g_ref_max,
-                               double *out_dist, int *out_idx, int *flags, double *err_stats, int *n_bad,
+                               int fit_part, float gres_ref_max, double *out_dist, int *out_idx, int *flags, double *err_stats, int *n_bad,
                                int *bad_rows, cudaStream_t st);
 
 // Exact FP64 d^2 of fit row(s) against every reference frame: out[n_rows][n_ref] (nm^2).
@@ -142,6 +150,7 @@ cudaError_t launch_phipsi(const float *xyz, long long n, int A, double *phipsi, 
 cudaError_t launch_sincos(const double *angles, long long n, double *out, cudaStream_t st);
 
 cudaError_t launch_max_float(const float *v, long long n, float *out, cudaStream_t st);
+cudaError_t launch_max_float_strided(const float *v, long long n, int stride, float *out, cudaStream_t st);   // max v[i*stride]
 cudaError_t launch_fill_u32(void *p, size_t n, uint32_t v, cudaStream_t st);
 
 }  // namespace mdsctk

@@ -7,6 +7,11 @@
 // plus the TF32 hi/lo split planes of the tensor-core sweep.
 // plus the BF16 and FP16 split planes.  One warp per frame; HBM-bound: 12*A bytes read +
 // 60*A_pad written per frame.
+// For the reduced-precision FP16 sweeps (2xFP16 / 1xFP16) the kernel also records, in FP64, what the
+// rounding did to each frame: Gh = |fh/64|^2 and G2 = |(fh+fl)/64|^2 (norms of the structures the
+// tensor cores actually see) and the residual norms g1 = |x - fh/64|, g2 = |x - (fh+fl)/64| (nm,
+// rounded up).  min-RMSD over rotations is a metric, so the distance between two ROUNDED structures
+// differs from the true one by at most g_q + g_r: the certificate's rigorous operand-rounding term.
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -27,7 +32,8 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
                                                           float *__restrict__ lo, __nv_bfloat16 *__restrict__ bh,
                                                           __nv_bfloat16 *__restrict__ bm, __half *__restrict__ fh,
                                                           __half *__restrict__ fl, float *__restrict__ G,
-                                                          double *__restrict__ cen)
+                                                          double *__restrict__ cen, float *__restrict__ Gh,
+                                                          float *__restrict__ G2, float2 *__restrict__ gres)
 {
     const int lane = threadIdx.x & 31;
     const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -49,16 +55,18 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
     const size_t pbase = (size_t)f * 3 * A_pad;
     float *px = planes + pbase;
     float *py = px + A_pad, *pz = py + A_pad;
-    double g = 0.0;
+    double g = 0.0, gh = 0.0, g2n = 0.0, r1 = 0.0, r2 = 0.0;
     for (int a = lane; a < A_pad; a += 32) {
         float ox = 0.0f, oy = 0.0f, oz = 0.0f;
+        double tx = 0.0, ty = 0.0, tz = 0.0;      // the FP64 operand sqrt(w) (x - c)
         if (a < A) {
             const double w = wnorm[a];
             const double dx = (double)x[3 * a + 0] - cx, dy = (double)x[3 * a + 1] - cy,
                          dz = (double)x[3 * a + 2] - cz;
             g += w * (dx * dx + dy * dy + dz * dz);
             const double s = sqrt(w);
-            ox = (float)(s * dx); oy = (float)(s * dy); oz = (float)(s * dz);
+            tx = s * dx; ty = s * dy; tz = s * dz;
+            ox = (float)tx; oy = (float)ty; oz = (float)tz;
         }
         px[a] = ox; py[a] = oy; pz[a] = oz;
         if (hi) {  // 3xTF32 operand split for the tensor-core sweep: x ~= hi + lo, both exact TF32 values
@@ -78,39 +86,59 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
         }
         if (fh) {  // FP16 split of kRmsHalfScale * x: fh + fl carries 22 bits (fl is exact in fp32 before rounding)
             const float o[3] = {ox * kRmsHalfScale, oy * kRmsHalfScale, oz * kRmsHalfScale};
+            const double t[3] = {tx, ty, tz};
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 const __half h = __float2half_rn(o[d]);
+                const __half l = __float2half_rn(o[d] - __half2float(h));
                 fh[pbase + d * A_pad + a] = h;
-                fl[pbase + d * A_pad + a] = __float2half_rn(o[d] - __half2float(h));
+                fl[pbase + d * A_pad + a] = l;
+                const double v1 = (double)__half2float(h) * (1.0 / kRmsHalfScale);
+                const double v2 = v1 + (double)__half2float(l) * (1.0 / kRmsHalfScale);
+                gh += v1 * v1; g2n += v2 * v2;
+                r1 += (t[d] - v1) * (t[d] - v1); r2 += (t[d] - v2) * (t[d] - v2);
             }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+        gh += __shfl_xor_sync(0xffffffffu, gh, o);
+        g2n += __shfl_xor_sync(0xffffffffu, g2n, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+    }
     if (lane == 0) {
+        if (Gh) {
+            Gh[f] = (float)gh;
+            G2[f] = (float)g2n;
+            // residual norms rounded up: they are subtracted from lower bounds
+            gres[f] = make_float2(__double2float_ru(sqrt(r1)), __double2float_ru(sqrt(r2)));
+        }
         G[f] = (float)g;
         cen[4 * f + 0] = cx; cen[4 * f + 1] = cy; cen[4 * f + 2] = cz; cen[4 * f + 3] = g;
     }
 }
 
 cudaError_t launch_pack_frames(const float *raw, const double *wnorm, long long n, int A, int A_pad, float *planes,
-                               float *hi, float *lo, void *bh, void *bm, void *fh, void *fl, float *G, double *cen, cudaStream_t st)
+                               float *hi, float *lo, void *bh, void *bm, void *fh, void *fl, float *G, double *cen, float *Gh, float *G2,
+                               float *gres, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
     const int warps = 8;
     const unsigned grid = (unsigned)((n + warps - 1) / warps);
     pack_frames_kernel<<<grid, warps * 32, 0, st>>>(raw, wnorm, n, A, A_pad, planes, hi, lo, static_cast<__nv_bfloat16 *>(bh),
                                                     static_cast<__nv_bfloat16 *>(bm), static_cast<__half *>(fh),
-                                                    static_cast<__half *>(fl), G, cen);
+                                                    static_cast<__half *>(fl), G, cen, Gh, G2,
+                                                    reinterpret_cast<float2 *>(gres));
     return cudaGetLastError();
 }
 
-__global__ void max_float_kernel(const float *v, long long n, float *out)
+__global__ void max_float_kernel(const float *v, long long n, int stride, float *out)
 {
     float m = 0.0f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        m = fmaxf(m, v[i]);
+        m = fmaxf(m, v[i * stride]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));  // m >= 0
@@ -128,13 +156,18 @@ cudaError_t launch_fill_u32(void *p, size_t n, uint32_t v, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_max_float(const float *v, long long n, float *out, cudaStream_t st)
+cudaError_t launch_max_float_strided(const float *v, long long n, int stride, float *out, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), st);
     if (e != cudaSuccess) return e;
     if (n <= 0) return cudaSuccess;
-    max_float_kernel<<<148, 256, 0, st>>>(v, n, out);
+    max_float_kernel<<<148, 256, 0, st>>>(v, n, stride, out);
     return cudaGetLastError();
+}
+
+cudaError_t launch_max_float(const float *v, long long n, float *out, cudaStream_t st)
+{
+    return launch_max_float_strided(v, n, 1, out, st);
 }
 
 }  // namespace mdsctk

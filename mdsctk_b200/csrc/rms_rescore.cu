@@ -90,6 +90,8 @@ struct RescoreArgs {
     CandLists<float> cl;
     double eps_scale;
     float g_ref_max;
+    int fit_part;            // column of fit.gres the sweep's fit operand corresponds to, -1: no operand-rounding term
+    float gres_ref_max;      // largest rounding residual norm of the reference operand (nm)
     double *out_dist;
     int *out_idx, *flags;
     double *err_stats;
@@ -109,6 +111,17 @@ struct RescoreArgs {
 //      (the bias -- fp32 accumulation truncation in the tensor core -- cancels).  eps is a
 //      model bound (eps_scale * E0), re-checked against the spread observed on the candidates.
 //      Rows that exhaust their candidates uncertified go to the exact FP64 fallback.
+//   2'. 2xFP16 / 1xFP16 sweeps (fit_part >= 0).  Their keys are, up to the same bias + noise, the
+//      exact min-RMSD^2 between the ROUNDED structures x~, y~ the tensor cores saw.  min_R |x - R y|
+//      is a metric on centred-or-not point sets modulo rotation, so the rounded distance d~ obeys
+//      |d~ - d| <= |x - x~| + |y - y~| <= g  (g = gres_q + max gres_r, FP64 norms from pack.cu):
+//            max(d - g, 0)^2 + B - eps  <=  key  <=  (d + g)^2 + B + eps.
+//      Every re-scored candidate i therefore brackets the bias, B <= key_i - max(d_i - g, 0)^2 + eps,
+//      and a pair that was not re-scored (key >= a_next) has (d + g)^2 >= a_next - B - eps.  It
+//      cannot beat the exact k1-th neighbour d_k if
+//            min_i [key_i - max(d_i - g, 0)^2] + (d_k + g)^2 + 2 eps < a_next.
+//      The brackets of all re-scored candidates must intersect (model check, replaces the spread
+//      test).  With g = 0 this is the rule of step 2 with min_i err_i in place of the top-k1 maximum.
 constexpr int RESCORE_ROUND = 64;
 
 __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
@@ -172,6 +185,8 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
     // RMSD^2 <= d2_k + margin, and RMSD >= |sqrt(G_q) - sqrt(G_r)| (both frames centred), so its
     // G_r <= (sqrt(G_q) + sqrt(d2_k + margin))^2 -- usually far below the largest G of the set.
     const double eps_max = a.eps_scale * 0.5 * (gq + (double)a.g_ref_max);
+    // operand-rounding allowance of the reduced FP16 sweeps (0 for the full-precision modes)
+    const double grd = a.fit_part >= 0 ? (double)a.fit.gres[2 * qf + a.fit_part] + (double)a.gres_ref_max : 0.0;
     double eps = eps_max;
     int done = 0;
     bool certified = false;
@@ -196,12 +211,18 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
             const double d2 = fmax(2.0 * (e0 - lam), 0.0);
             // distance exactly as distance() reports it: sqrt(msd) [nm] * 10.0 -> Angstrom
             u_dist[done + c] = sqrt(d2) * 10.0;
-            const double err = (double)u_apx[done + c] - d2;
+            // bracket of the row-common bias given this candidate: [key - (d+g)^2, key - max(d-g,0)^2];
+            // both ends are approx - exact when g = 0
+            const double dn = sqrt(d2), dm = fmax(dn - grd, 0.0);
+            const double err_hi = (double)u_apx[done + c] - dm * dm;
+            const double err_lo = (double)u_apx[done + c] - (dn + grd) * (dn + grd);
             // monotone map double -> u64 so that atomicMin/Max order like the doubles
-            unsigned long long bits = (unsigned long long)__double_as_longlong(err);
-            bits = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
-            atomicMin(&s_emin, bits);
-            atomicMax(&s_emax, bits);
+            auto enc = [](double v) {
+                unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+                return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+            };
+            atomicMin(&s_emin, enc(err_hi));
+            atomicMax(&s_emax, enc(err_lo));
         }
         __syncthreads();
         done += nb;
@@ -234,8 +255,14 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
                 const double reach = sqrt(gq) + sqrt(dk_nm * dk_nm + 4.0 * eps_max);
                 eps = a.eps_scale * 0.5 * (gq + fmin((double)a.g_ref_max, reach * reach));
             }
-            if (ok && a_next != kInfF)  // a_next == inf: nothing was ever dropped, every pair has been re-scored
-                ok = 0.5 * spread <= eps_max && (double)__uint_as_float(s_dtil) + 2.0 * eps < (double)a_next;
+            if (ok && a_next != kInfF) {  // a_next == inf: nothing was ever dropped, every pair has been re-scored
+                if (a.fit_part >= 0) {
+                    const double dkg = s_d[k1 - 1] * 0.1 + grd;
+                    ok = 0.5 * spread <= eps_max && dec(s_emin) + dkg * dkg + 2.0 * eps < (double)a_next;
+                } else {
+                    ok = 0.5 * spread <= eps_max && (double)__uint_as_float(s_dtil) + 2.0 * eps < (double)a_next;
+                }
+            }
             s_ok = ok ? 1 : 0;
         }
         __syncthreads();
@@ -256,7 +283,7 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
         if (total > 0) {
             const double lo = dec(s_emin), hi = dec(s_emax);
             atomic_max_nonneg(a.err_stats + 0, fmax(fabs(lo), fabs(hi)));
-            atomic_max_nonneg(a.err_stats + 1, hi - lo);
+            atomic_max_nonneg(a.err_stats + 1, fmax(hi - lo, 0.0));   // brackets may overlap (negative) when g > 0
             atomic_max_nonneg(a.err_stats + 2, (double)done);
         }
         a.flags[q] = certified ? 1 : 0;
@@ -269,13 +296,15 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
 
 cudaError_t launch_rms_rescore(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                const FrameSetView &ref, const double *wnorm, int do_fit, CandLists<float> cl, int k1,
-                               double eps_scale, float g_ref_max, double *out_dist, int *out_idx, int *flags,
+                               double eps_scale, float g_ref_max, int fit_part, float gres_ref_max, double *out_dist,
+                               int *out_idx, int *flags,
                                double *err_stats, int *n_bad, int *bad_rows, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
     RescoreArgs a;
     a.fit = fit; a.ref = ref; a.fit_begin = fit_begin; a.n_fit = n_fit; a.wnorm = wnorm;
     a.do_fit = do_fit; a.k1 = k1; a.cl = cl; a.eps_scale = eps_scale; a.g_ref_max = g_ref_max;
+    a.fit_part = fit_part; a.gres_ref_max = gres_ref_max;
     a.out_dist = out_dist; a.out_idx = out_idx; a.flags = flags; a.err_stats = err_stats; a.n_bad = n_bad;
     a.bad_rows = bad_rows;
     int P = 1;

@@ -23,8 +23,13 @@
 //                  1xTF32: D += Ah*Bh only (coarse filter).
 //                  3xFP16: as 3xBF16 on an fp16 split of 64 x (22 bits kept instead of 16)
 //                  2xFP16: D += Ah*Bh + Ah*Bl, fit operand rounded to fp16 (11 bits): two MMAs and
-//                          half the fit-operand traffic; its noise is linear in the reference frame,
-//                          so near neighbours of a row share it (the certificate only needs the spread)
+//                          half the fit-operand traffic
+//                  1xFP16: D += Ah*Bh only: ONE MMA per k-step.  These two modes compute, up to fp32
+//                          accumulation noise, the exact min-RMSD between the ROUNDED structures
+//                          (E0 from Gh / G2, the norms of what the tensor cores see); min-RMSD over
+//                          rotations is a metric, so it is within g_q + g_r (the rounding residual
+//                          norms, pack.cu) of the true distance -- the re-score certificate uses
+//                          that bound instead of an empirical noise constant (rms_rescore.cu)
 //   accumulators TMEM of each CTA: its 128 fit rows x 3 regions of 144 fp32 columns (432 of 512);
 //                TMEM lane = fit frame, so an epilogue thread reads the nine S values of ITS fit row
 //                with tcgen05.ld (no shuffles), bounds RMSD^2 from below (Frobenius bound, then QCP
@@ -59,12 +64,12 @@ constexpr int B_PART = 3 * TRH * ROW_BYTES;   // 4608 B : this CTA's 72 of the 1
 constexpr int MAX_NST = 6;
 constexpr int STATIC_SMEM = 20 * 1024;        // bound on the kernel's static shared memory (checked at launch)
 
-// MODE: 1 = 3xTF32, 2 = 1xTF32, 3 = 3xBF16, 4 = 3xFP16, 5 = 2xFP16 (fit operand: hi part only)
+// MODE: 1 = 3xTF32, 2 = 1xTF32, 3 = 3xBF16, 4 = 3xFP16, 5 = 2xFP16 (fit operand: hi part only), 6 = 1xFP16
 template <int MODE> struct Mode {
     static constexpr bool K16 = MODE >= 3;                         // 16-bit operands: K = 16 per MMA, 32 atoms per stage
     static constexpr int FMT = MODE == 3 ? 1 : (MODE >= 4 ? 0 : 2); // instruction-descriptor operand format
     static constexpr bool A_LO = MODE == 1 || MODE == 3 || MODE == 4;
-    static constexpr bool B_LO = MODE != 2;
+    static constexpr bool B_LO = MODE != 2 && MODE != 6;
     static constexpr int OFF_AHI = 0;
     static constexpr int OFF_ALO = A_PART;
     static constexpr int OFF_BHI = (A_LO ? 2 : 1) * A_PART;
@@ -606,7 +611,10 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
         !make_plane_map(&mr_lo, ref_lo, ref.n, ref.A_pad, tc::TRH, mode))
         return cudaErrorInvalidValue;
     TcArgs a;
-    a.q_G = fit.G; a.r_G = ref.G; a.q_begin = fit_begin; a.n_q = n_fit; a.n_r = ref.n;
+    // the reduced FP16 modes measure distances between the rounded structures: E0 from their norms
+    a.q_G = mode >= 5 ? fit.Gh : fit.G;
+    a.r_G = mode == 6 ? ref.Gh : (mode == 5 ? ref.G2 : ref.G);
+    a.q_begin = fit_begin; a.n_q = n_fit; a.n_r = ref.n;
     a.A_pad = ref.A_pad; a.do_fit = do_fit; a.n_seg = n_seg; a.cl = cl; a.debug_tile = debug_tile; a.row_tau = row_tau;
     const char *dbg = getenv("MDSCTK_TC_DEBUG");
     a.dbg = dbg ? atoi(dbg) : 0;
@@ -629,6 +637,7 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
     case 3: e = launch_tc_mode<3>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
     case 4: e = launch_tc_mode<4>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
     case 5: e = launch_tc_mode<5>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
+    case 6: e = launch_tc_mode<6>(mq_hi, mq_lo, mr_hi, mr_lo, a, n_items, n_sms, st); break;
     default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

@@ -45,6 +45,14 @@ def test_c3_full_size_properties_and_oracle_sample():
         # the BF16 split must give the same bytes (the FP64 stage decides, the contraction only filters)
         dist3, idx3 = mdsctk_b200.knn_rms(xyz, mass, k, ctx=ctx, rms_kernel=mdsctk_b200.RMS_TC_3XBF16)
         assert np.array_equal(idx3, idx) and np.array_equal(dist3, dist)
+        # and so must the one-MMA and the full three-MMA fp16 sweeps, whichever of them is the default
+        for kern in (mdsctk_b200.RMS_TC_1XFP16, mdsctk_b200.RMS_TC_3XFP16):
+            dist1, idx1 = mdsctk_b200.knn_rms(xyz, mass, k, ctx=ctx, rms_kernel=kern)
+            st1 = ctx.stats()
+            print("kernel", kern, {n_: st1[n_] for n_ in ("ms_sweep", "ms_rescore", "ms_fallback", "fallback_rows", "rescored_max",
+                                                        "max_filter_err", "cert_eps", "cert_gres", "k_keep")})
+            assert np.array_equal(idx1, idx) and np.array_equal(dist1, dist)
+            assert st1["fallback_rows"] <= 8
 
 
 def test_knn_data_c5_shape_properties_and_oracle_sample():

@@ -9,7 +9,7 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-TC_3X, TC_1X, TC_BF, TC_F3, TC_F2 = 1, 2, 3, 4, 5
+TC_3X, TC_1X, TC_BF, TC_F3, TC_F2, TC_F1 = 1, 2, 3, 4, 5, 6
 
 
 @pytest.fixture(scope="module")
@@ -27,7 +27,7 @@ def packed_planes(xyz, mass):
     return ((x - c) * np.sqrt(w)[None, :, None]).astype(np.float32).astype(np.float64)   # [n, A, 3]
 
 
-@pytest.mark.parametrize("kern,rtol", [(TC_3X, 2e-6), (TC_1X, 2e-3), (TC_BF, 3e-5), (TC_F3, 2e-6), (TC_F2, 5e-4)])
+@pytest.mark.parametrize("kern,rtol", [(TC_3X, 2e-6), (TC_1X, 2e-3), (TC_BF, 3e-5), (TC_F3, 2e-6), (TC_F2, 5e-4), (TC_F1, 1e-3)])
 def test_tmem_accumulators_match_numpy(ctx, trpcage, kern, rtol):
     xyz, mass = trpcage
     xyz = xyz[:300]
@@ -47,7 +47,7 @@ def test_tmem_accumulators_match_numpy(ctx, trpcage, kern, rtol):
     assert err.max() < rtol, f"max scaled error {err.max()}"
 
 
-@pytest.mark.parametrize("kern", [TC_3X, TC_1X, TC_BF, TC_F3, TC_F2])
+@pytest.mark.parametrize("kern", [TC_3X, TC_1X, TC_BF, TC_F3, TC_F2, TC_F1])
 @pytest.mark.parametrize("k", [10, 100])
 def test_trpcage_knn_rms_tc(ctx, trpcage, kern, k):
     import mdsctk_b200
@@ -60,12 +60,16 @@ def test_trpcage_knn_rms_tc(ctx, trpcage, kern, k):
     assert np.array_equal(idx, g["idx_f64"])
     assert (np.abs(dist - g["dist_f64"]) <= 1e-9 * g["dist_f64"]).all()
     assert (np.abs(dist - g["dist_ref"]) <= 1e-4 * g["dist_ref"]).all()
-    if kern not in (TC_1X, TC_F2):      # the coarse filters may fall back to exact rows; the result is the same
+    print("tc kernel", kern, "k", k, {n: st[n] for n in ("fallback_rows", "rescored_max", "max_filter_err", "max_filter_spread",
+                                                         "cert_eps", "cert_gres", "k_keep")})
+    if kern != TC_1X:                   # the coarse TF32 filter may fall back to exact rows; the result is the same
         assert st["fallback_rows"] <= 2
         assert 0.5 * st["max_filter_spread"] < st["cert_eps"]
+    if kern in (TC_F2, TC_F1):          # operand-rounding term of the certificate: residual norms from pack.cu
+        assert 0.0 < st["cert_gres"] < (2e-6 if kern == TC_F2 else 2e-3)
 
 
-@pytest.mark.parametrize("kern", [TC_3X, TC_1X, TC_BF, TC_F3, TC_F2])
+@pytest.mark.parametrize("kern", [TC_3X, TC_1X, TC_BF, TC_F3, TC_F2, TC_F1])
 def test_synthetic_300_atoms_tc(ctx, kern):
     import mdsctk_b200
     from mdsctk_b200 import synth
@@ -83,7 +87,41 @@ def test_synthetic_300_atoms_tc(ctx, kern):
     # both kernels must agree on every row (the FP64 stage decides, the sweep only filters)
     dist0, idx0 = mdsctk_b200.knn_rms(xyz, mass, 32, ctx=ctx, rms_kernel=0)
     assert np.array_equal(idx, idx0) and np.array_equal(dist, dist0)
-    print("tc kernel", kern, {k: st[k] for k in ("ms_sweep", "fallback_rows", "max_filter_err", "max_filter_spread", "cert_eps", "k_keep", "lists_per_row")})
+    print("tc kernel", kern, {k: st[k] for k in ("ms_sweep", "fallback_rows", "rescored_max", "max_filter_err", "max_filter_spread",
+                                                 "cert_eps", "cert_gres", "k_keep", "lists_per_row")})
+    if kern != TC_1X:
+        assert st["fallback_rows"] <= 2
+
+
+def test_rounding_residuals_bound_the_filter_error(ctx):
+    """1xFP16: |sqrt(key) - d| <= g_q + g_r up to accumulation noise -- the metric argument the certificate rests on.
+    Checked on the raw accumulators of one tile: the RMSD between the rounded structures (numpy, FP64) must equal the
+    kernel's key, and the residual norms numpy computes must match the stat the certificate used."""
+    import mdsctk_b200
+    from mdsctk_b200 import synth
+    n = 2000
+    xyz = synth.traj_frames(n, 300, 4)
+    mass = synth.traj_masses(300)
+    P = packed_planes(xyz, mass)                               # float32-rounded operands, as pack.cu forms them
+    hi = (P * 64.0).astype(np.float16).astype(np.float64) / 64.0
+    w = mass.astype(np.float64) / mass.astype(np.float64).sum()
+    x = xyz.astype(np.float64)
+    T = (x - (x * w[None, :, None]).sum(axis=1, keepdims=True)) * np.sqrt(w)[None, :, None]
+    g1 = np.sqrt(((T - hi) ** 2).sum(axis=(1, 2)))
+    ctx.set_option("debug_tile", 1)
+    try:
+        dist, idx = mdsctk_b200.knn_rms(xyz, mass, 32, ctx=ctx, rms_kernel=TC_F1)
+        st = ctx.stats()
+        tile = ctx.debug_fetch_tile()                          # [128 q][3a+b][48 j]: hi x hi contraction
+    finally:
+        ctx.set_option("debug_tile", 0)
+        ctx.set_option("rms_kernel", 0)
+    assert abs(st["cert_gres"] - g1.max()) <= 1e-6 * g1.max() + 1e-9
+    want = np.einsum("qna,jnb->qabj", hi[:128], hi[:48]).reshape(128, 9, 48)
+    assert np.abs(tile - want).max() <= 3e-6 * np.abs(want).max()      # products of fp16 values are exact; fp32 accumulation
+    dist0, idx0 = mdsctk_b200.knn_rms(xyz, mass, 32, ctx=ctx, rms_kernel=0)
+    assert np.array_equal(idx, idx0) and np.array_equal(dist, dist0)
+    assert st["fallback_rows"] == 0
 
 
 def test_ragged_and_out_of_sample_tc(ctx, trpcage):

@@ -59,9 +59,9 @@ enum {
     MDSCTK_KNN_RMS_TC_3XTF32 = 1,  /* tcgen05 kind::tf32, hi/lo operand split (3 MMAs)              */
     MDSCTK_KNN_RMS_TC_1XTF32 = 2,  /* tcgen05 kind::tf32, hi only (coarse filter)                   */
     MDSCTK_KNN_RMS_TC_3XBF16 = 3,  /* tcgen05 kind::f16 on bf16 hi/mid operand split (3 MMAs)       */
-    MDSCTK_KNN_RMS_TC_3XFP16 = 4,  /* tcgen05 kind::f16 on fp16 hi/lo split of 64x (3 MMAs, 22 bits): DEFAULT */
+    MDSCTK_KNN_RMS_TC_3XFP16 = 4,  /* tcgen05 kind::f16 on fp16 hi/lo split of 64x (3 MMAs, 22 bits)          */
     MDSCTK_KNN_RMS_TC_2XFP16 = 5,  /* fit operand fp16 hi only, reference hi/lo (2 MMAs)            */
-    MDSCTK_KNN_RMS_TC_1XFP16 = 6   /* both operands fp16 hi only (1 MMA); exactness comes from the FP64
+    MDSCTK_KNN_RMS_TC_1XFP16 = 6   /* DEFAULT: both operands fp16 hi only (1 MMA); exactness comes from the FP64
                                       re-score, whose certificate bounds the rounding rigorously
                                       (metric triangle inequality on the rounded structures)       */
 };

@@ -46,7 +46,9 @@ class Stats(C.Structure):
 
 
 def library_path():
-    return os.path.join(_PKG, "libmdsctk_knn.so")
+    # MDSCTK_KNN_LIBRARY: an alternative build of the same sources (e.g. the clock-counter build of
+    # scripts/build_prof.sh); never a different implementation
+    return os.environ.get("MDSCTK_KNN_LIBRARY") or os.path.join(_PKG, "libmdsctk_knn.so")
 
 
 def load_library():

@@ -100,9 +100,12 @@ struct mdsctk_knn_ctx {
     std::string err;
     PhaseTimer tm, user_tm;
     // options
-    // 3xFP16: same MMA count as 3xBF16 with 64x smaller split residual; ~5 % slower under the power cap, but its
-    // tighter noise bound certifies rows that 3xBF16 sends to the exact fallback (extended conformations, C4)
-    int rms_kernel = MDSCTK_KNN_RMS_TC_3XFP16;
+    // 1xFP16: one MMA per k-step on fp16-rounded operands; the sweep then measures the exact min-RMSD between the
+    // ROUNDED structures, which the metric triangle inequality ties to the true distance within the rounding
+    // residual norms recorded by pack.cu -- a rigorous term in the re-score certificate, so the result is still
+    // index-exact.  1.9x the sweep rate of 3xFP16 (the previous default: three MMAs, 22 operand bits).
+    int rms_kernel = MDSCTK_KNN_RMS_TC_1XFP16;
+    bool rms_kernel_set = false;   // chosen by the caller: never substituted
     long long slack = -1;
     long long cert_scale_ppm = 1000000;
     // RMSD state
@@ -246,8 +249,6 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
     S.ms_sweep = S.ms_rescore = S.ms_fallback = S.ms_download = 0;
     S.pairs = n_fit * ref.n; S.launches = 0; S.fallback_rows = 0; S.sweep_appends = 0; S.max_filter_err = 0;
     S.max_filter_spread = 0;
-    S.rms_kernel = ctx->rms_kernel;
-
     if (ctx->gmax_dirty) {
         CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
         CK(launch_max_float(ref.G, ref.n, ctx->scalars.as<float>(), ctx->st), "max(G)");
@@ -260,9 +261,15 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
         CK(cudaStreamSynchronize(ctx->st), "sync max(G)");
         ctx->gmax_dirty = false;
     }
+    // 64 * sqrt(G) bounds every fp16 operand element (overflow at 65504): the DEFAULT kernel gives way to 3xTF32
+    // for such coordinates; an explicitly chosen fp16 kernel is refused below instead
+    int rms_kernel = ctx->rms_kernel;
+    if (!ctx->rms_kernel_set && rms_kernel >= MDSCTK_KNN_RMS_TC_3XFP16 && 64.0 * std::sqrt((double)ctx->g_ref_max) > 3.0e4)
+        rms_kernel = MDSCTK_KNN_RMS_TC_3XTF32;
+    S.rms_kernel = rms_kernel;
 
     int keep, cap;
-    const bool use_tc = ctx->rms_kernel != MDSCTK_KNN_RMS_SIMT_FP32;
+    const bool use_tc = rms_kernel != MDSCTK_KNN_RMS_SIMT_FP32;
     choose_lists(ctx, k1, !use_tc, &keep, &cap);
     // tensor-core sweep: four private sub-lists per (row, segment), merged into one at the end of the segment
     if (use_tc) cap = rms_tc_list_stride(keep);
@@ -291,7 +298,7 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
 
     // ---- sweep: all pairs -> k1+slack candidates per row ------------------------------------
     ctx->tm.start(ctx->st);
-    switch (ctx->rms_kernel) {
+    switch (rms_kernel) {
     case MDSCTK_KNN_RMS_SIMT_FP32:
         CK(launch_rms_sweep_simt(fit, fit_begin, n_fit, ref, do_fit, cl, ctx->st), "rms_sweep_simt");
         break;
@@ -301,16 +308,16 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
         CK(launch_fill_u32(ctx->row_tau.p, (size_t)n_fit, 0x7f800000u, ctx->st), "fill row_tau");  // +inf
         {
             const void *q_hi = fitset.hi.p, *q_lo = fitset.lo.p, *r_hi = ctx->ref.hi.p, *r_lo = ctx->ref.lo.p;
-            if (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_3XBF16) {
+            if (rms_kernel == MDSCTK_KNN_RMS_TC_3XBF16) {
                 q_hi = fitset.bh.p; q_lo = fitset.bm.p; r_hi = ctx->ref.bh.p; r_lo = ctx->ref.bm.p;
-            } else if (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_3XFP16 || ctx->rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ||
-                       ctx->rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16) {
+            } else if (rms_kernel == MDSCTK_KNN_RMS_TC_3XFP16 || rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ||
+                       rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16) {
                 q_hi = fitset.fh.p; q_lo = fitset.fl.p; r_hi = ctx->ref.fh.p; r_lo = ctx->ref.fl.p;
                 // 64 * sqrt(G) bounds every operand element; fp16 overflows at 65504
                 if (64.0 * std::sqrt((double)ctx->g_ref_max) > 3.0e4)
                     return fail(ctx, MDSCTK_KNN_EINVAL, "coordinates too large for the fp16 kernels; use rms_kernel=1 (3xTF32)");
             }
-            CK(launch_rms_sweep_tc(ctx->rms_kernel, fit, q_hi, q_lo, fit_begin, n_fit, ref, r_hi, r_lo, do_fit, n_seg, cl,
+            CK(launch_rms_sweep_tc(rms_kernel, fit, q_hi, q_lo, fit_begin, n_fit, ref, r_hi, r_lo, do_fit, n_seg, cl,
                                    ctx->row_tau.as<float>(),
                                    ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
                "rms_sweep_tc");
@@ -322,13 +329,13 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
     CK(cudaGetLastError(), "sweep kernel");
 
     // ---- FP64 re-score + certificate -----------------------------------------------------------
-    const double eps_scale = default_eps_scale(ctx->rms_kernel, ref.A) * (double)ctx->cert_scale_ppm * 1e-6;
+    const double eps_scale = default_eps_scale(rms_kernel, ref.A) * (double)ctx->cert_scale_ppm * 1e-6;
     S.cert_eps = eps_scale * 0.5 * (double)ctx->g_ref_max * 2.0;
     ctx->tm.start(ctx->st);
     // operand-rounding term: 2xFP16 contracts fit fh with reference fh+fl, 1xFP16 fh with fh
-    const int fit_part = (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 || ctx->rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16) ? 0 : -1;
-    const float gres_ref = ctx->rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16 ? ctx->gres_ref_max[0]
-                           : (ctx->rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ? ctx->gres_ref_max[1] : 0.0f);
+    const int fit_part = (rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 || rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16) ? 0 : -1;
+    const float gres_ref = rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16 ? ctx->gres_ref_max[0]
+                           : (rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ? ctx->gres_ref_max[1] : 0.0f);
     S.cert_gres = fit_part >= 0 ? (double)gres_ref : 0.0;
     CK(launch_rms_rescore(fit, fit_begin, n_fit, ref, ctx->wnorm.as<double>(), do_fit, cl, k1, eps_scale,
                           ctx->g_ref_max, fit_part, gres_ref, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(),
@@ -638,6 +645,7 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
     if (!strcmp(key, "rms_kernel")) {
         if (value < 0 || value > 6) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_kernel must be 0..6");
         ctx->rms_kernel = (int)value;
+        ctx->rms_kernel_set = true;
     } else if (!strcmp(key, "slack")) {
         if (value < -1 || value > 1024) return fail(ctx, MDSCTK_KNN_EINVAL, "slack out of range");
         ctx->slack = value;

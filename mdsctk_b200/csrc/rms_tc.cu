@@ -30,6 +30,11 @@
 //                          rotations is a metric, so it is within g_q + g_r (the rounding residual
 //                          norms, pack.cu) of the true distance -- the re-score certificate uses
 //                          that bound instead of an empirical noise constant (rms_rescore.cu)
+//   residency    1xFP16 only (one 16-bit part per operand), atoms <= 352: the y and z planes of the CTA's fit
+//                tile (2 x 8 KB per 32-atom chunk, 160 KB at 300 atoms) are loaded ONCE per work item and
+//                stay in shared memory; the ring then carries only the x plane of the fit tile and the
+//                reference half-tile (12.5 KB per stage instead of 28.5 KB), which takes the L2->SM operand
+//                stream (the limiter once a pass needs a third of the MMAs) from 291 to 131 KB per pass.
 //   accumulators TMEM of each CTA: its 128 fit rows x 3 regions of 144 fp32 columns (432 of 512);
 //                TMEM lane = fit frame, so an epilogue thread reads the nine S values of ITS fit row
 //                with tcgen05.ld (no shuffles), bounds RMSD^2 from below (Frobenius bound, then QCP
@@ -62,6 +67,9 @@ constexpr int A_TILE = TQ * ROW_BYTES;        // 8192 B : one plane of the CTA's
 constexpr int A_PART = 3 * A_TILE;            // 24576 B: x|y|z planes of one split part
 constexpr int B_PART = 3 * TRH * ROW_BYTES;   // 4608 B : this CTA's 72 of the 144 reference operand rows
 constexpr int MAX_NST = 6;
+constexpr int RES_CHUNK = 2 * A_TILE;         // 16384 B: resident y|z planes of one 32-atom chunk (fp16)
+constexpr int RES_STAGE = A_TILE + B_PART;    // 12800 B: ring stage in resident mode (fit x plane + reference half-tile)
+constexpr int RES_MAX_NK = 11;                // resident chunks that still leave room for a 2-stage ring
 constexpr int STATIC_SMEM = 20 * 1024;        // bound on the kernel's static shared memory (checked at launch)
 
 // MODE: 1 = 3xTF32, 2 = 1xTF32, 3 = 3xBF16, 4 = 3xFP16, 5 = 2xFP16 (fit operand: hi part only), 6 = 1xFP16
@@ -85,7 +93,7 @@ constexpr int EPI_WARPS = 4 * SUBS;           // 16
 constexpr int NTHR = 64 + EPI_WARPS * 32;     // 576
 constexpr int TMEM_COLS = 512;
 constexpr int SUBW = TR / SUBS;               // 12 reference columns per epilogue warp
-constexpr int EB = 4;                         // pairs per lane and epilogue batch
+constexpr int EB = 2;                         // pairs per lane and epilogue batch (two batches in flight: TMEM reads of the next one run under the arithmetic of this one)
 constexpr int MERGE_EVERY = 4;                // passes between quarter-wide list merges (power of two)
 constexpr int SUB_APP = 2 * MERGE_EVERY * SUBW;   // 96: private append area per epilogue warp and row
 }  // namespace tc
@@ -97,6 +105,7 @@ struct TcArgs {
     CandLists<float> cl;        // H = n_seg lists per fit row
     float *debug_tile;          // optional [128][9][48]: raw accumulators of (fit tile 0, ref tile 0)
     float *row_tau;             // [n_q] running admission threshold per fit row (+inf before the first segment)
+    int res, res_nst;           // resident fit planes (1xFP16): on/off, ring stages that fit beside them
     int dbg;                    // MDSCTK_TC_DEBUG bits: 1 skip QCP, 2 skip MMA issue, 4 skip TMA, 8 no cheap bound
     long long *prof;            // MDSCTK_TC_PROF=1: [grid][8] clock sums (see launch_rms_sweep_tc)
 };
@@ -123,7 +132,8 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     constexpr uint32_t STAGE_TX = 2u * STAGE_BYTES;    // both CTAs' bytes land on the leader's barrier
 
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[MAX_NST], bar_empty[MAX_NST], bar_tmem_full, bar_tmem_empty;
+    __shared__ __align__(8) uint64_t bar_full[MAX_NST], bar_empty[MAX_NST], bar_tmem_full, bar_tmem_empty, bar_res_full,
+        bar_res_empty;
     __shared__ uint32_t s_tmem_base;
     __shared__ unsigned s_hist[EPI_WARPS][256];
     __shared__ int s_cnt[EPI_WARPS][32];
@@ -134,6 +144,12 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();           // 0 = leader (issues the pair's MMAs)
     const int nk = (a.A_pad + KC - 1) / KC;
+    // resident mode: smem = [nk chunks x (y|z planes)] [ring of nst stages x (x plane | reference half-tile)]
+    const bool res = (MODE == 6) && a.res != 0;
+    const int nst = res ? a.res_nst : NST;
+    const int stage_bytes = res ? RES_STAGE : STAGE_BYTES;
+    const int ring_off = res ? nk * RES_CHUNK : 0;
+    const int off_b = res ? A_TILE : OFF_BHI;          // reference operand inside a stage
     const long long n_qt = (a.n_q + UMMA_M - 1) / UMMA_M;          // fit super-tiles of 256 rows
     const long long n_rt = (a.n_r + TR - 1) / TR;
     const long long n_items = n_qt * a.n_seg;
@@ -142,6 +158,8 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_tmem_full, 1);
+        mbar_init(&bar_res_full, 1);
+        mbar_init(&bar_res_empty, 1);
         mbar_init(&bar_tmem_empty, 2 * EPI_WARPS);     // the epilogue warps of BOTH CTAs (used on the leader only)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -186,21 +204,43 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         // converged warp; one elected lane issues.  Each CTA loads its own fit rows and its half of
         // the reference tile; every copy completes on the LEADER's full barrier.
         int s = 0;
-        uint32_t ph = 0;
+        uint32_t ph = 0, rph = 0;
+        bool first_item = true;
         const uint64_t pol_a = (a.dbg & 16) ? kEvictNormal : kEvictLast, pol_b = (a.dbg & 32) ? kEvictFirst : kEvictNormal;
         for (long long it = pair_id; it < n_items; it += n_pairs) {
             long long qt, rt0, rt1, rot; int seg;
             item_range(it, qt, rt0, rt1, seg, rot);
             const int q0 = (int)(a.q_begin + qt * UMMA_M + rank * TQ);
+            if (res) {
+                // the y|z planes of this item's fit tile, once: the previous item's MMAs must be done with theirs
+                if (!first_item) { mbar_wait(&bar_res_empty, rph, 5); rph ^= 1; }
+                first_item = false;
+                const uint32_t res_leader = map_to_cta(&bar_res_full, 0);
+                if (elect_one()) {
+                    if (a.dbg & 4) {
+                        if (rank == 0) mbar_arrive(&bar_res_full);
+                    } else {
+                        if (rank == 0) mbar_expect_tx(&bar_res_full, 2u * (uint32_t)(nk * RES_CHUNK));
+                        for (int kc = 0; kc < nk; ++kc)          // map_q_lo: the single-plane box of the fit hi planes
+                            for (int p = 1; p < 3; ++p)
+                                tma_load_3d_2sm(smem + kc * RES_CHUNK + (p - 1) * A_TILE, &map_q_lo, res_leader, kc * KC, q0, p, pol_a);
+                    }
+                }
+                __syncwarp();
+            }
             for (long long ti = 0; ti < rt1 - rt0; ++ti) {
                 const int r0 = (int)(tile_at(ti, rt0, rt1, rot) * TR + rank * TRH);
                 for (int kc = 0; kc < nk; ++kc) {
                     mbar_wait(&bar_empty[s], ph ^ 1, 1);             // the pair's MMAs have read stage s (both CTAs)
-                    unsigned char *st = smem + s * STAGE_BYTES;
+                    unsigned char *st = smem + ring_off + s * stage_bytes;
                     const uint32_t full_leader = map_to_cta(&bar_full[s], 0);
                     if (elect_one()) {
                         if (a.dbg & 4) {
                             if (rank == 0) mbar_arrive(&bar_full[s]);
+                        } else if (res) {
+                            if (rank == 0) mbar_expect_tx(&bar_full[s], 2u * RES_STAGE);
+                            tma_load_3d_2sm(st, &map_q_lo, full_leader, kc * KC, q0, 0, pol_a);            // fit x plane
+                            tma_load_3d_2sm(st + A_TILE, &map_r_hi, full_leader, kc * KC, r0, 0, pol_b);   // reference half-tile
                         } else {
                             if (rank == 0) mbar_expect_tx(&bar_full[s], STAGE_TX);
                             // one box = 64 bytes of atoms x rows frames x 3 planes, landing as [plane][frame][atoms]
@@ -211,7 +251,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                         }
                     }
                     __syncwarp();
-                    if (++s == NST) { s = 0; ph ^= 1; }
+                    if (++s == nst) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -220,11 +260,15 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         // converged warp, descriptors in uniform registers, one elected lane issues
         if (rank == 0) {
             int s = 0;
-            uint32_t ph = 0, tph = 0;
+            uint32_t ph = 0, tph = 0, rfph = 0;
             bool first_pass = true;
             long long t_wait_empty = 0, t_wait_full = 0, t_total0 = MDSCTK_TC_PROF_BUILD ? clock64() : 0, n_pass_done = 0;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+            const uint32_t res_lo = umma_desc_lo(smem_u), ring_lo = umma_desc_lo(smem_u + ring_off);
+            const uint32_t stage_lo = (uint32_t)stage_bytes >> 4;
+            const bool skip_mma = (a.dbg & 2) != 0;
+            const int grp = nst >= 6 ? 2 : 1;          // a shallow ring (3x modes: 3 stages) cannot wait for two stages at once
             for (long long it = pair_id; it < n_items; it += n_pairs) {
                 long long qt, rt0, rt1, rot; int seg;
                 item_range(it, qt, rt0, rt1, seg, rot);
@@ -238,38 +282,61 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     ++n_pass_done;
                     first_pass = false;
                     tc_fence_after();
-                    for (int kc = 0; kc < nk; ++kc) {
+                    // Stages are taken in groups of GRP: one wait/fence/elect round per group.  tcgen05.mma issue
+                    // back-pressures (measured: the issuing thread's busy time equals the MMA execution time), so
+                    // whatever runs between two stages leaves the tensor pipe idle -- with one MMA per k-step a stage
+                    // is only 6 MMAs (430 clk) and a per-stage round cost a third of the MMA phase.
+                    for (int kc0 = 0; kc0 < nk; kc0 += grp) {
+                        const int ng = min(grp, nk - kc0);
                         {
                             const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
-                            if (a.dbg & 64) mbar_wait(&bar_full[s], ph, 3); else mbar_wait_spin(&bar_full[s], ph, 3);
+                            int s2 = s; uint32_t ph2 = ph;
+                            for (int u = 0; u < ng; ++u) {
+                                mbar_wait_spin(&bar_full[s2], ph2, 3);
+                                if (++s2 == nst) { s2 = 0; ph2 ^= 1; }
+                            }
                             if (MDSCTK_TC_PROF_BUILD && a.prof) t_wait_full += clock64() - t0;
                         }
+                        if (res && ti == 0 && kc0 == 0) { mbar_wait_spin(&bar_res_full, rfph, 6); rfph ^= 1; }   // this item's y|z planes
                         tc_fence_after();
-                        const uint32_t sa = smem_u + s * STAGE_BYTES;
-                        // atoms beyond A_pad are zero-filled by TMA; skip a k-step that is all padding
-                        const int ksteps = (a.A_pad - kc * KC) * (BF16 ? 2 : 4) > 32 ? KSTEPS : 1;
                         if (elect_one()) {
-                            for (int ks = 0; ks < ((a.dbg & 2) ? 0 : ksteps); ++ks) {
-                                const uint32_t koff = ks * 32;
-                                const uint64_t bhi = umma_desc_sw64(sa + OFF_BHI + koff);
-                                const uint64_t blo = umma_desc_sw64(sa + OFF_BLO + koff);
+                            // descriptor LOW words: ring slot / resident chunk base + constant offsets (one add per operand)
+                            int s2 = s;
+                            for (int u = 0; u < ng; ++u) {
+                                const int kc = kc0 + u;
+                                const uint32_t st_lo = ring_lo + (uint32_t)s2 * stage_lo;
+                                const uint32_t rs_lo = res_lo + (uint32_t)kc * (RES_CHUNK >> 4);
+                                // atoms beyond A_pad are zero-filled by TMA; skip a k-step that is all padding
+                                const int ksteps = skip_mma ? 0 : ((a.A_pad - kc * KC) * (BF16 ? 2 : 4) > 32 ? KSTEPS : 1);
 #pragma unroll
-                                for (int p = 0; p < 3; ++p) {
-                                    const uint32_t d = tmem_u + p * UMMA_N;
-                                    const uint64_t ahi = umma_desc_sw64(sa + OFF_AHI + p * A_TILE + koff);
-                                    tc_mma2<BF16>(d, ahi, bhi, IDESC, (kc | ks) != 0);
-                                    if constexpr (B_LO) tc_mma2<BF16>(d, ahi, blo, IDESC, 1);
-                                    if constexpr (A_LO) {
-                                        const uint64_t alo = umma_desc_sw64(sa + OFF_ALO + p * A_TILE + koff);
-                                        tc_mma2<BF16>(d, alo, bhi, IDESC, 1);
+                                for (int ks = 0; ks < KSTEPS; ++ks) {
+                                    if (ks < ksteps) {
+                                        const uint32_t koff = ks * 2;                      // 32 bytes >> 4
+                                        const uint32_t bhi = st_lo + (uint32_t)(off_b >> 4) + koff;
+                                        const uint32_t blo = st_lo + (OFF_BLO >> 4) + koff;
+#pragma unroll
+                                        for (int p = 0; p < 3; ++p) {
+                                            const uint32_t d = tmem_u + p * UMMA_N;
+                                            const uint32_t ahi = (res && p > 0) ? rs_lo + (p - 1) * (A_TILE >> 4) + koff
+                                                                                : st_lo + (OFF_AHI >> 4) + p * (A_TILE >> 4) + koff;
+                                            tc_mma2_lo<BF16>(d, ahi, bhi, IDESC, ks == 0 ? (uint32_t)(kc != 0) : 1u);
+                                            if constexpr (B_LO) tc_mma2_lo<BF16>(d, ahi, blo, IDESC, 1);
+                                            if constexpr (A_LO) {
+                                                const uint32_t alo = st_lo + (OFF_ALO >> 4) + p * (A_TILE >> 4) + koff;
+                                                tc_mma2_lo<BF16>(d, alo, bhi, IDESC, 1);
+                                            }
+                                        }
                                     }
                                 }
+                                tc_commit2_mc(&bar_empty[s2], 3);                      // frees the stage in both CTAs
+                                if (kc == nk - 1) tc_commit2_mc(&bar_tmem_full, 3);    // accumulators complete -> both epilogues
+                                if (res && kc == nk - 1 && ti == rt1 - rt0 - 1) tc_commit2_mc(&bar_res_empty, 3);   // item done with its y|z planes
+                                if (++s2 == nst) s2 = 0;
                             }
-                            tc_commit2_mc(&bar_empty[s], 3);                       // frees stage s in both CTAs
-                            if (kc == nk - 1) tc_commit2_mc(&bar_tmem_full, 3);    // accumulators complete -> both epilogues
                         }
                         __syncwarp();
-                        if (++s == NST) { s = 0; ph ^= 1; }
+                        s += ng;                                  // ng <= nst
+                        if (s >= nst) { s -= nst; ph ^= 1; }
                     }
                 }
             }
@@ -431,19 +498,28 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 const float htau = 0.5f * tau;
                 const float ge[SUBW] = {gv[0].x, gv[0].y, gv[0].z, gv[0].w, gv[1].x, gv[1].y, gv[1].z, gv[1].w,
                                         gv[2].x, gv[2].y, gv[2].z, gv[2].w};
-#pragma unroll
-                for (int h = 0; h < SUBW; h += EB) {
-                    float sv[9][EB];
+                // Software-pipelined drain: the tcgen05.ld of batch hb+1 are issued before the arithmetic of batch
+                // hb, so the TMEM read port (the floor of the hold: 128 lanes x 432 columns per pass) stays busy.
+                float svb[2][9][EB];
+                auto load_batch = [&](int h, float (&dst)[9][EB]) {
 #pragma unroll
                     for (int p = 0; p < 3; ++p)
 #pragma unroll
                         for (int b = 0; b < 3; ++b)
-                            tc_ld4(t_warp + p * UMMA_N + b * TRH + h, sv, p * 3 + b);
+                            tc_ld2(t_warp + p * UMMA_N + b * TRH + h, dst, p * 3 + b);
+                };
+                load_batch(0, svb[0]);
+#pragma unroll
+                for (int hb = 0; hb < SUBW / EB; ++hb) {
+                    const int h = hb * EB;
+                    float (&sv)[9][EB] = svb[hb & 1];
                     tc_wait_ld();
-                    if (h + EB == SUBW) {             // last TMEM read of this pass: hand the accumulators back
+                    if (hb + 1 < SUBW / EB) {
+                        load_batch(h + EB, svb[(hb + 1) & 1]);
+                    } else {                          // last TMEM read of this pass: hand the accumulators back
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(empty_leader);
+                        if (lane == 0) { if (a.dbg & 512) mbar_arrive_cluster(empty_leader); else mbar_arrive_cluster_nofence(empty_leader); }
                         if (MDSCTK_TC_PROF_BUILD && a.prof) tp2 = clock64();
                     }
                     if (a.debug_tile && it == 0 && rt == 0 && rank == 0) {
@@ -474,7 +550,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     }
                     // (1) cheap bound: lambda_max <= sqrt(3) |S|_F, so RMSD^2 >= 2 (E0 - sqrt(3 F)).  Far
                     //     pairs (other conformational basins) are rejected for 9 FMAs; a batch whose
-                    //     128 pairs are all far skips the characteristic polynomial altogether.
+                    //     64 pairs are all far skips the characteristic polynomial altogether.
                     float f[EB];
                     bool far = true;
 #pragma unroll
@@ -530,7 +606,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 // ---------------------------------------------------------------- host side ----
 // planes[n][3][A_pad] as a 3-D tensor ordered (atom, frame, plane); box = 64 bytes of atoms x `rows`
 // frames x 3 planes, so one TMA op lands the three plane tiles back to back as [plane][frame][atoms].
-static bool make_plane_map(CUtensorMap *m, const void *planes, long long n, int A_pad, int rows, int mode)
+static bool make_plane_map(CUtensorMap *m, const void *planes, long long n, int A_pad, int rows, int mode, int box_planes = 3)
 {
     EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) return false;
@@ -539,7 +615,7 @@ static bool make_plane_map(CUtensorMap *m, const void *planes, long long n, int 
                                    : (mode >= 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
     cuuint64_t dims[3] = {(cuuint64_t)A_pad, (cuuint64_t)n, 3};
     cuuint64_t strides[2] = {(cuuint64_t)A_pad * 3 * esz, (cuuint64_t)A_pad * esz};
-    cuuint32_t box[3] = {(cuuint32_t)(tc::ROW_BYTES / esz), (cuuint32_t)rows, 3};
+    cuuint32_t box[3] = {(cuuint32_t)(tc::ROW_BYTES / esz), (cuuint32_t)rows, (cuuint32_t)box_planes};
     cuuint32_t estr[3] = {1, 1, 1};
     return enc(m, dt, 3, const_cast<void *>(planes),
                dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -569,11 +645,22 @@ int rms_tc_lists_per_segment() { return 1; }
 // Entries reserved per list: keep merged + one append area per epilogue warp of a lane quarter.
 int rms_tc_list_stride(int keep) { return (keep + tc::SUBS * tc::SUB_APP + 31) / 32 * 32; }
 
+// resident mode (1xFP16): ring stages that fit beside the y|z planes of the fit tile; 0 = does not fit
+static int res_ring_stages(int A_pad)
+{
+    const int nk = (A_pad + 31) / 32;
+    if (nk > tc::RES_MAX_NK) return 0;
+    const int room = 227 * 1024 - tc::STATIC_SMEM - 1024 - nk * tc::RES_CHUNK;
+    const int nst = room / tc::RES_STAGE;
+    return nst < 2 ? 0 : (nst < tc::MAX_NST ? nst : tc::MAX_NST);
+}
+
 template <int M>
 static cudaError_t launch_tc_mode(const CUtensorMap &mq_hi, const CUtensorMap &mq_lo, const CUtensorMap &mr_hi,
                                   const CUtensorMap &mr_lo, const TcArgs &a, long long n_items, int n_sms, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(rms_sweep_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Mode<M>::SMEM_BYTES);
+    const int smem_bytes = a.res ? ((a.A_pad + 31) / 32) * tc::RES_CHUNK + a.res_nst * tc::RES_STAGE + 1024 : tc::Mode<M>::SMEM_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(rms_sweep_tc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, rms_sweep_tc_kernel<M>);
@@ -584,7 +671,7 @@ static cudaError_t launch_tc_mode(const CUtensorMap &mq_hi, const CUtensorMap &m
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(tc::NTHR); cfg.dynamicSmemBytes = tc::Mode<M>::SMEM_BYTES; cfg.stream = st;
+    cfg.blockDim = dim3(tc::NTHR); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
     int max_pairs = n_sms / 2;
     cfg.gridDim = dim3((unsigned)(max_pairs * 2));
     int q = 0;
@@ -604,9 +691,17 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
 {
     if (n_fit <= 0) return cudaSuccess;
     if (cl.H != n_seg || cl.cap < cl.keep + tc::SUBS * tc::SUB_APP) return cudaErrorInvalidValue;
+    const char *dbg = getenv("MDSCTK_TC_DEBUG");
+    const int dbg_bits = dbg ? atoi(dbg) : 0;
+    // 1xFP16, MDSCTK_TC_DEBUG bit 256: keep two of the three fit planes resident in shared memory when they fit.
+    // Off by default: it cuts the L2->SM operand stream 2.2x but leaves room for only 3 ring stages at 300 atoms,
+    // and the sweep is bound by the MMA <-> epilogue hand-over, not by the stream (measured 92-101 ms vs 84-89 ms).
+    const int res_nst = (mode == 6 && (dbg_bits & 256)) ? res_ring_stages(ref.A_pad) : 0;
     CUtensorMap mq_hi, mq_lo, mr_hi, mr_lo;
     if (!make_plane_map(&mq_hi, fit_hi, fit.n, fit.A_pad, tc::TQ, mode) ||
-        !make_plane_map(&mq_lo, fit_lo, fit.n, fit.A_pad, tc::TQ, mode) ||
+        // resident mode has no lo operand: the slot carries the single-plane box of the fit hi planes
+        !(res_nst ? make_plane_map(&mq_lo, fit_hi, fit.n, fit.A_pad, tc::TQ, mode, 1)
+                  : make_plane_map(&mq_lo, fit_lo, fit.n, fit.A_pad, tc::TQ, mode)) ||
         !make_plane_map(&mr_hi, ref_hi, ref.n, ref.A_pad, tc::TRH, mode) ||
         !make_plane_map(&mr_lo, ref_lo, ref.n, ref.A_pad, tc::TRH, mode))
         return cudaErrorInvalidValue;
@@ -616,8 +711,8 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
     a.r_G = mode == 6 ? ref.Gh : (mode == 5 ? ref.G2 : ref.G);
     a.q_begin = fit_begin; a.n_q = n_fit; a.n_r = ref.n;
     a.A_pad = ref.A_pad; a.do_fit = do_fit; a.n_seg = n_seg; a.cl = cl; a.debug_tile = debug_tile; a.row_tau = row_tau;
-    const char *dbg = getenv("MDSCTK_TC_DEBUG");
-    a.dbg = dbg ? atoi(dbg) : 0;
+    a.dbg = dbg_bits;
+    a.res = res_nst > 0; a.res_nst = res_nst;
     // MDSCTK_TC_PROF=1: per-CTA clock sums {MMA warp: total, wait tmem_empty, wait full, passes |
     // epilogue warp 0: wait tmem_full, TMEM hold, post-release compute, merges}, printed to stderr
     static long long *d_prof = nullptr;

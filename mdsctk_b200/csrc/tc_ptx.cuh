@@ -112,6 +112,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// Hand-off of TMEM accumulators to the MMA issuer of the leader CTA: the reads are ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync, no global/shared data is published, so the
+// arrive needs no cluster-scope release fence (measured: the MEMBAR of the .release.cluster form was 11 % of
+// the epilogue's stall samples, on the critical path of every pass).  Same form as cutlass ClusterBarrier::arrive.
+__device__ __forceinline__ void mbar_arrive_cluster_nofence(uint32_t bar_cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 // one lane of a converged warp (the others fall through); keeps the operands of the guarded
 // instruction in uniform registers instead of a per-lane "waterfall" loop
 __device__ __forceinline__ bool elect_one()
@@ -172,12 +180,45 @@ __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_
             : "memory");
     }
 }
+// Same with the descriptors given as their LOW words (start address >> 4 | LBO field); the high word of
+// every SWIZZLE_64B K-major descriptor here is the constant kDescHiSw64, so stepping through a tile is one
+// 32-bit add per operand instead of rebuilding the 64-bit descriptor.  ACC: accumulate flag known at compile time.
+constexpr uint32_t kDescHiSw64 = (uint32_t)((512u >> 4) | (1u << 14) | (4u << 29));   // SBO=512 B, version 1, SWIZZLE_64B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <bool BF16>
+__device__ __forceinline__ void tc_mma2_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc)
+{
+    if constexpr (BF16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %5};\n\t"
+            "mov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHiSw64)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %5};\n\t"
+            "mov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHiSw64)
+            : "memory");
+    }
+}
 // four consecutive accumulator columns of this thread's TMEM lane -> v[c][0..3] (valid after tc_wait_ld)
 __device__ __forceinline__ void tc_ld4(uint32_t taddr, float (&v)[9][4], int c)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v[c][0]), "=f"(v[c][1]), "=f"(v[c][2]), "=f"(v[c][3])
                  : "r"(taddr));
+}
+// two consecutive accumulator columns -> v[c][0..1]
+__device__ __forceinline__ void tc_ld2(uint32_t taddr, float (&v)[9][2], int c)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=f"(v[c][0]), "=f"(v[c][1]) : "r"(taddr));
 }
 // sixteen consecutive accumulator columns of this thread's TMEM lane (valid after tc_wait_ld)
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])

@@ -27,9 +27,9 @@ def test_c3_full_size_properties_and_oracle_sample():
     xyz = synth.traj_frames(n, 300, 16, 20260117)
     mass = synth.traj_masses(300)
     with mdsctk_b200.KnnContext(0) as ctx:
-        dist, idx = mdsctk_b200.knn_rms(xyz, mass, k, ctx=ctx)                      # default kernel (3xFP16)
+        dist, idx = mdsctk_b200.knn_rms(xyz, mass, k, ctx=ctx)                      # default kernel (1xFP16)
         st = ctx.stats()
-        assert st["fallback_rows"] <= 8
+        assert st["rms_kernel"] == mdsctk_b200.RMS_TC_1XFP16 and st["fallback_rows"] <= 8
         assert dist.shape == (n, k) and (np.diff(dist, axis=1) >= 0).all()
         assert (idx != np.arange(n)[:, None]).all() and (idx >= 0).all() and (idx < n).all()
         assert all(len(set(r)) == k for r in idx[::997])

@@ -124,6 +124,23 @@ def test_rounding_residuals_bound_the_filter_error(ctx):
     assert st["fallback_rows"] == 0
 
 
+def test_default_kernel_and_fp16_overflow_substitution(trpcage):
+    """The default is the 1xFP16 sweep; coordinates that would overflow fp16 (64*sqrt(G) > 3e4) make the default give
+    way to 3xTF32, while an explicitly requested fp16 kernel is refused.  Same neighbours either way (RMSD scales)."""
+    import mdsctk_b200
+    xyz, mass = trpcage
+    xyz = xyz[:300]
+    with mdsctk_b200.KnnContext(0) as c:
+        dist, idx = mdsctk_b200.knn_rms(xyz, mass, 10, ctx=c)
+        assert c.stats()["rms_kernel"] == TC_F1
+        big = (xyz * np.float32(1000.0)).astype(np.float32)          # G ~ 5e5 nm^2
+        dist_b, idx_b = mdsctk_b200.knn_rms(big, mass, 10, ctx=c)
+        assert c.stats()["rms_kernel"] == TC_3X
+        assert np.array_equal(idx_b, idx) and np.allclose(dist_b, dist * 1000.0, rtol=1e-5)
+        with pytest.raises(mdsctk_b200.KnnError):
+            mdsctk_b200.knn_rms(big, mass, 10, ctx=c, rms_kernel=TC_F1)
+
+
 def test_ragged_and_out_of_sample_tc(ctx, trpcage):
     import mdsctk_b200
     from oracle import binding as ob

@@ -183,3 +183,39 @@ def test_partial_row_is_dropped():
     # knn_data.cpp:146-151 drops a trailing partial row; load_pts mirrors that
     raw = np.fromfile(os.path.join(DATA, "rings.pts"), dtype=np.float64)
     assert load_pts("rings.pts", 3).shape == (raw.size // 3, 3)
+
+
+def test_qcp_c0_identity():
+    """det K = |S|_F^4 - 4 |cof S|_F^2 for the 4x4 key matrix K of a 3x3 cross-covariance S: the form
+    mdsctk_b200/csrc/qcp.cuh uses for the constant coefficient of the QCP characteristic polynomial."""
+    rng = np.random.default_rng(7)
+    for _ in range(500):
+        S = rng.standard_normal((3, 3)) * rng.uniform(0.01, 3.0, (3, 1))
+        (sxx, sxy, sxz), (syx, syy, syz), (szx, szy, szz) = S
+        K = np.array([[sxx + syy + szz, syz - szy, szx - sxz, sxy - syx],
+                      [syz - szy, sxx - syy - szz, sxy + syx, szx + sxz],
+                      [szx - sxz, sxy + syx, -sxx + syy - szz, syz + szy],
+                      [sxy - syx, szx + sxz, syz + szy, -sxx - syy + szz]])
+        F = (S ** 2).sum()
+        cof = np.array([[np.linalg.det(np.delete(np.delete(S, i, 0), j, 1)) for j in range(3)] for i in range(3)])
+        assert abs(np.linalg.det(K) - (F * F - 4.0 * (cof ** 2).sum())) <= 1e-12 * F * F
+
+
+def test_rounded_structure_triangle_bound():
+    """The certificate of the 1xFP16 sweep: min-RMSD between the fp16-rounded structures is within
+    g_q + g_r (the rounding residual norms) of the true min-RMSD.  Checked with the oracle's FP64 Kabsch."""
+    from mdsctk_b200 import synth
+    xyz = synth.traj_frames(600, 100, 3, 5).astype(np.float64)
+    w = np.full(100, 1.0 / 100)
+    T = (xyz - (xyz * w[None, :, None]).sum(axis=1, keepdims=True)) * np.sqrt(w)[None, :, None]
+    R = (T * 64.0).astype(np.float32).astype(np.float16).astype(np.float64) / 64.0
+    g = np.sqrt(((T - R) ** 2).sum(axis=(1, 2)))
+
+    def min_rmsd(a, b):                       # rotation only (the rounded structures are not re-centred)
+        u, s, vt = np.linalg.svd(a.T @ b)
+        s[-1] *= np.sign(np.linalg.det(u @ vt))
+        return np.sqrt(max((a ** 2).sum() + (b ** 2).sum() - 2.0 * s.sum(), 0.0))
+
+    rng = np.random.default_rng(1)
+    for q, r in rng.integers(0, 600, (300, 2)):
+        assert abs(min_rmsd(T[q], T[r]) - min_rmsd(R[q], R[r])) <= g[q] + g[r] + 1e-12

@@ -48,7 +48,7 @@ struct FrameSet {
     {
         FrameSetView v;
         v.raw = raw.as<float>(); v.planes = planes.as<float>(); v.G = G.as<float>(); v.cen = cen.as<double>();
-        v.Gh = Gh.as<float>(); v.G2 = G2.as<float>(); v.gres = gres.as<float>();
+        v.Gh = Gh.as<float>(); v.G2 = G2.as<float>(); v.gres = gres.as<float>(); v.fh = fh.p; v.fl = fl.p;
         v.n = n; v.A = A; v.A_pad = A_pad;
         return v;
     }
@@ -226,10 +226,12 @@ double default_eps_scale(int rms_kernel, int n_atoms)
     switch (rms_kernel) {
     case MDSCTK_KNN_RMS_TC_1XTF32: return 4e-5 * sa;
     case MDSCTK_KNN_RMS_TC_3XBF16: return 1.5e-5;       // bf16 split residual 2^-18 per product dominates
-    // the reduced FP16 modes bound the operand rounding separately and rigorously (gres, rms_rescore.cu);
-    // what is left is the same fp32 accumulation noise as 3xFP16 (fewer accumulation steps, if anything)
+    // the reduced FP16 modes bound the operand rounding separately and rigorously (gres, rms_rescore.cu); what is
+    // left is the fp32 accumulation error of 19-38 MMAs per accumulator, which the re-score MEASURES on every
+    // row (key - exact distance of the rounded structures, stats.max_filter_spread): largest half-spread seen
+    // over 1.6e6 candidates 1.8e-5 nm^2 at E0 = 17.5 nm^2 (1.0e-6 E0); the bound is 2.5x that
     case MDSCTK_KNN_RMS_TC_2XFP16:
-    case MDSCTK_KNN_RMS_TC_1XFP16:
+    case MDSCTK_KNN_RMS_TC_1XFP16: return 1.5e-7 * sa;
     case MDSCTK_KNN_RMS_TC_3XFP16:
     case MDSCTK_KNN_RMS_TC_3XTF32:
     default: return 5e-7 * sa;
@@ -277,7 +279,7 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
     const int H = use_tc ? rms_tc_lists_per_segment() * n_seg : 1;
     S.k_keep = keep;
     S.lists_per_row = H;
-    if ((size_t)ref.A * 24 + (size_t)keep * H * 2 * 28 + 64 * 80 > 220 * 1024)
+    if ((size_t)ref.A * 48 + (size_t)std::min(keep * H, 2048) * 2 * 28 + 64 * 80 > 220 * 1024 || keep > 2048)
         return fail(ctx, MDSCTK_KNN_EINVAL, "k too large for the FP64 re-score kernel's shared memory");
     CandLists<float> cl;
     CK(ctx->cand_key.reserve((size_t)n_fit * H * cap * 4), "cudaMalloc(cand_key)");
@@ -338,7 +340,7 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
                            : (rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ? ctx->gres_ref_max[1] : 0.0f);
     S.cert_gres = fit_part >= 0 ? (double)gres_ref : 0.0;
     CK(launch_rms_rescore(fit, fit_begin, n_fit, ref, ctx->wnorm.as<double>(), do_fit, cl, k1, eps_scale,
-                          ctx->g_ref_max, fit_part, gres_ref, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(),
+                          ctx->g_ref_max, fit_part, rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ? 2 : 1, gres_ref, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(),
                           d_err, d_nbad, ctx->bad_rows.as<int>(), ctx->st), "rms_rescore");
     S.launches += 1;
     struct { double pad, err, spread, done_max; int nbad; } host_sc;

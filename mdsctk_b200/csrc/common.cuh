@@ -31,6 +31,7 @@ struct FrameSetView {
     const float *G;       // [n]
     const float *Gh, *G2; // [n]     norms of the fp16-rounded structures (1 part / 2 parts)
     const float *gres;    // [n][2]  their distance from the true structure
+    const void *fh, *fl;  // fp16 [n][3][A_pad]  the rounded operand planes themselves (64 * sqrt(w) (x - c), hi / lo part)
     const double *cen;    // [n][4]
     long long n;
     int A, A_pad;
@@ -77,12 +78,12 @@ int rms_tc_list_stride(int keep);
 //   err_stats: device double[2] = {max |approx - exact| d^2, max per-row spread of (approx - exact)};
 //   n_bad: device int counter of uncertified rows, listed in bad_rows.
 //   fit_part / gres_ref_max: operand-rounding term of the certificate for the 2xFP16 / 1xFP16 sweeps
-//   (fit_part = column of fit.gres the sweep's fit operand corresponds to, -1 = none; gres_ref_max =
-//   largest residual norm of the reference operand), see rms_rescore.cu.
+//   (fit_part = column of fit.gres the sweep's fit operand corresponds to, -1 = none; ref_parts = fp16 parts of
+//   the reference operand, 1 or 2; gres_ref_max = largest residual norm of the reference operand), see rms_rescore.cu.
 cudaError_t launch_rms_rescore(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                const FrameSetView &ref, const double *mass_norm, int do_fit,
                                CandLists<float> cl, int k1, double eps_scale, float g_ref_max,
-                               int fit_part, float gres_ref_max, double *out_dist, int *out_idx, int *flags, double *err_stats, int *n_bad,
+                               int fit_part, int ref_parts, float gres_ref_max, double *out_dist, int *out_idx, int *flags, double *err_stats, int *n_bad,
                                int *bad_rows, cudaStream_t st);
 
 // Exact FP64 d^2 of fit row(s) against every reference frame: out[n_rows][n_ref] (nm^2).

@@ -13,6 +13,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cuda_fp16.h>
 #include "sort.cuh"
 
 namespace mdsctk {
@@ -91,6 +92,7 @@ struct RescoreArgs {
     double eps_scale;
     float g_ref_max;
     int fit_part;            // column of fit.gres the sweep's fit operand corresponds to, -1: no operand-rounding term
+    int ref_parts;           // fp16 parts of the sweep's reference operand (1: fh, 2: fh + fl)
     float gres_ref_max;      // largest rounding residual norm of the reference operand (nm)
     double *out_dist;
     int *out_idx, *flags;
@@ -122,23 +124,32 @@ struct RescoreArgs {
 //            min_i [key_i - max(d_i - g, 0)^2] + (d_k + g)^2 + 2 eps < a_next.
 //      The brackets of all re-scored candidates must intersect (model check, replaces the spread
 //      test).  With g = 0 this is the rule of step 2 with min_i err_i in place of the top-k1 maximum.
+//      For the first ROUNDED_EXACT candidates of a row the kernel also computes d~ itself -- the FP64
+//      min-RMSD of the two ROUNDED structures, from the fp16 planes -- so their bracket of B is exact
+//      (key - d~^2, no g on that side): only the g that ties an UNSEEN pair's d to its d~ remains.
 constexpr int RESCORE_ROUND = 64;
+constexpr int ROUNDED_EXACT = 8;
+constexpr int RESCORE_PMAX = 2048;   // working-set cap (candidates with key <= tau_row); a row that exceeds it is redone exactly
 
 __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int A = a.fit.A, P = a.P;
     double *wq = reinterpret_cast<double *>(dsm);          // [3A]
-    double *s_d = wq + 3 * A;                              // [P] sort keys
+    double *wqh = wq + 3 * A;                              // [3A] the fit row as the sweep saw it: fp16 planes / 64
+    double *s_d = wqh + 3 * A;                             // [P] sort keys
     double *u_dist = s_d + P;                              // [P] exact distance, candidate order
     double *s_S = u_dist + P;                              // [RESCORE_ROUND][10] cross-covariance + Gr
-    int *s_i = reinterpret_cast<int *>(s_S + RESCORE_ROUND * 10);  // [P]
+    double *s_Sh = s_S + RESCORE_ROUND * 10;               // [ROUNDED_EXACT][10] the same between the rounded structures
+    int *s_i = reinterpret_cast<int *>(s_Sh + ROUNDED_EXACT * 10);  // [P]
     int *u_i = s_i + P;                                    // [P] candidate reference index
     float *u_apx = reinterpret_cast<float *>(u_i + P);     // [P] approximate d^2
     __shared__ int s_total, s_ok;
     __shared__ float s_taumin;
+    __shared__ double s_gqh;
     __shared__ unsigned s_dtil;
     __shared__ unsigned long long s_emin, s_emax;   // order-preserving encodings of the error range
+    __shared__ unsigned long long s_nmin, s_nmax;   // range of key - d~^2 over the candidates with an exact d~ (pure accumulation error)
 
     const long long q = blockIdx.x;
     const long long qf = a.fit_begin + q;
@@ -146,29 +157,46 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
     const double *cen_q = a.fit.cen + 4 * qf;
     load_fit_frame(wq, a.fit.raw + (size_t)qf * A * 3, cen_q, a.wnorm, A);
     const double gq = cen_q[3];
+    const int A_pad = a.fit.A_pad;
+    if (a.fit_part >= 0) {     // rounded fit row, atom-major like wq
+        const __half *fh = static_cast<const __half *>(a.fit.fh) + (size_t)qf * 3 * A_pad;
+        for (int i = threadIdx.x; i < 3 * A; i += blockDim.x) {
+            const int n = i / 3, d = i - 3 * n;
+            wqh[i] = (double)__half2float(fh[d * A_pad + n]) * (1.0 / kRmsHalfScale);
+        }
+    }
     const double kInfD = __longlong_as_double(0x7ff0000000000000LL);
     const float kInfF = __uint_as_float(0x7f800000u);
     const int k1 = a.k1;
 
     // ---- 0. gather + order by approximate key ---------------------------------------------------
-    if (threadIdx.x == 0) { s_total = 0; s_taumin = kInfF; s_ok = 0; s_emin = ~0ull; s_emax = 0ull; }
+    if (threadIdx.x == 0) { s_total = 0; s_taumin = kInfF; s_ok = 0; s_emin = ~0ull; s_emax = 0ull; s_nmin = ~0ull; s_nmax = 0ull; s_gqh = 0.0; }
     for (int i = threadIdx.x; i < P; i += blockDim.x) { s_d[i] = kInfD; s_i[i] = 0x7fffffff; }
+    __syncthreads();
+    // admission threshold of the row = the smallest of its lists' thresholds; entries above it carry no
+    // information (every pair outside the lists has key >= its list's tau >= tau_row)
+    if (threadIdx.x == 0) {
+        float t = kInfF;
+        for (int h = 0; h < a.cl.H; ++h) t = fminf(t, a.cl.tau[(size_t)q * a.cl.H + h]);
+        s_taumin = t;
+    }
     __syncthreads();
     for (int h = 0; h < a.cl.H; ++h) {
         const size_t lid = (size_t)q * a.cl.H + h;
         const int c = min(a.cl.cnt[lid], a.cl.keep);
-        if (threadIdx.x == 0) {
-            s_total += c;
-            s_taumin = fminf(s_taumin, a.cl.tau[lid]);
-        }
-        __syncthreads();
-        const int base = s_total - c;
         for (int i = threadIdx.x; i < c; i += blockDim.x) {
-            s_d[base + i] = (double)a.cl.key[lid * a.cl.cap + i];
-            s_i[base + i] = a.cl.idx[lid * a.cl.cap + i];
+            const float kv = a.cl.key[lid * a.cl.cap + i];
+            if (kv <= s_taumin) {
+                const int pos = atomicAdd(&s_total, 1);
+                if (pos < P) { s_d[pos] = (double)kv; s_i[pos] = a.cl.idx[lid * a.cl.cap + i]; }
+            }
         }
-        __syncthreads();
     }
+    __syncthreads();
+    const bool overflow = s_total > P;         // cannot happen unless H * keep > RESCORE_PMAX
+    __syncthreads();
+    if (threadIdx.x == 0 && overflow) s_total = 0;
+    __syncthreads();
     const int total = s_total;
     int Pr = 32;                       // this row's working size: the lists are mostly short
     while (Pr < total) Pr <<= 1;
@@ -200,6 +228,46 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
             if (lane < 9) s_S[c * 10 + lane] = tot[lane];
             if (lane == 9) s_S[c * 10 + 9] = a.ref.cen[4 * (size_t)r + 3];
         }
+        const bool rounded_round = a.fit_part >= 0 && done == 0;
+        if (rounded_round) {
+            // the same contraction between the ROUNDED structures (what the sweep's tensor cores multiplied), in FP64
+            for (int c = warp; c < min(nb, ROUNDED_EXACT); c += 4) {
+                const size_t rb = (size_t)u_i[c] * 3 * A_pad;
+                const __half *rh = static_cast<const __half *>(a.ref.fh) + rb;
+                const __half *rl = static_cast<const __half *>(a.ref.fl) + rb;
+                double tot[10];
+#pragma unroll
+                for (int e = 0; e < 10; ++e) tot[e] = 0.0;
+                for (int n = lane; n < A; n += 32) {
+                    double y0 = (double)__half2float(rh[n]), y1 = (double)__half2float(rh[A_pad + n]),
+                           y2 = (double)__half2float(rh[2 * A_pad + n]);
+                    if (a.ref_parts == 2) {
+                        y0 += (double)__half2float(rl[n]); y1 += (double)__half2float(rl[A_pad + n]);
+                        y2 += (double)__half2float(rl[2 * A_pad + n]);
+                    }
+                    y0 *= 1.0 / kRmsHalfScale; y1 *= 1.0 / kRmsHalfScale; y2 *= 1.0 / kRmsHalfScale;
+                    const double x0 = wqh[3 * n + 0], x1 = wqh[3 * n + 1], x2 = wqh[3 * n + 2];
+                    tot[0] += x0 * y0; tot[1] += x0 * y1; tot[2] += x0 * y2;
+                    tot[3] += x1 * y0; tot[4] += x1 * y1; tot[5] += x1 * y2;
+                    tot[6] += x2 * y0; tot[7] += x2 * y1; tot[8] += x2 * y2;
+                    tot[9] += y0 * y0 + y1 * y1 + y2 * y2;
+                }
+#pragma unroll
+                for (int e = 0; e < 10; ++e)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) tot[e] += __shfl_xor_sync(0xffffffffu, tot[e], o);
+                if (lane == 0)
+#pragma unroll
+                    for (int e = 0; e < 10; ++e) s_Sh[c * 10 + e] = tot[e];
+            }
+            if (warp == 0) {               // |x~|^2 of the fit row (one warp: deterministic order)
+                double gs = 0.0;
+                for (int i = lane; i < 3 * A; i += 32) gs += wqh[i] * wqh[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                if (lane == 0) s_gqh = gs;
+            }
+        }
         __syncthreads();
         if (threadIdx.x < nb) {
             const int c = threadIdx.x;
@@ -214,13 +282,23 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
             // bracket of the row-common bias given this candidate: [key - (d+g)^2, key - max(d-g,0)^2];
             // both ends are approx - exact when g = 0
             const double dn = sqrt(d2), dm = fmax(dn - grd, 0.0);
-            const double err_hi = (double)u_apx[done + c] - dm * dm;
-            const double err_lo = (double)u_apx[done + c] - (dn + grd) * (dn + grd);
+            double err_hi = (double)u_apx[done + c] - dm * dm;
+            double err_lo = (double)u_apx[done + c] - (dn + grd) * (dn + grd);
             // monotone map double -> u64 so that atomicMin/Max order like the doubles
             auto enc = [](double v) {
                 unsigned long long bits = (unsigned long long)__double_as_longlong(v);
                 return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
             };
+            if (rounded_round && c < ROUNDED_EXACT) {   // exact d~ of this candidate: its bracket is a point
+                double Sh[9];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) Sh[e] = s_Sh[c * 10 + e];
+                const double e0h = 0.5 * (s_gqh + s_Sh[c * 10 + 9]);
+                const double lamh = a.do_fit ? qcp_lambda_f64(Sh, e0h) : (Sh[0] + Sh[4] + Sh[8]);
+                err_hi = err_lo = (double)u_apx[done + c] - fmax(2.0 * (e0h - lamh), 0.0);
+                atomicMin(&s_nmin, enc(err_hi));
+                atomicMax(&s_nmax, enc(err_hi));
+            }
             atomicMin(&s_emin, enc(err_hi));
             atomicMax(&s_emax, enc(err_lo));
         }
@@ -283,7 +361,10 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
         if (total > 0) {
             const double lo = dec(s_emin), hi = dec(s_emax);
             atomic_max_nonneg(a.err_stats + 0, fmax(fabs(lo), fabs(hi)));
-            atomic_max_nonneg(a.err_stats + 1, fmax(hi - lo, 0.0));   // brackets may overlap (negative) when g > 0
+            // spread statistic: range of approx - exact; for the reduced FP16 sweeps the range of key - d~^2 over
+            // the candidates whose rounded-structure distance was computed (the accumulation error alone)
+            const double sp = a.fit_part >= 0 ? (s_nmax >= s_nmin ? dec(s_nmax) - dec(s_nmin) : 0.0) : hi - lo;
+            atomic_max_nonneg(a.err_stats + 1, fmax(sp, 0.0));
             atomic_max_nonneg(a.err_stats + 2, (double)done);
         }
         a.flags[q] = certified ? 1 : 0;
@@ -296,7 +377,8 @@ __global__ void __launch_bounds__(128) rms_rescore_kernel(RescoreArgs a)
 
 cudaError_t launch_rms_rescore(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                const FrameSetView &ref, const double *wnorm, int do_fit, CandLists<float> cl, int k1,
-                               double eps_scale, float g_ref_max, int fit_part, float gres_ref_max, double *out_dist,
+                               double eps_scale, float g_ref_max, int fit_part, int ref_parts, float gres_ref_max,
+                               double *out_dist,
                                int *out_idx, int *flags,
                                double *err_stats, int *n_bad, int *bad_rows, cudaStream_t st)
 {
@@ -304,13 +386,14 @@ cudaError_t launch_rms_rescore(const FrameSetView &fit, long long fit_begin, lon
     RescoreArgs a;
     a.fit = fit; a.ref = ref; a.fit_begin = fit_begin; a.n_fit = n_fit; a.wnorm = wnorm;
     a.do_fit = do_fit; a.k1 = k1; a.cl = cl; a.eps_scale = eps_scale; a.g_ref_max = g_ref_max;
-    a.fit_part = fit_part; a.gres_ref_max = gres_ref_max;
+    a.fit_part = fit_part; a.ref_parts = ref_parts; a.gres_ref_max = gres_ref_max;
     a.out_dist = out_dist; a.out_idx = out_idx; a.flags = flags; a.err_stats = err_stats; a.n_bad = n_bad;
     a.bad_rows = bad_rows;
     int P = 1;
-    while (P < cl.keep * cl.H) P <<= 1;
+    while (P < cl.keep * cl.H && P < RESCORE_PMAX) P <<= 1;
+    while (P < cl.keep) P <<= 1;           // one list alone must always fit
     a.P = P;
-    const size_t smem = (size_t)fit.A * 3 * 8 + (size_t)P * 28 + RESCORE_ROUND * 80;
+    const size_t smem = (size_t)fit.A * 3 * 16 + (size_t)P * 28 + (RESCORE_ROUND + ROUNDED_EXACT) * 80;
     cudaError_t e = cudaFuncSetAttribute(rms_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     rms_rescore_kernel<<<(unsigned)n_fit, 128, smem, st>>>(a);

@@ -324,7 +324,7 @@ def main():
                 6: "rms_sweep_tc_kernel<6> (tcgen05 cta_group::2 kind::f16, 1xFP16 contraction + QCP bounds + streaming top-k; "
                    "FP64 re-score with the rounded-structure triangle bound)"}[st["rms_kernel"]]
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_r01c.json")
+        tp = os.path.join(ROOT, "profiles", "traffic_r01d.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(str(st["rms_kernel"]))
         line = {

@@ -41,14 +41,14 @@ struct DevBuf {
 };
 
 struct FrameSet {
-    DevBuf raw, planes, hi, lo, bh, bm, fh, fl, G, cen, Gh, G2, gres;
+    DevBuf raw, planes, hi, lo, bh, bm, fh, fl, G, cen, Gh, G2, gres, sig;
     long long n = 0;
     int A = 0, A_pad = 0;
     FrameSetView view() const
     {
         FrameSetView v;
         v.raw = raw.as<float>(); v.planes = planes.as<float>(); v.G = G.as<float>(); v.cen = cen.as<double>();
-        v.Gh = Gh.as<float>(); v.G2 = G2.as<float>(); v.gres = gres.as<float>(); v.fh = fh.p; v.fl = fl.p;
+        v.Gh = Gh.as<float>(); v.G2 = G2.as<float>(); v.gres = gres.as<float>(); v.fh = fh.p; v.fl = fl.p; v.sig = sig.as<float>();
         v.n = n; v.A = A; v.A_pad = A_pad;
         return v;
     }
@@ -68,12 +68,16 @@ struct FrameSet {
         if ((e = Gh.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;
         if ((e = G2.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;
         if ((e = gres.reserve((size_t)n * 8)) != cudaSuccess) return e;
+        if (sig.bytes < (size_t)(n + 64) * 16) {     // read in 48-frame tiles: the padding must be zero, not garbage
+            if ((e = sig.reserve((size_t)(n + 64) * 16)) != cudaSuccess) return e;
+            if ((e = cudaMemset(sig.p, 0, (size_t)(n + 64) * 16)) != cudaSuccess) return e;
+        }
         return cen.reserve((size_t)n * 32);
     }
     void release()
     {
         raw.release(); planes.release(); hi.release(); lo.release(); bh.release(); bm.release(); fh.release(); fl.release(); G.release();
-        cen.release(); Gh.release(); G2.release(); gres.release(); n = 0;
+        cen.release(); Gh.release(); G2.release(); gres.release(); sig.release(); n = 0;
     }
 };
 
@@ -198,7 +202,7 @@ int pack_into(mdsctk_knn_ctx *ctx, FrameSet &fs, const float *xyz, long long off
                           fs.fh.as<uint16_t>() + (size_t)off * 3 * fs.A_pad, fs.fl.as<uint16_t>() + (size_t)off * 3 * fs.A_pad,
                           fs.G.as<float>() + off,
                           fs.cen.as<double>() + 4 * off, fs.Gh.as<float>() + off, fs.G2.as<float>() + off,
-                          fs.gres.as<float>() + 2 * off, ctx->st), "pack_frames");
+                          fs.gres.as<float>() + 2 * off, fs.sig.as<float>() + 4 * off, ctx->st), "pack_frames");
     ctx->stats.ms_pack += ctx->tm.stop(ctx->st);
     return 0;
 }
@@ -320,7 +324,7 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
                     return fail(ctx, MDSCTK_KNN_EINVAL, "coordinates too large for the fp16 kernels; use rms_kernel=1 (3xTF32)");
             }
             CK(launch_rms_sweep_tc(rms_kernel, fit, q_hi, q_lo, fit_begin, n_fit, ref, r_hi, r_lo, do_fit, n_seg, cl,
-                                   ctx->row_tau.as<float>(),
+                                   ctx->row_tau.as<float>(), ctx->g_ref_max,
                                    ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
                "rms_sweep_tc");
         }
@@ -706,8 +710,8 @@ int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_
 {
     if (!ctx || !n_arrays) return MDSCTK_KNN_EINVAL;
     if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
-    *n_arrays = 13;
-    if (max_arrays < 13 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 13 arrays");
+    *n_arrays = 14;
+    if (max_arrays < 14 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 14 arrays");
     dev_ptrs[0] = ctx->ref.raw.p;    bytes_per_frame[0] = (size_t)ctx->ref.A * 12;
     dev_ptrs[1] = ctx->ref.planes.p; bytes_per_frame[1] = (size_t)ctx->ref.A_pad * 12;
     dev_ptrs[2] = ctx->ref.G.p;      bytes_per_frame[2] = 4;
@@ -721,6 +725,7 @@ int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_
     dev_ptrs[10] = ctx->ref.Gh.p;    bytes_per_frame[10] = 4;
     dev_ptrs[11] = ctx->ref.G2.p;    bytes_per_frame[11] = 4;
     dev_ptrs[12] = ctx->ref.gres.p;  bytes_per_frame[12] = 8;
+    dev_ptrs[13] = ctx->ref.sig.p;   bytes_per_frame[13] = 16;
     ctx->gmax_dirty = true;  // the caller is about to overwrite them (all-gather)
     return 0;
 }

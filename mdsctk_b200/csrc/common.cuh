@@ -12,6 +12,8 @@
 //   Gh, G2 float  [n] (+64 pad)    |fh/64|^2 and |(fh+fl)/64|^2: norms of the ROUNDED structures the
 //                                  1xFP16 / 2xFP16 sweeps contract (their E0 uses these, not G)
 //   gres   float  [n][2]           residual norms |x - fh/64|, |x - (fh+fl)/64| in nm, rounded up
+//   sig    float  [n][4] (+64 pad) singular values of the weighted frame matrix, descending (+ one unused lane):
+//                                  RMSD^2(x,y) >= sum_i (sig_i(x) - sig_i(y))^2, tested before the accumulators are read
 //   cen    double [n][4]           mass-weighted centroid (x,y,z) and G in FP64
 // With the weights normalised to sum 1, min-RMSD^2 = G_q + G_r - 2*lambda_max (nm^2).
 #pragma once
@@ -31,6 +33,7 @@ struct FrameSetView {
     const float *G;       // [n]
     const float *Gh, *G2; // [n]     norms of the fp16-rounded structures (1 part / 2 parts)
     const float *gres;    // [n][2]  their distance from the true structure
+    const float *sig;     // [n][4]  singular values of the weighted frame (descending) + 0: von Neumann pre-bound
     const void *fh, *fl;  // fp16 [n][3][A_pad]  the rounded operand planes themselves (64 * sqrt(w) (x - c), hi / lo part)
     const double *cen;    // [n][4]
     long long n;
@@ -56,7 +59,7 @@ struct CandLists {
 // ---- launch wrappers (defined in the .cu files) -----------------------------------
 cudaError_t launch_pack_frames(const float *raw, const double *mass_norm, long long n, int A, int A_pad,
                                float *planes, float *hi, float *lo, void *bh, void *bm, void *fh, void *fl, float *G,
-                               double *cen, float *Gh, float *G2, float *gres, cudaStream_t st);
+                               double *cen, float *Gh, float *G2, float *gres, float *sig, cudaStream_t st);
 
 cudaError_t launch_rms_sweep_simt(const FrameSetView &fit, long long fit_begin, long long n_fit,
                                   const FrameSetView &ref, int do_fit, CandLists<float> cl, cudaStream_t st);
@@ -68,7 +71,7 @@ cudaError_t launch_rms_sweep_simt(const FrameSetView &fit, long long fit_begin, 
 cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *fit_hi, const void *fit_lo,
                                 long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,
                                 const void *ref_lo, int do_fit, int n_seg, CandLists<float> cl, float *row_tau,
-                                float *debug_tile, int n_sms, cudaStream_t st);
+                                float g_ref_max, float *debug_tile, int n_sms, cudaStream_t st);
 int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms);
 int rms_tc_lists_per_segment();
 int rms_tc_list_stride(int keep);

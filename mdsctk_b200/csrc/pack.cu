@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
                                                           __nv_bfloat16 *__restrict__ bm, __half *__restrict__ fh,
                                                           __half *__restrict__ fl, float *__restrict__ G,
                                                           double *__restrict__ cen, float *__restrict__ Gh,
-                                                          float *__restrict__ G2, float2 *__restrict__ gres)
+                                                          float *__restrict__ G2, float2 *__restrict__ gres,
+                                                          float4 *__restrict__ sig)
 {
     const int lane = threadIdx.x & 31;
     const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
     float *px = planes + pbase;
     float *py = px + A_pad, *pz = py + A_pad;
     double g = 0.0, gh = 0.0, g2n = 0.0, r1 = 0.0, r2 = 0.0;
+    double t00 = 0.0, t01 = 0.0, t02 = 0.0, t11 = 0.0, t12 = 0.0, t22 = 0.0;   // gyration tensor of the weighted frame
     for (int a = lane; a < A_pad; a += 32) {
         float ox = 0.0f, oy = 0.0f, oz = 0.0f;
         double tx = 0.0, ty = 0.0, tz = 0.0;      // the FP64 operand sqrt(w) (x - c)
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
             const double s = sqrt(w);
             tx = s * dx; ty = s * dy; tz = s * dz;
             ox = (float)tx; oy = (float)ty; oz = (float)tz;
+            t00 += tx * tx; t01 += tx * ty; t02 += tx * tz; t11 += ty * ty; t12 += ty * tz; t22 += tz * tz;
         }
         px[a] = ox; py[a] = oy; pz[a] = oz;
         if (hi) {  // 3xTF32 operand split for the tensor-core sweep: x ~= hi + lo, both exact TF32 values
@@ -107,6 +110,9 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
         g2n += __shfl_xor_sync(0xffffffffu, g2n, o);
         r1 += __shfl_xor_sync(0xffffffffu, r1, o);
         r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        t00 += __shfl_xor_sync(0xffffffffu, t00, o); t01 += __shfl_xor_sync(0xffffffffu, t01, o);
+        t02 += __shfl_xor_sync(0xffffffffu, t02, o); t11 += __shfl_xor_sync(0xffffffffu, t11, o);
+        t12 += __shfl_xor_sync(0xffffffffu, t12, o); t22 += __shfl_xor_sync(0xffffffffu, t22, o);
     }
     if (lane == 0) {
         if (Gh) {
@@ -115,6 +121,31 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
             // residual norms rounded up: they are subtracted from lower bounds
             gres[f] = make_float2(__double2float_ru(sqrt(r1)), __double2float_ru(sqrt(r2)));
         }
+        if (sig) {
+            // singular values of the 3 x A frame matrix = sqrt of the eigenvalues of its gyration tensor (closed form
+            // for a symmetric 3x3, FP64).  min-RMSD^2(x, y) >= sum_i (sigma_i(x) - sigma_i(y))^2 by von Neumann's
+            // trace inequality: the sweep's cheapest test, applied before the accumulators are even read.
+            const double q = (t00 + t11 + t22) / 3.0;
+            const double p1 = t01 * t01 + t02 * t02 + t12 * t12;
+            const double p2 = (t00 - q) * (t00 - q) + (t11 - q) * (t11 - q) + (t22 - q) * (t22 - q) + 2.0 * p1;
+            double e1 = t00, e2 = t11, e3 = t22;
+            if (p2 > 0.0) {
+                const double p = sqrt(p2 / 6.0), ip = 1.0 / p;
+                const double b00 = (t00 - q) * ip, b11 = (t11 - q) * ip, b22 = (t22 - q) * ip;
+                const double b01 = t01 * ip, b02 = t02 * ip, b12 = t12 * ip;
+                double r = 0.5 * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+                r = fmin(1.0, fmax(-1.0, r));
+                const double phi = acos(r) / 3.0;
+                e1 = q + 2.0 * p * cos(phi);
+                e3 = q + 2.0 * p * cos(phi + 2.0943951023931953);
+                e2 = 3.0 * q - e1 - e3;
+            }
+            // descending order (the closed form gives e1 >= e2 >= e3; the diagonal case may not)
+            if (e1 < e2) { const double t = e1; e1 = e2; e2 = t; }
+            if (e2 < e3) { const double t = e2; e2 = e3; e3 = t; }
+            if (e1 < e2) { const double t = e1; e1 = e2; e2 = t; }
+            sig[f] = make_float4((float)sqrt(fmax(e1, 0.0)), (float)sqrt(fmax(e2, 0.0)), (float)sqrt(fmax(e3, 0.0)), 0.0f);
+        }
         G[f] = (float)g;
         cen[4 * f + 0] = cx; cen[4 * f + 1] = cy; cen[4 * f + 2] = cz; cen[4 * f + 3] = g;
     }
@@ -122,7 +153,7 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
 
 cudaError_t launch_pack_frames(const float *raw, const double *wnorm, long long n, int A, int A_pad, float *planes,
                                float *hi, float *lo, void *bh, void *bm, void *fh, void *fl, float *G, double *cen, float *Gh, float *G2,
-                               float *gres, cudaStream_t st)
+                               float *gres, float *sig, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
     const int warps = 8;
@@ -130,7 +161,7 @@ cudaError_t launch_pack_frames(const float *raw, const double *wnorm, long long 
     pack_frames_kernel<<<grid, warps * 32, 0, st>>>(raw, wnorm, n, A, A_pad, planes, hi, lo, static_cast<__nv_bfloat16 *>(bh),
                                                     static_cast<__nv_bfloat16 *>(bm), static_cast<__half *>(fh),
                                                     static_cast<__half *>(fl), G, cen, Gh, G2,
-                                                    reinterpret_cast<float2 *>(gres));
+                                                    reinterpret_cast<float2 *>(gres), reinterpret_cast<float4 *>(sig));
     return cudaGetLastError();
 }
 

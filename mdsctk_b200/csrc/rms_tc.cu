@@ -105,6 +105,8 @@ struct TcArgs {
     CandLists<float> cl;        // H = n_seg lists per fit row
     float *debug_tile;          // optional [128][9][48]: raw accumulators of (fit tile 0, ref tile 0)
     float *row_tau;             // [n_q] running admission threshold per fit row (+inf before the first segment)
+    const float4 *q_sig, *r_sig;   // singular values of the weighted frames (pack.cu): von Neumann pre-bound
+    float pre_rel, pre_sqrt_gmax;  // operand rounding allowance of the pre-bound: g <= pre_rel (sqrt(Gq) + sqrt(max Gr)); < 0: off
     int res, res_nst;           // resident fit planes (1xFP16): on/off, ring stages that fit beside them
     int dbg;                    // MDSCTK_TC_DEBUG bits: 1 skip QCP, 2 skip MMA issue, 4 skip TMA, 8 no cheap bound
     long long *prof;            // MDSCTK_TC_PROF=1: [grid][8] clock sums (see launch_rms_sweep_tc)
@@ -114,6 +116,7 @@ struct TcArgs {
 // (E0, thresholds, Newton iterates) is kept in units of SCALE nm^2 and converted when a candidate
 // is stored.
 template <int MODE>
+// 96 registers: 576 threads x 112 is refused at launch ("too many resources") although it is below 64 K
 __global__ void __launch_bounds__(tc::NTHR, 1)
 rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                     const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
@@ -231,7 +234,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             for (long long ti = 0; ti < rt1 - rt0; ++ti) {
                 const int r0 = (int)(tile_at(ti, rt0, rt1, rot) * TR + rank * TRH);
                 for (int kc = 0; kc < nk; ++kc) {
-                    mbar_wait(&bar_empty[s], ph ^ 1, 1);             // the pair's MMAs have read stage s (both CTAs)
+                    if (a.dbg & 4096) mbar_wait_spin(&bar_empty[s], ph ^ 1, 1); else mbar_wait(&bar_empty[s], ph ^ 1, 1);   // the pair's MMAs have read stage s (both CTAs)
                     unsigned char *st = smem + ring_off + s * stage_bytes;
                     const uint32_t full_leader = map_to_cta(&bar_full[s], 0);
                     if (elect_one()) {
@@ -370,7 +373,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         int *wcnt = s_cnt[ew];                        // fill of this warp's append area of row (quarter*32 + l)
         const size_t row_stride = (size_t)a.cl.H * a.cl.cap;
         uint32_t tph = 0;
-        long long t_wait_tmem = 0, t_hold = 0, t_post = 0, t_merge = 0;
+        long long t_wait_tmem = 0, t_hold = 0, t_post = 0, t_merge = 0, n_live = 0;
         int qn = 0;                                   // queue fill (warp-uniform)
         size_t lbase0 = 0;                            // list of the quarter's row 0 in the current item
         float *lkeys = a.cl.key;
@@ -474,6 +477,16 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             const bool qvalid = qrow < a.n_q;
             const float hgq = (0.5f * SC) * a.q_G[a.q_begin + (qvalid ? qrow : a.n_q - 1)];   // accumulator units
             lbase0 = ((size_t)(row0 + quarter * 32) * a.cl.H + seg) * a.cl.cap;
+            // pre-bound (nm units): RMSD >= |sigma(x) - sigma(y)|_2 - g, g = rounding residuals of what the sweep contracts
+            // The warp's 32 fit rows are consecutive frames: their singular values span a small box, and the largest
+            // rounding allowance / G of the 32 serve all of them, so ONE lane can test a reference frame for the warp.
+            const float4 sq = __ldg(a.q_sig + a.q_begin + (qvalid ? qrow : a.n_q - 1));
+            const float gq_nm = 2.0f * INV_SC * hgq;
+            auto wmax = [](float v) { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v))); };   // v >= 0
+            auto wmin = [](float v) { return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v))); };
+            const float bx0 = wmin(sq.x), bx1 = wmax(sq.x), by0 = wmin(sq.y), by1 = wmax(sq.y), bz0 = wmin(sq.z), bz1 = wmax(sq.z);
+            const float gq_max = wmax(gq_nm);
+            const float pre_g = a.pre_rel * (sqrtf(gq_max) + a.pre_sqrt_gmax) + 1e-6f;
             wcnt[lane] = 0;
             if (sub == 0) {
                 s_mcnt[row_in_tile] = 0;
@@ -481,12 +494,43 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 s_tau[row_in_tile] = qvalid ? __ldcg(a.row_tau + qrow) : 0.0f;
             }
             quarter_sync(quarter);
+            // per-reference scalars of a pass (G and the singular values of the warp's 12 frames): lane l < 12 fetches
+            // those of frame l one pass AHEAD, the warp broadcasts them by shuffle -- twelve dependent-latency
+            // broadcast loads per pass and lane cost more than the whole TMEM drain when registers are short
+            float4 nx_sig = make_float4(0.f, 0.f, 0.f, 0.f);
+            float nx_g = 0.f;
+            auto fetch_refs = [&](long long ti2) {
+                const long long rb2 = tile_at(ti2, rt0, rt1, rot) * TR + sub * SUBW;
+                if (lane < SUBW) { nx_sig = __ldg(a.r_sig + rb2 + lane); nx_g = __ldg(a.r_G + rb2 + lane); }
+            };
+            fetch_refs(0);
             for (long long ti = 0; ti < rt1 - rt0; ++ti) {
                 const long long rt = tile_at(ti, rt0, rt1, rot);
                 const long long rb = rt * TR + sub * SUBW;       // first reference frame of this warp's columns
-                float4 gv[SUBW / 4];
+                const float4 cs = nx_sig;
+                const float cg = nx_g;
+                if (ti + 1 < rt1 - rt0) fetch_refs(ti + 1);
+                // Cheapest test first, while the MMAs of this pass still run: min-RMSD^2 >= sum_i (sigma_i(x) - sigma_i(y))^2
+                // (von Neumann).  Lane l < 12 tests reference frame l against the box of the warp's rows and the
+                // largest threshold among them; a batch whose frames all fail is not even read from TMEM -- for
+                // frames of another conformational basin that is nearly every batch, and the hold shrinks to the
+                // hand-back.
+                unsigned live = (1u << (SUBW / EB)) - 1u;          // batches whose accumulators must be read
+                if (a.pre_rel >= 0.0f && a.do_fit) {
+                    const float tau_max = wmax(*reinterpret_cast<volatile float *>(&s_tau[row_in_tile]));   // only decreases: stale is safe
+                    const float d0 = fmaxf(fmaxf(bx0 - cs.x, cs.x - bx1), 0.0f), d1 = fmaxf(fmaxf(by0 - cs.y, cs.y - by1), 0.0f),
+                                d2 = fmaxf(fmaxf(bz0 - cs.z, cs.z - bz1), 0.0f);
+                    const float lb = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2))) - pre_g;
+                    // key = rounded-structure RMSD^2 + accumulation bias/noise (< 2e-5 E0): keep clear of it
+                    const bool far = lane >= SUBW || (lb > 0.0f && lb * lb > tau_max + 2e-5f * (gq_max + cg));
+                    const unsigned near = ~__ballot_sync(0xffffffffu, far);      // bit l: frame l may hold a neighbour
+                    live = 0;
 #pragma unroll
-                for (int j = 0; j < SUBW / 4; ++j) gv[j] = __ldg(reinterpret_cast<const float4 *>(a.r_G + min(rb, a.n_r & ~3LL)) + j);
+                    for (int hb = 0; hb < SUBW / EB; ++hb)
+                        if (near & (((1u << EB) - 1u) << (hb * EB))) live |= 1u << hb;
+                    if (a.dbg & 1024) live = (1u << (SUBW / EB)) - 1u;
+                }
+                if (MDSCTK_TC_PROF_BUILD && a.prof) n_live += __popc(live);
                 const long long tp0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                 if (lane == 0) { if (a.dbg & 128) mbar_wait_spin(&bar_tmem_full, tph, 4); else mbar_wait(&bar_tmem_full, tph, 4); }
                 tph ^= 1;
@@ -496,8 +540,6 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 long long tp2 = tp1;
                 const float tau = SC * *reinterpret_cast<volatile float *>(&s_tau[row_in_tile]);   // accumulator units
                 const float htau = 0.5f * tau;
-                const float ge[SUBW] = {gv[0].x, gv[0].y, gv[0].z, gv[0].w, gv[1].x, gv[1].y, gv[1].z, gv[1].w,
-                                        gv[2].x, gv[2].y, gv[2].z, gv[2].w};
                 // Software-pipelined drain: the tcgen05.ld of batch hb+1 are issued before the arithmetic of batch
                 // hb, so the TMEM read port (the floor of the hold: 128 lanes x 432 columns per pass) stays busy.
                 float svb[2][9][EB];
@@ -508,20 +550,26 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                         for (int b = 0; b < 3; ++b)
                             tc_ld2(t_warp + p * UMMA_N + b * TRH + h, dst, p * 3 + b);
                 };
-                load_batch(0, svb[0]);
+                bool released = false;
+                auto release = [&]() {                // hand the accumulators back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (a.dbg & 512) mbar_arrive_cluster(empty_leader); else if (a.dbg & 16384) mbar_arrive_cluster_relaxed(empty_leader); else mbar_arrive_cluster_nofence(empty_leader); }
+                    if (MDSCTK_TC_PROF_BUILD && a.prof) tp2 = clock64();
+                    released = true;
+                };
+                if (a.debug_tile) live = (1u << (SUBW / EB)) - 1u;
+                if (live == 0) release();
+                if (live & 1u) load_batch(0, svb[0]);
 #pragma unroll
                 for (int hb = 0; hb < SUBW / EB; ++hb) {
                     const int h = hb * EB;
                     float (&sv)[9][EB] = svb[hb & 1];
-                    tc_wait_ld();
-                    if (hb + 1 < SUBW / EB) {
-                        load_batch(h + EB, svb[(hb + 1) & 1]);
-                    } else {                          // last TMEM read of this pass: hand the accumulators back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) { if (a.dbg & 512) mbar_arrive_cluster(empty_leader); else mbar_arrive_cluster_nofence(empty_leader); }
-                        if (MDSCTK_TC_PROF_BUILD && a.prof) tp2 = clock64();
-                    }
+                    const bool cur = (live >> hb) & 1u;
+                    if (cur) tc_wait_ld();
+                    if (hb + 1 < SUBW / EB && ((live >> (hb + 1)) & 1u)) load_batch(h + EB, svb[(hb + 1) & 1]);
+                    if (!released && (live >> (hb + 1)) == 0) release();     // last TMEM read of this pass is complete
+                    if (!cur) continue;
                     if (a.debug_tile && it == 0 && rt == 0 && rank == 0) {
 #pragma unroll
                         for (int c = 0; c < 9; ++c)
@@ -531,7 +579,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     }
                     float e0[EB];
 #pragma unroll
-                    for (int j = 0; j < EB; ++j) e0[j] = fmaf(0.5f * SC, ge[h + j], hgq);
+                    for (int j = 0; j < EB; ++j) e0[j] = fmaf(0.5f * SC, __shfl_sync(0xffffffffu, cg, h + j), hgq);
                     if (a.dbg & 1) {
                         float acc = 0.f;
 #pragma unroll
@@ -589,7 +637,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         }
         if (MDSCTK_TC_PROF_BUILD && a.prof && ew == 0 && lane == 0) {
             long long *pr = a.prof + (size_t)blockIdx.x * 8 + 4;
-            pr[0] = t_wait_tmem; pr[1] = t_hold; pr[2] = t_post; pr[3] = t_merge;
+            pr[0] = t_wait_tmem; pr[1] = t_hold; pr[2] = t_post; pr[3] = (a.dbg & 8192) ? n_live : t_merge;   // dbg 8192: live batches instead of merge clocks
         }
     }
 
@@ -687,7 +735,7 @@ static cudaError_t launch_tc_mode(const CUtensorMap &mq_hi, const CUtensorMap &m
 cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *fit_hi, const void *fit_lo,
                                 long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,
                                 const void *ref_lo, int do_fit, int n_seg, CandLists<float> cl, float *row_tau,
-                                float *debug_tile, int n_sms, cudaStream_t st)
+                                float g_ref_max, float *debug_tile, int n_sms, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
     if (cl.H != n_seg || cl.cap < cl.keep + tc::SUBS * tc::SUB_APP) return cudaErrorInvalidValue;
@@ -713,6 +761,12 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
     a.A_pad = ref.A_pad; a.do_fit = do_fit; a.n_seg = n_seg; a.cl = cl; a.debug_tile = debug_tile; a.row_tau = row_tau;
     a.dbg = dbg_bits;
     a.res = res_nst > 0; a.res_nst = res_nst;
+    // pre-bound: relative rounding error of one operand of this mode (what ties the contracted structures to the
+    // true ones): tf32/fp16 hi only 2^-11, bf16 hi+mid 2^-16, two-part splits 2^-20; MDSCTK_TC_DEBUG bit 2048: off
+    static const float kPreRel[7] = {0.f, 1.0e-6f, 4.9e-4f, 1.6e-5f, 1.0e-6f, 4.9e-4f, 4.9e-4f};
+    a.q_sig = reinterpret_cast<const float4 *>(fit.sig); a.r_sig = reinterpret_cast<const float4 *>(ref.sig);
+    a.pre_rel = (dbg_bits & 2048) ? -1.0f : kPreRel[mode];
+    a.pre_sqrt_gmax = sqrtf(g_ref_max > 0.f ? g_ref_max : 0.f);
     // MDSCTK_TC_PROF=1: per-CTA clock sums {MMA warp: total, wait tmem_empty, wait full, passes |
     // epilogue warp 0: wait tmem_full, TMEM hold, post-release compute, merges}, printed to stderr
     static long long *d_prof = nullptr;

@@ -116,6 +116,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr)
 // tcgen05.wait::ld + tcgen05.fence::before_thread_sync, no global/shared data is published, so the
 // arrive needs no cluster-scope release fence (measured: the MEMBAR of the .release.cluster form was 11 % of
 // the epilogue's stall samples, on the critical path of every pass).  Same form as cutlass ClusterBarrier::arrive.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster_addr)
+{
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster_nofence(uint32_t bar_cluster_addr)
 {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");

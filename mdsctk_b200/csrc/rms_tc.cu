@@ -66,7 +66,7 @@ constexpr int UMMA_N = 3 * TR;                // 144
 constexpr int A_TILE = TQ * ROW_BYTES;        // 8192 B : one plane of the CTA's fit tile
 constexpr int A_PART = 3 * A_TILE;            // 24576 B: x|y|z planes of one split part
 constexpr int B_PART = 3 * TRH * ROW_BYTES;   // 4608 B : this CTA's 72 of the 144 reference operand rows
-constexpr int MAX_NST = 6;
+constexpr int MAX_NST = 8;
 constexpr int RES_CHUNK = 2 * A_TILE;         // 16384 B: resident y|z planes of one 32-atom chunk (fp16)
 constexpr int RES_STAGE = A_TILE + B_PART;    // 12800 B: ring stage in resident mode (fit x plane + reference half-tile)
 constexpr int RES_MAX_NK = 11;                // resident chunks that still leave room for a 2-stage ring

@@ -122,7 +122,9 @@ int mdsctk_knn_rms_query(mdsctk_knn_ctx *ctx, const float *fit_xyz, long long n_
  *   1. mdsctk_knn_rms_alloc_reference(n_total)          on every rank
  *   2. mdsctk_knn_rms_pack_shard(own frames, offset)    each rank packs ITS frames on ITS GPU
  *   3. all-gather the arrays listed by mdsctk_knn_rms_reference_arrays over NCCL
- *      (each is frame-major, bytes_per_frame[i] bytes per frame, n_total frames)
+ *      (each is frame-major, bytes_per_frame[i] bytes per frame, n_total frames; 14 arrays today --
+ *      raw, planes, G, cen, the TF32 / BF16 / FP16 operand splits, and the per-frame scalars of the
+ *      1xFP16 sweep: rounded norms, rounding residuals, singular values -- pass max_arrays >= 16)
  *   4. mdsctk_knn_rms_query_range(begin, n)             fit rows = reference rows [begin, begin+n) */
 int mdsctk_knn_rms_alloc_reference(mdsctk_knn_ctx *ctx, long long n_total, int n_atoms, const float *mass);
 int mdsctk_knn_rms_pack_shard(mdsctk_knn_ctx *ctx, const float *xyz, long long frame_offset, long long n_frames);

@@ -137,7 +137,7 @@ struct mdsctk_knn_ctx {
     long long c_nnz = -1;
     // scratch + results
     DevBuf cand_key, cand_idx, cand_cnt, cand_tau, flags, bad_rows, scalars, rows_buf;
-    DevBuf out_dist, out_idx, debug_tile, row_tau;
+    DevBuf out_dist, out_idx, debug_tile, row_tau, own_tile;
     bool debug_tile_on = false;
     int n_sms = 148;
     long long out_rows = 0;
@@ -312,6 +312,8 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
         if (ctx->debug_tile_on) CK(ctx->debug_tile.reserve(128 * 432 * 4), "cudaMalloc(debug_tile)");
         CK(ctx->row_tau.reserve((size_t)n_fit * 4), "cudaMalloc(row_tau)");
         CK(launch_fill_u32(ctx->row_tau.p, (size_t)n_fit, 0x7f800000u, ctx->st), "fill row_tau");  // +inf
+        const bool oos = &fitset != &ctx->ref;      // out-of-sample: the fit rows are not reference frames
+        if (oos) CK(ctx->own_tile.reserve((size_t)((n_fit + 255) / 256) * 4), "cudaMalloc(own_tile)");
         {
             const void *q_hi = fitset.hi.p, *q_lo = fitset.lo.p, *r_hi = ctx->ref.hi.p, *r_lo = ctx->ref.lo.p;
             if (rms_kernel == MDSCTK_KNN_RMS_TC_3XBF16) {
@@ -324,7 +326,7 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
                     return fail(ctx, MDSCTK_KNN_EINVAL, "coordinates too large for the fp16 kernels; use rms_kernel=1 (3xTF32)");
             }
             CK(launch_rms_sweep_tc(rms_kernel, fit, q_hi, q_lo, fit_begin, n_fit, ref, r_hi, r_lo, do_fit, n_seg, cl,
-                                   ctx->row_tau.as<float>(), ctx->g_ref_max,
+                                   ctx->row_tau.as<float>(), ctx->g_ref_max, oos ? ctx->own_tile.as<int>() : nullptr,
                                    ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
                "rms_sweep_tc");
         }
@@ -636,7 +638,7 @@ void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx)
     ctx->d_ref.release(); ctx->d_fit.release(); ctx->d_ref_stats.release(); ctx->d_fit_stats.release();
     ctx->cand_key.release(); ctx->cand_idx.release(); ctx->cand_cnt.release(); ctx->cand_tau.release();
     ctx->flags.release(); ctx->bad_rows.release(); ctx->scalars.release(); ctx->rows_buf.release();
-    ctx->out_dist.release(); ctx->out_idx.release(); ctx->debug_tile.release(); ctx->row_tau.release();
+    ctx->out_dist.release(); ctx->out_idx.release(); ctx->debug_tile.release(); ctx->row_tau.release(); ctx->own_tile.release();
     ctx->tm.destroy();
     ctx->user_tm.destroy();
     cudaStreamDestroy(ctx->st);

@@ -68,10 +68,11 @@ cudaError_t launch_rms_sweep_simt(const FrameSetView &fit, long long fit_begin, 
 // mode: 1 = 3xTF32 (hi/lo fp32 planes), 2 = 1xTF32 (hi only), 3 = 3xBF16 (bh/bm bf16 planes),
 //       4 = 3xFP16 (fh/fl), 5 = 2xFP16 (fit fh only, reference fh/fl), 6 = 1xFP16 (fh only).
 // cl.H must be rms_tc_lists_per_segment() * n_seg (reference segments x column groups).
+// own_tile_scratch: NULL when the fit rows are reference frames fit_begin..; else device ints, one per 256 fit rows.
 cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *fit_hi, const void *fit_lo,
                                 long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,
                                 const void *ref_lo, int do_fit, int n_seg, CandLists<float> cl, float *row_tau,
-                                float g_ref_max, float *debug_tile, int n_sms, cudaStream_t st);
+                                float g_ref_max, int *own_tile_scratch, float *debug_tile, int n_sms, cudaStream_t st);
 int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms);
 int rms_tc_lists_per_segment();
 int rms_tc_list_stride(int keep);

@@ -107,6 +107,7 @@ struct TcArgs {
     float *row_tau;             // [n_q] running admission threshold per fit row (+inf before the first segment)
     const float4 *q_sig, *r_sig;   // singular values of the weighted frames (pack.cu): von Neumann pre-bound
     float pre_rel, pre_sqrt_gmax;  // operand rounding allowance of the pre-bound: g <= pre_rel (sqrt(Gq) + sqrt(max Gr)); < 0: off
+    const int *own_tile;        // out-of-sample queries: per fit super-tile, the reference tile to start from (else NULL)
     int res, res_nst;           // resident fit planes (1xFP16): on/off, ring stages that fit beside them
     int dbg;                    // MDSCTK_TC_DEBUG bits: 1 skip QCP, 2 skip MMA issue, 4 skip TMA, 8 no cheap bound
     long long *prof;            // MDSCTK_TC_PROF=1: [grid][8] clock sums (see launch_rms_sweep_tc)
@@ -187,7 +188,9 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         int s_rest = -1;
         if (it < n_qt) qt = it;
         else { s_rest = (int)((it - n_qt) / n_qt); qt = (it - n_qt) - (long long)s_rest * n_qt; }
-        const long long own = min((a.q_begin + qt * UMMA_M) / TR, n_rt - 1);     // reference tile of the first fit frame
+        // reference tile of the first fit frame (fit rows that ARE reference frames), else the guess of
+        // rms_guess_own_tile_kernel
+        const long long own = min(a.own_tile ? (long long)a.own_tile[qt] : (a.q_begin + qt * UMMA_M) / TR, n_rt - 1);
         int sd = (int)(own * a.n_seg / n_rt);
         while (sd + 1 < a.n_seg && n_rt * (sd + 1) / a.n_seg <= own) ++sd;
         while (sd > 0 && n_rt * sd / a.n_seg > own) --sd;
@@ -651,6 +654,60 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     }
 }
 
+// Out-of-sample queries (knn_rms -f): the fit rows are not reference frames, so "start at the row's own tile" has
+// no meaning -- but the frames that can be near a fit frame have nearly its singular values (the von Neumann bound
+// again), so every fit super-tile starts at the reference tile whose mid frame is closest to the super-tile's mean
+// in singular-value space.  Trajectory frames of one conformational basin are contiguous, so the admission
+// thresholds are tight after a few passes, as in the in-sample order.  One block per super-tile.
+__global__ void __launch_bounds__(256) rms_guess_own_tile_kernel(const float4 *q_sig, long long q_begin, long long n_q,
+                                                                 const float4 *r_sig, long long n_r, int *own_tile)
+{
+    __shared__ float s_sum[3][8];
+    __shared__ float s_best[8];
+    __shared__ int s_arg[8], s_cnt[8];
+    const long long qt = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long row = qt * tc::UMMA_M + tid;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int have = 0;
+    if (row < n_q) { v = q_sig[q_begin + row]; have = 1; }
+    float sx = v.x, sy = v.y, sz = v.z;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o); have += __shfl_xor_sync(0xffffffffu, have, o);
+    }
+    if (lane == 0) { s_sum[0][warp] = sx; s_sum[1][warp] = sy; s_sum[2][warp] = sz; s_cnt[warp] = have; }
+    __syncthreads();
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    int cnt = 0;
+    for (int w = 0; w < 8; ++w) { mx += s_sum[0][w]; my += s_sum[1][w]; mz += s_sum[2][w]; cnt += s_cnt[w]; }
+    const float inv = 1.0f / (float)max(cnt, 1);
+    mx *= inv; my *= inv; mz *= inv;
+    const long long n_rt = (n_r + tc::TR - 1) / tc::TR;
+    float best = __uint_as_float(0x7f800000u);
+    int arg = 0;
+    for (long long t = tid; t < n_rt; t += 256) {
+        const float4 r = r_sig[min(t * tc::TR + tc::TR / 2, n_r - 1)];
+        const float d0 = r.x - mx, d1 = r.y - my, d2 = r.z - mz;
+        const float d = fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
+        if (d < best) { best = d; arg = (int)t; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (lane == 0) { s_best[warp] = best; s_arg[warp] = arg; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (s_best[w] < best || (s_best[w] == best && s_arg[w] < arg)) { best = s_best[w]; arg = s_arg[w]; }
+        own_tile[qt] = arg;
+    }
+}
+
 // ---------------------------------------------------------------- host side ----
 // planes[n][3][A_pad] as a 3-D tensor ordered (atom, frame, plane); box = 64 bytes of atoms x `rows`
 // frames x 3 planes, so one TMA op lands the three plane tiles back to back as [plane][frame][atoms].
@@ -735,7 +792,7 @@ static cudaError_t launch_tc_mode(const CUtensorMap &mq_hi, const CUtensorMap &m
 cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *fit_hi, const void *fit_lo,
                                 long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,
                                 const void *ref_lo, int do_fit, int n_seg, CandLists<float> cl, float *row_tau,
-                                float g_ref_max, float *debug_tile, int n_sms, cudaStream_t st)
+                                float g_ref_max, int *own_tile_scratch, float *debug_tile, int n_sms, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
     if (cl.H != n_seg || cl.cap < cl.keep + tc::SUBS * tc::SUB_APP) return cudaErrorInvalidValue;
@@ -767,6 +824,12 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
     a.q_sig = reinterpret_cast<const float4 *>(fit.sig); a.r_sig = reinterpret_cast<const float4 *>(ref.sig);
     a.pre_rel = (dbg_bits & 2048) ? -1.0f : kPreRel[mode];
     a.pre_sqrt_gmax = sqrtf(g_ref_max > 0.f ? g_ref_max : 0.f);
+    a.own_tile = nullptr;
+    if (own_tile_scratch && !(dbg_bits & 32768)) {     // out-of-sample: where to start each fit super-tile (bit 32768: off)
+        const long long n_qt = (n_fit + tc::UMMA_M - 1) / tc::UMMA_M;
+        rms_guess_own_tile_kernel<<<(unsigned)n_qt, 256, 0, st>>>(a.q_sig, fit_begin, n_fit, a.r_sig, ref.n, own_tile_scratch);
+        a.own_tile = own_tile_scratch;
+    }
     // MDSCTK_TC_PROF=1: per-CTA clock sums {MMA warp: total, wait tmem_empty, wait full, passes |
     // epilogue warp 0: wait tmem_full, TMEM hold, post-release compute, merges}, printed to stderr
     static long long *d_prof = nullptr;

@@ -141,6 +141,25 @@ def test_default_kernel_and_fp16_overflow_substitution(trpcage):
             mdsctk_b200.knn_rms(big, mass, 10, ctx=c, rms_kernel=TC_F1)
 
 
+def test_out_of_sample_start_tile_guess(ctx):
+    """Fit rows handed over as host frames (the -f path) that happen to be reference frames must give the bytes of
+    the in-sample range query: the singular-value start-tile guess only changes the order of the sweep."""
+    from mdsctk_b200 import synth
+    n = 6000
+    xyz = synth.traj_frames(n, 300, 8)
+    mass = synth.traj_masses(300)
+    ctx.set_option("rms_kernel", TC_F1)
+    try:
+        ctx.rms_set_reference(xyz, mass)
+        d0, i0 = ctx.rms_query(33, fit_range=(2500, 700))
+        d1, i1 = ctx.rms_query(33, fit=np.ascontiguousarray(xyz[2500:3200]))
+        assert ctx.stats()["fallback_rows"] == 0
+    finally:
+        ctx.set_option("rms_kernel", 0)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+    assert (i0[:, 0] == np.arange(2500, 3200)).all() and (d0[:, 0] == 0.0).all()      # rank 0 is the frame itself
+
+
 def test_ragged_and_out_of_sample_tc(ctx, trpcage):
     import mdsctk_b200
     from oracle import binding as ob

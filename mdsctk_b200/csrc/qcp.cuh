@@ -48,7 +48,7 @@ __device__ __forceinline__ QcpCoef qcp_coefficients(const float *s, float f)
     // in the (signed) singular values of S, and their product is  sum s_i^4 - 2 sum s_i^2 s_j^2
     // = (sum s_i^2)^2 - 4 sum_{i<j} s_i^2 s_j^2, where sum_{i<j} s_i^2 s_j^2 is the squared Frobenius norm of
     // the cofactor matrix.  29 operations instead of the ~60 of the 2x2-minor expansion of the 4x4
-    // determinant (checked against it in tests/test_oracle.py::test_qcp_c0_identity).
+    // determinant (the identity is checked numerically in the CPU test suite: test_qcp_c0_identity).
     const float m3 = fmaf(sxy, szz, -sxz * szy);
     const float m4 = fmaf(sxx, szz, -sxz * szx);
     const float m5 = fmaf(sxx, szy, -sxy * szx);

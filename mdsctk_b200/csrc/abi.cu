@@ -211,10 +211,11 @@ void choose_lists(const mdsctk_knn_ctx *ctx, int k1, bool single_list, int *keep
 {
     // The admission threshold is the keep-th smallest approximate distance of the row, so `slack`
     // is what the adaptive re-score can fall back on when neighbours sit on a plateau of nearly
-    // equal distances (thermal noise): measured on the 100k x 300 workload, slack >= 96 certifies
-    // every row, and the sweep costs ~5% more per extra 64 kept candidates.
+    // equal distances (thermal noise): measured on the 100k x 300 workload, slack >= 48 certifies
+    // every row with the 1xFP16 certificate (>= 96 with the uniform noise bound of the 3x modes), C4's most
+    // extended basin needs 2 k1 at k = 64, and the sweep costs ~4% more per extra 32 kept candidates.
     (void)single_list;
-    long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(96, 2LL * k1);
+    long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(ctx->rms_kernel >= MDSCTK_KNN_RMS_TC_2XFP16 ? 64 : 96, 2LL * k1);
     long long kp = ((long long)k1 + slack + 7) / 8 * 8;
     *keep = (int)kp;
     *cap = (int)((kp + 128 + 31) / 32 * 32);

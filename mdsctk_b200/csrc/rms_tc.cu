@@ -137,8 +137,9 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
 
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[MAX_NST], bar_empty[MAX_NST], bar_tmem_full, bar_tmem_empty, bar_res_full,
-        bar_res_empty;
+        bar_res_empty, bar_epi_done;
     __shared__ uint32_t s_tmem_base;
+    __shared__ long long s_tcommit;      // clock-counter build: when the issuer committed the pass (leader CTA)
     __shared__ unsigned s_hist[EPI_WARPS][256];
     __shared__ int s_cnt[EPI_WARPS][32];
     __shared__ float s_tau[TQ];
@@ -164,7 +165,12 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         mbar_init(&bar_tmem_full, 1);
         mbar_init(&bar_res_full, 1);
         mbar_init(&bar_res_empty, 1);
-        mbar_init(&bar_tmem_empty, 2 * EPI_WARPS);     // the epilogue warps of BOTH CTAs (used on the leader only)
+        // accumulator hand-back (used on the leader only): the epilogue warps of BOTH CTAs arrive on it.  With
+        // MDSCTK_TC_DEBUG bit 131072 the peer's warps arrive on their own bar_epi_done and its otherwise idle warp 1
+        // forwards ONE remote arrival (measured: no difference, 79.9 vs 81.5 ms -- the 16 remote arrivals are not
+        // what the hand-back costs).
+        mbar_init(&bar_tmem_empty, (a.dbg & 131072) ? EPI_WARPS + 1 : 2 * EPI_WARPS);
+        mbar_init(&bar_epi_done, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -335,7 +341,10 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                                     }
                                 }
                                 tc_commit2_mc(&bar_empty[s2], 3);                      // frees the stage in both CTAs
-                                if (kc == nk - 1) tc_commit2_mc(&bar_tmem_full, 3);    // accumulators complete -> both epilogues
+                                if (kc == nk - 1) {
+                                    tc_commit2_mc(&bar_tmem_full, 3);                  // accumulators complete -> both epilogues
+                                    if (MDSCTK_TC_PROF_BUILD && a.prof) *reinterpret_cast<volatile long long *>(&s_tcommit) = clock64();
+                                }
                                 if (res && kc == nk - 1 && ti == rt1 - rt0 - 1) tc_commit2_mc(&bar_res_empty, 3);   // item done with its y|z planes
                                 if (++s2 == nst) s2 = 0;
                             }
@@ -349,6 +358,22 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
             if (MDSCTK_TC_PROF_BUILD && a.prof && lane == 0) {
                 long long *pr = a.prof + (size_t)blockIdx.x * 8;
                 pr[0] = clock64() - t_total0; pr[1] = t_wait_empty; pr[2] = t_wait_full; pr[3] = n_pass_done;
+            }
+        } else if (a.dbg & 131072) {
+            // =============================== hand-back forwarder (peer CTA, experiment) =
+            uint32_t fph = 0;
+            const uint32_t empty_leader = map_to_cta(&bar_tmem_empty, 0);
+            for (long long it = pair_id; it < n_items; it += n_pairs) {
+                long long qt, rt0, rt1, rot; int seg;
+                item_range(it, qt, rt0, rt1, seg, rot);
+                for (long long ti = 0; ti < rt1 - rt0; ++ti) {
+                    if (lane == 0) {
+                        mbar_wait_spin(&bar_epi_done, fph, 7);       // this CTA's 16 epilogue warps have read their accumulators
+                        mbar_arrive_cluster_nofence(empty_leader);
+                    }
+                    fph ^= 1;
+                    __syncwarp();
+                }
             }
         }
     } else {
@@ -376,7 +401,7 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         int *wcnt = s_cnt[ew];                        // fill of this warp's append area of row (quarter*32 + l)
         const size_t row_stride = (size_t)a.cl.H * a.cl.cap;
         uint32_t tph = 0;
-        long long t_wait_tmem = 0, t_hold = 0, t_post = 0, t_merge = 0, n_live = 0;
+        long long t_wait_tmem = 0, t_hold = 0, t_post = 0, t_merge = 0, n_live = 0, t_commit_lat = 0;
         int qn = 0;                                   // queue fill (warp-uniform)
         size_t lbase0 = 0;                            // list of the quarter's row 0 in the current item
         float *lkeys = a.cl.key;
@@ -533,13 +558,14 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                         if (near & (((1u << EB) - 1u) << (hb * EB))) live |= 1u << hb;
                     if (a.dbg & 1024) live = (1u << (SUBW / EB)) - 1u;
                 }
-                if (MDSCTK_TC_PROF_BUILD && a.prof) n_live += __popc(live);
+                if (MDSCTK_TC_PROF_BUILD && a.prof && !(a.dbg & 65536)) n_live += __popc(live);
                 const long long tp0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                 if (lane == 0) { if (a.dbg & 128) mbar_wait_spin(&bar_tmem_full, tph, 4); else mbar_wait(&bar_tmem_full, tph, 4); }
                 tph ^= 1;
                 __syncwarp();
                 tc_fence_after();
                 const long long tp1 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
+                if (MDSCTK_TC_PROF_BUILD && a.prof && rank == 0) t_commit_lat += tp1 - *reinterpret_cast<volatile long long *>(&s_tcommit);
                 long long tp2 = tp1;
                 const float tau = SC * *reinterpret_cast<volatile float *>(&s_tau[row_in_tile]);   // accumulator units
                 const float htau = 0.5f * tau;
@@ -557,7 +583,12 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 auto release = [&]() {                // hand the accumulators back to the MMA issuer
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if (a.dbg & 512) mbar_arrive_cluster(empty_leader); else if (a.dbg & 16384) mbar_arrive_cluster_relaxed(empty_leader); else mbar_arrive_cluster_nofence(empty_leader); }
+                    if (lane == 0) {
+                        if (a.dbg & 512) mbar_arrive_cluster(empty_leader);
+                        else if (a.dbg & 16384) mbar_arrive_cluster_relaxed(empty_leader);
+                        else if (rank == 0 || !(a.dbg & 131072)) mbar_arrive_cluster_nofence(empty_leader);
+                        else mbar_arrive(&bar_epi_done);              // peer CTA: local arrival, forwarded once by warp 1
+                    }
                     if (MDSCTK_TC_PROF_BUILD && a.prof) tp2 = clock64();
                     released = true;
                 };
@@ -634,13 +665,18 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                 const long long tp3 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                 // an append area takes at most SUBW entries per pass
                 if (((ti & (MERGE_EVERY - 1)) == MERGE_EVERY - 1) && ti + 1 < rt1 - rt0) merge_rows(row0, seg, false);
-                if (MDSCTK_TC_PROF_BUILD && a.prof) { t_wait_tmem += tp1 - tp0; t_hold += tp2 - tp1; t_post += tp3 - tp2; t_merge += clock64() - tp3; }
+                if (MDSCTK_TC_PROF_BUILD && a.prof) {
+                    // dbg bit 65536: count only the passes that read accumulators (live != 0), and how many there were
+                    const bool cnt = !(a.dbg & 65536) || live != 0;
+                    if (cnt) { t_wait_tmem += tp1 - tp0; t_hold += tp2 - tp1; t_post += tp3 - tp2; t_merge += clock64() - tp3; }
+                    if ((a.dbg & 65536) && live != 0) n_live += 1;
+                }
             }
             merge_rows(row0, seg, true);              // leaves one list of <= keep candidates per row
         }
         if (MDSCTK_TC_PROF_BUILD && a.prof && ew == 0 && lane == 0) {
             long long *pr = a.prof + (size_t)blockIdx.x * 8 + 4;
-            pr[0] = t_wait_tmem; pr[1] = t_hold; pr[2] = t_post; pr[3] = (a.dbg & 8192) ? n_live : t_merge;   // dbg 8192: live batches instead of merge clocks
+            pr[0] = (a.dbg & 65536) ? n_live : t_wait_tmem; pr[1] = t_hold; pr[2] = (a.dbg & 8192) ? t_commit_lat : t_post; pr[3] = (a.dbg & 8192) ? n_live : t_merge;   // dbg 8192: live batches instead of merge clocks
         }
     }
 

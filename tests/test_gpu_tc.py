@@ -157,7 +157,7 @@ def test_out_of_sample_start_tile_guess(ctx):
     finally:
         ctx.set_option("rms_kernel", 0)
     assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
-    assert (i0[:, 0] == np.arange(2500, 3200)).all() and (d0[:, 0] == 0.0).all()      # rank 0 is the frame itself
+    assert (i0[:, 0] == np.arange(2500, 3200)).all() and (d0[:, 0] < 1e-5).all()       # rank 0 is the frame itself (sqrt of FP64 noise)
 
 
 def test_ragged_and_out_of_sample_tc(ctx, trpcage):

@@ -20,8 +20,9 @@ e2e     the same metric through the public C-ABI call with HOST buffers: H2D of 
         frames from pinned memory + pack + sweep + re-score + D2H of the k-lists inside the
         timed region.
 roofline  dominant kernel = the sweep; algorithmic flops = 18 * atoms per pair (nine length-A
-        dot products) over the sweep's CUDA-event time; peak = dense TF32
-        = half of MEASURED_PEAKS.json's sustained bf16 figure (same tensor datapath).
+        dot products) over the sweep's CUDA-event time; peak =
+        MEASURED_PEAKS.json's sustained bf16 figure for the 16-bit kernels (the default 1xFP16
+        sweep issues one MMA per algorithmic flop, the 3x splits three), half of it for TF32.
 cpu_baseline  the oracle's reference-faithful float chain (oracle/, OpenMP, all host cores)
         on the first rows of the same workload.
 """

@@ -109,7 +109,14 @@ struct TcArgs {
     float pre_rel, pre_sqrt_gmax;  // operand rounding allowance of the pre-bound: g <= pre_rel (sqrt(Gq) + sqrt(max Gr)); < 0: off
     const int *own_tile;        // out-of-sample queries: per fit super-tile, the reference tile to start from (else NULL)
     int res, res_nst;           // resident fit planes (1xFP16): on/off, ring stages that fit beside them
-    int dbg;                    // MDSCTK_TC_DEBUG bits: 1 skip QCP, 2 skip MMA issue, 4 skip TMA, 8 no cheap bound
+    // MDSCTK_TC_DEBUG bits (timing experiments; results are only valid with 0, 16-128, 256, 512, 1024, 2048, 4096, 16384, 131072):
+    //   1 skip QCP   2 skip MMA issue   4 skip TMA   8 no Frobenius batch skip   16 / 32 eviction hints off / evict-first
+    //   64 suspending waits in the issuer   128 spinning waits in the epilogue   256 resident fit planes (1xFP16)
+    //   512 release.cluster arrive on the hand-back   1024 read every batch (pre-bound computed, not used)
+    //   2048 pre-bound off   4096 spinning waits in the producer   8192 / 65536 alternative clock counters (prof build)
+    //   16384 relaxed.cluster arrive   32768 no start-tile guess for out-of-sample queries   131072 forward the peer
+    //   CTA's hand-back through one remote arrival
+    int dbg;
     long long *prof;            // MDSCTK_TC_PROF=1: [grid][8] clock sums (see launch_rms_sweep_tc)
 };
 

@@ -146,7 +146,7 @@ def knn_data_sample(ctx):
     tot = st["ms_sweep"] + st["ms_rescore"] + st["ms_fallback"]
     return {"metric": "knn_data Euclidean row pairs/sec (all-pairs kNN)", "value": n * n / tot * 1e3, "unit": "pairs/s",
             "workload": f"synthetic phi-psi sin/cos rows {n} x {dim}, k=64 (C5 shape at reduced row count), 1 GPU",
-            "kernel": "data_sweep_tc_kernel (tcgen05 cta_group::2, 3xFP16 split) + exact FP64 re-score, bit-identical output",
+            "kernel": "data_sweep_tc_kernel (tcgen05 cta_group::2, 1xFP16 operands) + exact FP64 re-score with the rounding term in its certificate, bit-identical output",
             "sweep_ms": st["ms_sweep"], "rescore_ms": st["ms_rescore"], "fallback_rows": st["fallback_rows"],
             "sweep_tflops_algorithmic": n * n * 2 * dim / st["ms_sweep"] * 1e3 / 1e12}
 

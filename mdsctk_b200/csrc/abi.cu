@@ -125,11 +125,13 @@ struct mdsctk_knn_ctx {
     bool have_dref = false, dstats_dirty = true;
     // tensor-core filter state of the vector path (data_tc.cu)
     DevBuf dt_ref_hi, dt_ref_lo, dt_ref_norm, dt_fit_hi, dt_fit_lo, dt_fit_norm;
+    DevBuf dt_ref_norm1, dt_ref_g, dt_fit_norm1, dt_fit_g;   // one-part filter: norms of the hi parts, rounding residual norms
+    float dt_g_ref_max = 0.f;
     DevBuf fb_rows, fb_key, fb_idx, fb_cnt, fb_tau, fb_dist, fb_oidx;
     bool dpack_dirty = true;
     double dt_scale = 1.0, dt_ref_maxabs = 0.0;
     float dt_rnorm_max = 0.f;
-    int data_kernel = -1;      // -1 auto, 0 exact FP64 sweep, 1 tensor-core filter + exact re-score
+    int data_kernel = -1;      // -1 auto (= 2 for large Euclidean inputs), 0 exact FP64 sweep, 1 tensor-core filter (3xFP16) + exact re-score, 2 one-part filter (1xFP16)
     // CSC builder state (csc.cu)
     DevBuf c_idx, c_dist, c_ints, c_key, c_val, c_irow, c_oval;
     DevBuf f_in, f_ang, f_sc;   // featuriser buffers
@@ -405,20 +407,29 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
         CK(ctx->dt_ref_lo.reserve((size_t)n_ref * D_pad * 2), "cudaMalloc(ref lo)");
         CK(ctx->dt_ref_norm.reserve((size_t)(n_ref + 512) * 4), "cudaMalloc(ref norm)");
         CK(cudaMemsetAsync(ctx->dt_ref_norm.p, 0, (size_t)(n_ref + 512) * 4, ctx->st), "memset ref norm");
+        CK(ctx->dt_ref_norm1.reserve((size_t)(n_ref + 512) * 4), "cudaMalloc(ref norm1)");
+        CK(cudaMemsetAsync(ctx->dt_ref_norm1.p, 0, (size_t)(n_ref + 512) * 4, ctx->st), "memset ref norm1");
+        CK(ctx->dt_ref_g.reserve((size_t)n_ref * 4), "cudaMalloc(ref g)");
         CK(launch_data_pack(ctx->d_ref.as<double>(), n_ref, dim, D_pad, ctx->dt_scale, ctx->dt_ref_hi.p, ctx->dt_ref_lo.p,
-                            ctx->dt_ref_norm.as<float>(), ctx->st), "data_pack(ref)");
+                            ctx->dt_ref_norm.as<float>(), ctx->dt_ref_norm1.as<float>(), ctx->dt_ref_g.as<float>(), ctx->st),
+           "data_pack(ref)");
         CK(launch_max_float(ctx->dt_ref_norm.as<float>(), n_ref, ctx->scalars.as<float>() + 4, ctx->st), "max(norm)");
         CK(cudaMemcpyAsync(&ctx->dt_rnorm_max, ctx->scalars.as<float>() + 4, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H max(norm)");
+        CK(launch_max_float(ctx->dt_ref_g.as<float>(), n_ref, ctx->scalars.as<float>() + 5, ctx->st), "max(g)");
+        CK(cudaMemcpyAsync(&ctx->dt_g_ref_max, ctx->scalars.as<float>() + 5, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H max(g)");
         CK(cudaStreamSynchronize(ctx->st), "sync max(norm)");
         ctx->dpack_dirty = false;
         S.launches += 3;
     }
+    const bool one = ctx->data_kernel == 2 || ctx->data_kernel < 0;      // one-part (1xFP16) filter: what auto selects
     const void *fit_hi, *fit_lo;
-    const float *fit_norm;
+    const float *fit_norm, *fit_norm1, *fit_g;
     if (fit_is_ref) {
         fit_hi = ctx->dt_ref_hi.as<uint16_t>() + (size_t)fit_begin * D_pad;
         fit_lo = ctx->dt_ref_lo.as<uint16_t>() + (size_t)fit_begin * D_pad;
         fit_norm = ctx->dt_ref_norm.as<float>() + fit_begin;
+        fit_norm1 = ctx->dt_ref_norm1.as<float>() + fit_begin;
+        fit_g = ctx->dt_ref_g.as<float>() + fit_begin;
     } else {
         double fit_max = 0.0;
         CK(launch_data_maxabs(d_fit, (size_t)n_fit * dim, ctx->scalars.as<double>(), ctx->st), "maxabs(fit)");
@@ -428,9 +439,13 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
         CK(ctx->dt_fit_hi.reserve((size_t)n_fit * D_pad * 2), "cudaMalloc(fit hi)");
         CK(ctx->dt_fit_lo.reserve((size_t)n_fit * D_pad * 2), "cudaMalloc(fit lo)");
         CK(ctx->dt_fit_norm.reserve((size_t)(n_fit + 512) * 4), "cudaMalloc(fit norm)");
+        CK(ctx->dt_fit_norm1.reserve((size_t)(n_fit + 512) * 4), "cudaMalloc(fit norm1)");
+        CK(ctx->dt_fit_g.reserve((size_t)n_fit * 4), "cudaMalloc(fit g)");
         CK(launch_data_pack(d_fit, n_fit, dim, D_pad, ctx->dt_scale, ctx->dt_fit_hi.p, ctx->dt_fit_lo.p,
-                            ctx->dt_fit_norm.as<float>(), ctx->st), "data_pack(fit)");
+                            ctx->dt_fit_norm.as<float>(), ctx->dt_fit_norm1.as<float>(), ctx->dt_fit_g.as<float>(), ctx->st),
+           "data_pack(fit)");
         fit_hi = ctx->dt_fit_hi.p; fit_lo = ctx->dt_fit_lo.p; fit_norm = ctx->dt_fit_norm.as<float>();
+        fit_norm1 = ctx->dt_fit_norm1.as<float>(); fit_g = ctx->dt_fit_g.as<float>();
         S.launches += 2;
     }
     S.ms_pack += ctx->tm.stop(ctx->st);
@@ -460,9 +475,9 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
 
     ctx->tm.start(ctx->st);
     CK(launch_fill_u32(ctx->row_tau.p, (size_t)n_fit, 0x7f800000u, ctx->st), "fill row_tau");
-    CK(launch_data_sweep_tc(fit_hi, fit_lo, fit_norm, n_fit, fit_is_ref ? fit_begin : -1, ctx->dt_ref_hi.p, ctx->dt_ref_lo.p,
-                            ctx->dt_ref_norm.as<float>(), n_ref, D_pad, ctx->dt_scale, n_seg, cl, ctx->row_tau.as<float>(),
-                            ctx->n_sms, ctx->st), "data_sweep_tc");
+    CK(launch_data_sweep_tc(fit_hi, fit_lo, one ? fit_norm1 : fit_norm, n_fit, fit_is_ref ? fit_begin : -1, ctx->dt_ref_hi.p,
+                            ctx->dt_ref_lo.p, one ? ctx->dt_ref_norm1.as<float>() : ctx->dt_ref_norm.as<float>(), n_ref, D_pad,
+                            ctx->dt_scale, n_seg, cl, ctx->row_tau.as<float>(), one ? 1 : 0, ctx->n_sms, ctx->st), "data_sweep_tc");
     S.ms_sweep = ctx->tm.stop(ctx->st);
     CK(cudaGetLastError(), "data tensor sweep kernel");
     S.launches += 2;
@@ -472,8 +487,9 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
     const double eps_rel = 2.0e-6 * std::sqrt((double)std::max(dim, 64) / 64.0) * (double)ctx->cert_scale_ppm * 1e-6;
     S.cert_eps = eps_rel * 2.0 * (double)ctx->dt_rnorm_max / (ctx->dt_scale * ctx->dt_scale);
     ctx->tm.start(ctx->st);
+    S.cert_gres = one ? (double)ctx->dt_g_ref_max : 0.0;
     CK(launch_data_rescore(d_fit, ctx->d_ref.as<double>(), n_fit, dim, k1, cl, eps_rel, fit_norm, ctx->dt_scale,
-                           ctx->dt_rnorm_max, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(), d_err,
+                           ctx->dt_rnorm_max, one ? fit_g : nullptr, ctx->dt_g_ref_max, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(), d_err,
                            d_nbad, ctx->bad_rows.as<int>(), ctx->st), "data_rescore");
     struct { double pad, err, spread, done_max; int nbad; } host_sc;
     CK(cudaMemcpyAsync(&host_sc, ctx->scalars.p, sizeof(host_sc), cudaMemcpyDeviceToHost, ctx->st), "D2H scalars");
@@ -528,7 +544,7 @@ int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long lon
     S.max_filter_spread = 0; S.rescored_max = 0; S.lists_per_row = 1;
     // tensor-core filter: Euclidean metric; by default only where the contraction is worth staging
     const bool want_tc = metric == MDSCTK_KNN_EUCLIDEAN &&
-                         (ctx->data_kernel == 1 ||
+                         (ctx->data_kernel >= 1 ||
                           (ctx->data_kernel < 0 && dim >= 8 && (double)n_fit * (double)ctx->dn_ref >= 2.5e7));
     if (want_tc) {
         const int rc = data_run_tc(ctx, d_fit, fit_is_ref, fit_begin, n_fit, k1, out_dist, out_idx);
@@ -640,6 +656,12 @@ void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx)
     ctx->cand_key.release(); ctx->cand_idx.release(); ctx->cand_cnt.release(); ctx->cand_tau.release();
     ctx->flags.release(); ctx->bad_rows.release(); ctx->scalars.release(); ctx->rows_buf.release();
     ctx->out_dist.release(); ctx->out_idx.release(); ctx->debug_tile.release(); ctx->row_tau.release(); ctx->own_tile.release();
+    for (DevBuf *b2 : {&ctx->dt_ref_hi, &ctx->dt_ref_lo, &ctx->dt_ref_norm, &ctx->dt_fit_hi, &ctx->dt_fit_lo, &ctx->dt_fit_norm,
+                       &ctx->dt_ref_norm1, &ctx->dt_ref_g, &ctx->dt_fit_norm1, &ctx->dt_fit_g, &ctx->fb_rows, &ctx->fb_key,
+                       &ctx->fb_idx, &ctx->fb_cnt, &ctx->fb_tau, &ctx->fb_dist, &ctx->fb_oidx, &ctx->c_idx, &ctx->c_dist,
+                       &ctx->c_ints, &ctx->c_key, &ctx->c_val, &ctx->c_irow, &ctx->c_oval, &ctx->f_in, &ctx->f_ang, &ctx->f_sc,
+                       &ctx->s_int, &ctx->s_val, &ctx->s_vec, &ctx->s_basis, &ctx->s_rot, &ctx->s_small, &ctx->s_evec})
+        b2->release();
     ctx->tm.destroy();
     ctx->user_tm.destroy();
     cudaStreamDestroy(ctx->st);
@@ -662,7 +684,8 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
         if (value < 0) return fail(ctx, MDSCTK_KNN_EINVAL, "cert_scale_ppm must be >= 0");
         ctx->cert_scale_ppm = value;
     } else if (!strcmp(key, "data_kernel")) {
-        if (value < -1 || value > 1) return fail(ctx, MDSCTK_KNN_EINVAL, "data_kernel must be -1 (auto), 0 (exact) or 1 (tensor)");
+        if (value < -1 || value > 2)
+            return fail(ctx, MDSCTK_KNN_EINVAL, "data_kernel must be -1 (auto), 0 (exact), 1 (tensor, 3xFP16) or 2 (tensor, 1xFP16)");
         ctx->data_kernel = (int)value;
     } else if (!strcmp(key, "debug_tile")) {
         ctx->debug_tile_on = value != 0;

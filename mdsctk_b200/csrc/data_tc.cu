@@ -72,13 +72,14 @@ cudaError_t launch_data_maxabs(const double *v, size_t n, double *out, cudaStrea
 // one warp per row
 __global__ void __launch_bounds__(256) data_pack_kernel(const double *__restrict__ rows, long long n, int dim, int D_pad,
                                                         double scale, __half *__restrict__ hi, __half *__restrict__ lo,
-                                                        float *__restrict__ norm)
+                                                        float *__restrict__ norm, float *__restrict__ norm1,
+                                                        float *__restrict__ gres)
 {
     const int lane = threadIdx.x & 31;
     const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n) return;
     const double *v = rows + (size_t)r * dim;
-    double nn = 0.0;
+    double nn = 0.0, n1 = 0.0, r1 = 0.0;
     for (int x = lane; x < D_pad; x += 32) {
         float h = 0.0f, l = 0.0f;
         if (x < dim) {
@@ -86,6 +87,8 @@ __global__ void __launch_bounds__(256) data_pack_kernel(const double *__restrict
             nn += sv * sv;
             const __half hh = __float2half_rn((float)sv);
             h = __half2float(hh);
+            n1 += (double)h * (double)h;                       // the one-part filter contracts hi only: its norm ...
+            r1 += (sv - (double)h) * (sv - (double)h);         // ... and how far the rounded row is from the true one
             l = (float)(sv - (double)h);
             hi[(size_t)r * D_pad + x] = hh;
             lo[(size_t)r * D_pad + x] = __float2half_rn(l);
@@ -95,16 +98,23 @@ __global__ void __launch_bounds__(256) data_pack_kernel(const double *__restrict
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
-    if (lane == 0) norm[r] = (float)nn;
+    for (int o = 16; o > 0; o >>= 1) {
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+    }
+    if (lane == 0) {
+        norm[r] = (float)nn;
+        if (norm1) { norm1[r] = (float)n1; gres[r] = __double2float_ru(sqrt(r1) / scale); }   // residual norm in INPUT units, rounded up
+    }
 }
 
 cudaError_t launch_data_pack(const double *rows, long long n, int dim, int D_pad, double scale, void *hi, void *lo,
-                             float *norm, cudaStream_t st)
+                             float *norm, float *norm1, float *gres, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
     data_pack_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(rows, n, dim, D_pad, scale, static_cast<__half *>(hi),
-                                                               static_cast<__half *>(lo), norm);
+                                                               static_cast<__half *>(lo), norm, norm1, gres);
     return cudaGetLastError();
 }
 
@@ -116,6 +126,7 @@ struct DataTcArgs {
     float inv_scale2;                 // 1 / s^2: accumulator units -> input units^2
     CandLists<float> cl;              // H = n_seg lists per fit row; key = approximate d^2 in input units
     float *row_tau;
+    int one;                          // one-part filter: hi x hi only (q_norm / r_norm are then the norms of the hi parts)
 };
 
 __global__ void __launch_bounds__(dtc::NTHR, 1)
@@ -193,11 +204,13 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
                     unsigned char *st = smem + s * STAGE_BYTES;
                     const uint32_t full_leader = map_to_cta(&bar_full[s], 0);
                     if (elect_one()) {
-                        if (rank == 0) mbar_expect_tx(&bar_full[s], STAGE_TX);
+                        if (rank == 0) mbar_expect_tx(&bar_full[s], a.one ? STAGE_TX / 2 : STAGE_TX);
                         tma_load_2d_2sm(st + OFF_AHI, &map_q_hi, full_leader, kc * KC, q0, kEvictLast);
-                        tma_load_2d_2sm(st + OFF_ALO, &map_q_lo, full_leader, kc * KC, q0, kEvictLast);
                         tma_load_2d_2sm(st + OFF_BHI, &map_r_hi, full_leader, kc * KC, r0, kEvictNormal);
-                        tma_load_2d_2sm(st + OFF_BLO, &map_r_lo, full_leader, kc * KC, r0, kEvictNormal);
+                        if (!a.one) {
+                            tma_load_2d_2sm(st + OFF_ALO, &map_q_lo, full_leader, kc * KC, q0, kEvictLast);
+                            tma_load_2d_2sm(st + OFF_BLO, &map_r_lo, full_leader, kc * KC, r0, kEvictNormal);
+                        }
                     }
                     __syncwarp();
                     if (++s == NST) { s = 0; ph ^= 1; }
@@ -234,8 +247,10 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
                                 const uint64_t ahi = umma_desc_sw64(sa + OFF_AHI + koff), alo = umma_desc_sw64(sa + OFF_ALO + koff);
                                 const uint64_t bhi = umma_desc_sw64(sa + OFF_BHI + koff), blo = umma_desc_sw64(sa + OFF_BLO + koff);
                                 tc_mma2<true>(d, ahi, bhi, IDESC, (kc | ks) != 0);
-                                tc_mma2<true>(d, ahi, blo, IDESC, 1);
-                                tc_mma2<true>(d, alo, bhi, IDESC, 1);
+                                if (!a.one) {
+                                    tc_mma2<true>(d, ahi, blo, IDESC, 1);
+                                    tc_mma2<true>(d, alo, bhi, IDESC, 1);
+                                }
                             }
                             tc_commit2_mc(&bar_empty[s], 3);
                             if (kc == nk - 1) tc_commit2_mc(&bar_tmem_full[buf], 3);
@@ -422,7 +437,7 @@ int data_tc_choose_segments(long long n_fit, long long n_ref, int n_sms)
 cudaError_t launch_data_sweep_tc(const void *fit_hi, const void *fit_lo, const float *fit_norm, long long n_fit,
                                  long long fit_begin_in_ref, const void *ref_hi, const void *ref_lo, const float *ref_norm,
                                  long long n_ref, int D_pad, double scale, int n_seg, CandLists<float> cl, float *row_tau,
-                                 int n_sms, cudaStream_t st)
+                                 int one_part, int n_sms, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
     if (cl.H != n_seg || cl.cap < cl.keep + dtc::SUBS * dtc::SUB_APP || D_pad % dtc::KC) return cudaErrorInvalidValue;
@@ -433,6 +448,7 @@ cudaError_t launch_data_sweep_tc(const void *fit_hi, const void *fit_lo, const f
     DataTcArgs a;
     a.q_norm = fit_norm; a.r_norm = ref_norm; a.q_begin = fit_begin_in_ref; a.n_q = n_fit; a.n_r = n_ref;
     a.D_pad = D_pad; a.n_seg = n_seg; a.inv_scale2 = (float)(1.0 / (scale * scale)); a.cl = cl; a.row_tau = row_tau;
+    a.one = one_part;
     cudaError_t e = cudaFuncSetAttribute(data_sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dtc::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -459,6 +475,9 @@ cudaError_t launch_data_sweep_tc(const void *fit_hi, const void *fit_lo, const f
 // squared distances in FP64 exactly as euclidean_distance does (mdsctk.cpp:330-335: d = a[x]-b[x];
 // sum += d*d, left to right, no FMA), 64 candidates per round, then (distance, index) order and the
 // certificate  max approx key of the exact top-k1 + 2 eps < smallest approx key not yet re-scored.
+// One-part filter (q_g != NULL): its key is the exact squared distance of the fp16-ROUNDED rows plus bias and noise,
+// and |d~ - d| <= g = g_q + max g_r (triangle inequality), so the rule becomes, exactly as in rms_rescore.cu,
+//   min_i [key_i - max(d_i - g, 0)^2] + (d_k + g)^2 + 2 eps < a_next,  with the brackets of all candidates intersecting.
 struct DataRescoreArgs {
     const double *fit, *ref;          // fit rows of this query (row 0 = fit row 0), reference rows
     long long n_fit;
@@ -467,6 +486,8 @@ struct DataRescoreArgs {
     double eps_rel;                   // noise bound of the filter as a fraction of (|x|^2 + |y|^2)
     const float *q_norm;              // scaled norms; inv_scale2 converts
     float inv_scale2, r_norm_max;
+    const float *q_g;                 // one-part filter: residual norm |x - hi/s| of every fit row (input units), else NULL
+    float g_ref_max;                  // ... and the largest one of the reference set
     double *out_dist;
     int *out_idx, *flags, *n_bad, *bad_rows;
     double *err_stats;
@@ -525,6 +546,7 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
     __syncthreads();
 
     const double nq = (double)a.q_norm[q] * (double)a.inv_scale2;
+    const double grd = a.q_g ? (double)a.q_g[q] + (double)a.g_ref_max : 0.0;
     const double eps_max = a.eps_rel * (nq + (double)a.r_norm_max * (double)a.inv_scale2);
     double eps = eps_max;
     int done = 0;
@@ -553,11 +575,16 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
         }
         if (threadIdx.x < nb) {
             u_key[done + threadIdx.x] = sum;
-            const double err = (double)u_apx[done + threadIdx.x] - sum;
-            unsigned long long bits = (unsigned long long)__double_as_longlong(err);
-            bits = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
-            atomicMin(&s_emin, bits);
-            atomicMax(&s_emax, bits);
+            // bracket of the row-common bias: [key - (d+g)^2, key - max(d-g,0)^2]; a point (approx - exact) when g = 0
+            const double dn = sqrt(sum), dm = fmax(dn - grd, 0.0);
+            const double err_hi = (double)u_apx[done + threadIdx.x] - (grd > 0.0 ? dm * dm : sum);
+            const double err_lo = (double)u_apx[done + threadIdx.x] - (grd > 0.0 ? (dn + grd) * (dn + grd) : sum);
+            auto enc = [](double v) {
+                unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+                return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+            };
+            atomicMin(&s_emin, enc(err_hi));
+            atomicMax(&s_emax, enc(err_lo));
         }
         __syncthreads();
         done += nb;
@@ -588,7 +615,14 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
                 const double reach = sqrt(nq) + sqrt(s_d[k1 - 1] + 4.0 * eps_max);
                 eps = a.eps_rel * (nq + fmin((double)a.r_norm_max * (double)a.inv_scale2, reach * reach));
             }
-            if (ok && a_next != kInfF) ok = 0.5 * spread <= eps_max && (double)__uint_as_float(s_dtil) + 2.0 * eps < (double)a_next;
+            if (ok && a_next != kInfF) {
+                if (a.q_g) {
+                    const double dkg = sqrt(s_d[k1 - 1]) + grd;
+                    ok = 0.5 * spread <= eps_max && dec(s_emin) + dkg * dkg + 2.0 * eps < (double)a_next;
+                } else {
+                    ok = 0.5 * spread <= eps_max && (double)__uint_as_float(s_dtil) + 2.0 * eps < (double)a_next;
+                }
+            }
             s_ok = ok ? 1 : 0;
         }
         __syncthreads();
@@ -609,7 +643,7 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
         if (total > 0) {
             const double lo = dec(s_emin), hi = dec(s_emax);
             atomic_max_nonneg(a.err_stats + 0, fmax(fabs(lo), fabs(hi)));
-            atomic_max_nonneg(a.err_stats + 1, hi - lo);
+            atomic_max_nonneg(a.err_stats + 1, fmax(hi - lo, 0.0));
             atomic_max_nonneg(a.err_stats + 2, (double)done);
         }
         a.flags[q] = certified ? 1 : 0;
@@ -621,13 +655,15 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
 }
 
 cudaError_t launch_data_rescore(const double *fit, const double *ref, long long n_fit, int dim, int k1, CandLists<float> cl,
-                                double eps_rel, const float *q_norm, double scale, float r_norm_max, double *out_dist,
-                                int *out_idx, int *flags, double *err_stats, int *n_bad, int *bad_rows, cudaStream_t st)
+                                double eps_rel, const float *q_norm, double scale, float r_norm_max, const float *q_g,
+                                float g_ref_max, double *out_dist, int *out_idx, int *flags, double *err_stats, int *n_bad,
+                                int *bad_rows, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
     DataRescoreArgs a;
     a.fit = fit; a.ref = ref; a.n_fit = n_fit; a.dim = dim; a.k1 = k1; a.cl = cl; a.eps_rel = eps_rel; a.q_norm = q_norm;
     a.inv_scale2 = (float)(1.0 / (scale * scale)); a.r_norm_max = r_norm_max; a.out_dist = out_dist; a.out_idx = out_idx;
+    a.q_g = q_g; a.g_ref_max = g_ref_max;
     a.flags = flags; a.err_stats = err_stats; a.n_bad = n_bad; a.bad_rows = bad_rows;
     int P = 32;
     while (P < cl.keep * cl.H) P <<= 1;

@@ -90,3 +90,33 @@ def test_large_values_and_scale_tc(ctx):
     dist, idx = mdsctk_b200.knn_data(rows, 8, ctx=ctx)
     d, i = ob.knn_data(rows, 8)
     assert np.array_equal(idx, i) and np.array_equal(dist, d)
+
+
+def test_one_part_filter_gives_the_same_bytes():
+    """data_kernel 2: the fp16 hi parts alone feed the filter (one MMA per k-step); the re-score's certificate bounds
+    the rounding by the triangle inequality, so the files stay bit-identical to the three-MMA filter and the oracle."""
+    import mdsctk_b200
+    from mdsctk_b200 import synth
+    from oracle import binding as ob
+    rows = synth.phipsi_rows(20000, 512, 16)
+    with mdsctk_b200.KnnContext(0) as c:
+        c.set_option("data_kernel", 2)
+        dist, idx = mdsctk_b200.knn_data(rows, 64, ctx=c)
+        st = c.stats()
+        print("data one-part", {k: st[k] for k in ("ms_sweep", "ms_rescore", "ms_fallback", "fallback_rows", "max_filter_err",
+                                                   "cert_eps", "cert_gres", "k_keep", "rescored_max")})
+        assert st["cert_gres"] > 0.0 and st["fallback_rows"] < 200
+        d, i = ob.knn_data(rows, 64, fit=rows[:256])
+        assert np.array_equal(idx[:256], i) and np.array_equal(dist[:256], d)
+        c.set_option("data_kernel", 1)
+        dist1, idx1 = mdsctk_b200.knn_data(rows, 64, ctx=c)
+        assert np.array_equal(idx, idx1) and np.array_equal(dist, dist1)
+        # the reference's small examples and an out-of-sample query
+        pts = np.fromfile(os.path.join(DATA, "swissroll.pts"), dtype=np.float64).reshape(-1, 3)
+        g = np.load(os.path.join(GOLDEN, "swissroll_data_k10.npz"))
+        c.set_option("data_kernel", 2)
+        dist, idx = mdsctk_b200.knn_data(pts, 10, ctx=c)
+        assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
+        dist, idx = mdsctk_b200.knn_data(rows[:3000], 20, fit_rows=rows[5000:5400], ctx=c)
+        d, i = ob.knn_data(rows[:3000], 20, fit=rows[5000:5400])
+        assert np.array_equal(idx, i) and np.array_equal(dist, d)

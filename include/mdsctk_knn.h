@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MDSCTK_KNN_ABI_VERSION 1
+#define MDSCTK_KNN_ABI_VERSION 2
 
 enum {
     MDSCTK_KNN_OK = 0,
@@ -48,7 +48,9 @@ enum {
     MDSCTK_KNN_ECUDA = -2,    /* CUDA runtime / driver error                     */
     MDSCTK_KNN_ENOMEM = -3,   /* device or host allocation failed                */
     MDSCTK_KNN_ESTATE = -4,   /* call order (no reference set yet, ...)          */
-    MDSCTK_KNN_ENODEV = -5    /* no sm_100 device / device id out of range       */
+    MDSCTK_KNN_ENODEV = -5,   /* no sm_100 device / device id out of range       */
+    MDSCTK_KNN_EAUDIT = -6    /* a certified row disagrees with its exact recomputation (results were still
+                                 written; the message names the rows) -- never expected, fails loudly */
 };
 
 enum { MDSCTK_KNN_EUCLIDEAN = 0, MDSCTK_KNN_CORRELATION = 1 };
@@ -87,6 +89,8 @@ typedef struct mdsctk_knn_stats {
     int lists_per_row;     /* candidate lists per row kept by the sweep             */
     int rescored_max;      /* most candidates any row needed before its certificate held */
     double cert_gres;      /* 2xFP16 / 1xFP16: largest operand-rounding residual norm of the reference set (nm) */
+    long long audit_rows;       /* certified rows recomputed exactly (full FP64 row + exact selection) by the last query */
+    long long audit_mismatches; /* of those, rows whose result differed: must be 0                                     */
 } mdsctk_knn_stats;
 
 int mdsctk_knn_abi_version(void);
@@ -97,8 +101,16 @@ void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx);
 /* ctx may be NULL: returns the message of the last failed mdsctk_knn_create on this thread. */
 const char *mdsctk_knn_last_error(const mdsctk_knn_ctx *ctx);
 
-/* Tunables: "rms_kernel" (enum above), "slack" (extra candidates kept per row, -1 = auto),
+/* Tunables: "rms_kernel" (enum above; set it BEFORE loading the reference set: the pack kernel writes only the
+ * operand planes that kernel reads -- a later change re-packs from the resident raw frames),
+ * "slack" (extra candidates kept per row, -1 = auto),
  * "cert_scale_ppm" (certificate margin multiplier in parts-per-million of the default),
+ * "chunk_rows" (fit rows per internal row block of a query, default 131072: bounds the candidate-list memory the
+ * way the reference's --block-size bounds its row buffers, knn_rms.cpp:213-221),
+ * "data_kernel" (-1 auto, 0 exact FP64 sweep, 1 / 2 tensor-core filter with 3 / 1 fp16 parts + exact re-score),
+ * "audit_rows" (RMSD path: certified rows per row block that are recomputed through the exact FP64 path and
+ * compared, default 8; a mismatch makes the query return MDSCTK_KNN_EAUDIT; 0 = off),
+ * "force_exact" (0/1: every row goes through the exact FP64 path -- the certificate decides nothing; test hook),
  * "debug_tile" (0/1, see mdsctk_knn_debug_fetch_tile). */
 int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value);
 int mdsctk_knn_get_stats(const mdsctk_knn_ctx *ctx, mdsctk_knn_stats *out);
@@ -122,9 +134,10 @@ int mdsctk_knn_rms_query(mdsctk_knn_ctx *ctx, const float *fit_xyz, long long n_
  *   1. mdsctk_knn_rms_alloc_reference(n_total)          on every rank
  *   2. mdsctk_knn_rms_pack_shard(own frames, offset)    each rank packs ITS frames on ITS GPU
  *   3. all-gather the arrays listed by mdsctk_knn_rms_reference_arrays over NCCL
- *      (each is frame-major, bytes_per_frame[i] bytes per frame, n_total frames; 14 arrays today --
- *      raw, planes, G, cen, the TF32 / BF16 / FP16 operand splits, and the per-frame scalars of the
- *      1xFP16 sweep: rounded norms, rounding residuals, singular values -- pass max_arrays >= 16)
+ *      (each is frame-major, bytes_per_frame[i] bytes per frame, n_total frames: the raw frames, the per-frame
+ *      scalars -- G, centroid, singular values, rounded norms, rounding residuals -- and ONLY the operand planes
+ *      of the sweep kernel selected when the set was allocated: 8 arrays, 5.5 KB per 300-atom frame with the
+ *      default 1xFP16 kernel; at most 13 -- pass max_arrays >= 16)
  *   4. mdsctk_knn_rms_query_range(begin, n)             fit rows = reference rows [begin, begin+n) */
 int mdsctk_knn_rms_alloc_reference(mdsctk_knn_ctx *ctx, long long n_total, int n_atoms, const float *mass);
 int mdsctk_knn_rms_pack_shard(mdsctk_knn_ctx *ctx, const float *xyz, long long frame_offset, long long n_frames);
@@ -192,6 +205,12 @@ int mdsctk_knn_sincos(mdsctk_knn_ctx *ctx, const double *angles, long long n, do
  * TMEM accumulators of (fit tile 0, reference tile 0): out[128][9][48] floats, S_ab of fit row q
  * against reference j at out[q][3*a+b][j]. */
 int mdsctk_knn_debug_fetch_tile(mdsctk_knn_ctx *ctx, float *out);
+
+/* Diagnostic: copies one packed array of the RMSD reference set to the host (tests of the pack kernel).
+ * which: 0 raw float[n][A][3], 1 G float[n], 2 cen double[n][4], 3 sig float[n][4], 4 Gh float[n], 5 G2 float[n],
+ * 6 gres float[n][2], 7 planes float[n][3][A_pad], 8/9 TF32 hi/lo, 10/11 BF16 hi/mid, 12/13 FP16 hi/lo.
+ * Returns MDSCTK_KNN_ESTATE when that array is not packed for the current kernel; *n_bytes = its size. */
+int mdsctk_knn_debug_fetch_array(mdsctk_knn_ctx *ctx, int which, void *out, size_t out_capacity, size_t *n_bytes);
 
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of this library
  * is launched on): start records an event, stop records a second one, waits for it and returns

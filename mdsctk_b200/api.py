@@ -26,6 +26,7 @@ SYMBOLS = [
     "mdsctk_knn_fetch", "mdsctk_knn_rms_rows", "mdsctk_knn_timer_start", "mdsctk_knn_timer_stop",
     "mdsctk_knn_debug_fetch_tile", "mdsctk_knn_csc_build_sym", "mdsctk_knn_csc_build_general", "mdsctk_knn_csc_fetch",
     "mdsctk_knn_phipsi", "mdsctk_knn_sincos", "mdsctk_knn_data_rows", "mdsctk_knn_spectral_decomp",
+    "mdsctk_knn_debug_fetch_array",
 ]
 
 
@@ -39,7 +40,8 @@ class Stats(C.Structure):
                 ("pairs", C.c_longlong), ("launches", C.c_longlong), ("fallback_rows", C.c_longlong),
                 ("sweep_appends", C.c_longlong), ("max_filter_err", C.c_double), ("max_filter_spread", C.c_double),
                 ("cert_eps", C.c_double), ("rms_kernel", C.c_int), ("k_keep", C.c_int), ("lists_per_row", C.c_int),
-                ("rescored_max", C.c_int), ("cert_gres", C.c_double)]
+                ("rescored_max", C.c_int), ("cert_gres", C.c_double), ("audit_rows", C.c_longlong),
+                ("audit_mismatches", C.c_longlong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -88,6 +90,7 @@ def load_library():
     L.mdsctk_knn_timer_start.argtypes = [vp]
     L.mdsctk_knn_debug_fetch_tile.argtypes = [vp, fp]
     L.mdsctk_knn_timer_stop.argtypes = [vp, dp]
+    L.mdsctk_knn_debug_fetch_array.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.mdsctk_knn_csc_build_sym.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_build_general.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_fetch.argtypes = [vp, ip, dp]
@@ -312,6 +315,20 @@ class KnnContext:
     def debug_fetch_tile(self):
         out = np.empty((128, 9, 48), dtype=np.float32)
         self._ck(self._L.mdsctk_knn_debug_fetch_tile(self._h, _ptr(out, C.c_float)), "debug_fetch_tile")
+        return out
+
+    ARRAYS = {"raw": (0, np.float32), "G": (1, np.float32), "cen": (2, np.float64), "sig": (3, np.float32), "Gh": (4, np.float32),
+              "G2": (5, np.float32), "gres": (6, np.float32), "planes": (7, np.float32), "hi": (8, np.float32), "lo": (9, np.float32),
+              "bh": (10, np.uint16), "bm": (11, np.uint16), "fh": (12, np.float16), "fl": (13, np.float16)}
+
+    def debug_fetch_array(self, name):
+        """One packed array of the RMSD reference set as a flat numpy array (tests of the pack kernel)."""
+        which, dt = self.ARRAYS[name]
+        nb = C.c_size_t(0)
+        self._ck(self._L.mdsctk_knn_debug_fetch_array(self._h, which, None, 0, C.byref(nb)), "debug_fetch_array")
+        out = np.empty(nb.value // np.dtype(dt).itemsize, dtype=dt)
+        self._ck(self._L.mdsctk_knn_debug_fetch_array(self._h, which, out.ctypes.data_as(C.c_void_p), nb.value, C.byref(nb)),
+                 "debug_fetch_array")
         return out
 
     def timer_start(self):

@@ -40,10 +40,29 @@ struct DevBuf {
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Operand families of a packed frame set.  raw, G, cen, sig (and the small Gh / G2 / gres scalars) always exist;
+// the operand planes are written only for the sweep kernel in use (pack.cu), so the default 1xFP16 run holds
+// raw + fh = 5.4 KB per 300-atom frame instead of 22 KB, and the all-gather of a sharded run moves a quarter.
+enum { F_PLANES = 1, F_TF32 = 2, F_BF16 = 4, F_FP16 = 8, F_FP16LO = 16 };
+
+int families_of_kernel(int rms_kernel)
+{
+    switch (rms_kernel) {
+    case MDSCTK_KNN_RMS_SIMT_FP32: return F_PLANES;
+    case MDSCTK_KNN_RMS_TC_3XTF32:
+    case MDSCTK_KNN_RMS_TC_1XTF32: return F_TF32;
+    case MDSCTK_KNN_RMS_TC_3XBF16: return F_BF16;
+    case MDSCTK_KNN_RMS_TC_3XFP16:
+    case MDSCTK_KNN_RMS_TC_2XFP16: return F_FP16 | F_FP16LO;
+    default: return F_FP16;
+    }
+}
+
 struct FrameSet {
     DevBuf raw, planes, hi, lo, bh, bm, fh, fl, G, cen, Gh, G2, gres, sig;
     long long n = 0;
     int A = 0, A_pad = 0;
+    int have = 0;        // operand families packed for every frame of the set
     FrameSetView view() const
     {
         FrameSetView v;
@@ -54,16 +73,10 @@ struct FrameSet {
     }
     cudaError_t alloc(long long n_, int A_)
     {
+        if (n_ != n || A_ != A) have = 0;
         n = n_; A = A_; A_pad = pad_atoms(A_);
         cudaError_t e;
         if ((e = raw.reserve((size_t)n * A * 12)) != cudaSuccess) return e;
-        if ((e = planes.reserve((size_t)n * 3 * A_pad * 4)) != cudaSuccess) return e;
-        if ((e = hi.reserve((size_t)n * 3 * A_pad * 4)) != cudaSuccess) return e;
-        if ((e = lo.reserve((size_t)n * 3 * A_pad * 4)) != cudaSuccess) return e;
-        if ((e = bh.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
-        if ((e = bm.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
-        if ((e = fh.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
-        if ((e = fl.reserve((size_t)n * 3 * A_pad * 2)) != cudaSuccess) return e;
         if ((e = G.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;  // tensor-core epilogue reads G in 48-wide tiles
         if ((e = Gh.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;
         if ((e = G2.reserve((size_t)(n + 64) * 4)) != cudaSuccess) return e;
@@ -74,10 +87,21 @@ struct FrameSet {
         }
         return cen.reserve((size_t)n * 32);
     }
+    cudaError_t reserve_families(int fam)
+    {
+        cudaError_t e;
+        const size_t p4 = (size_t)n * 3 * A_pad * 4, p2 = (size_t)n * 3 * A_pad * 2;
+        if ((fam & F_PLANES) && (e = planes.reserve(p4)) != cudaSuccess) return e;
+        if ((fam & F_TF32) && ((e = hi.reserve(p4)) != cudaSuccess || (e = lo.reserve(p4)) != cudaSuccess)) return e;
+        if ((fam & F_BF16) && ((e = bh.reserve(p2)) != cudaSuccess || (e = bm.reserve(p2)) != cudaSuccess)) return e;
+        if ((fam & F_FP16) && (e = fh.reserve(p2)) != cudaSuccess) return e;
+        if ((fam & F_FP16LO) && (e = fl.reserve(p2)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
     void release()
     {
         raw.release(); planes.release(); hi.release(); lo.release(); bh.release(); bm.release(); fh.release(); fl.release(); G.release();
-        cen.release(); Gh.release(); G2.release(); gres.release(); sig.release(); n = 0;
+        cen.release(); Gh.release(); G2.release(); gres.release(); sig.release(); n = 0; have = 0;
     }
 };
 
@@ -116,6 +140,11 @@ struct mdsctk_knn_ctx {
     FrameSet ref, fit;
     DevBuf wnorm;  // double[A]
     bool have_ref = false, gmax_dirty = true;
+    int ref_pack_fam = F_FP16;   // operand families every shard of the current reference set is packed with (fixed at alloc)
+    long long chunk_rows = 131072;   // fit rows per internal row block of a query (bounds the candidate-list memory)
+    long long audit_rows = 8;        // certified rows per row block recomputed exactly and compared (0 = off)
+    bool force_exact = false;        // every row through the exact FP64 path (test hook)
+    DevBuf audit_ids, audit_seq, audit_dist, audit_idx;
     float g_ref_max = 0.f;
     float gres_ref_max[2] = {0.f, 0.f};   // largest rounding residual norm of the reference set (1 / 2 fp16 parts)
     // vector state
@@ -142,7 +171,7 @@ struct mdsctk_knn_ctx {
     DevBuf out_dist, out_idx, debug_tile, row_tau, own_tile;
     bool debug_tile_on = false;
     int n_sms = 148;
-    long long out_rows = 0;
+    long long out_rows = 0, out_off = 0;
     int out_k1 = 0;
     mdsctk_knn_stats stats;
 };
@@ -189,7 +218,24 @@ int upload_weights(mdsctk_knn_ctx *ctx, const float *mass, int A)
     return 0;
 }
 
-int pack_into(mdsctk_knn_ctx *ctx, FrameSet &fs, const float *xyz, long long off, long long n)
+// Packs frames [off, off+n) of fs from its raw array for the operand families `fam` (F_FP16LO implies F_FP16:
+// the lo part is the remainder of the hi part).
+int pack_launch(mdsctk_knn_ctx *ctx, FrameSet &fs, long long off, long long n, int fam)
+{
+    if (fam & F_FP16LO) fam |= F_FP16;
+    CK(fs.reserve_families(fam), "cudaMalloc(operand planes)");
+    const size_t po = (size_t)off * 3 * fs.A_pad;
+    CK(launch_pack_frames(fs.raw.as<float>() + (size_t)off * fs.A * 3, ctx->wnorm.as<double>(), n, fs.A, fs.A_pad,
+                          (fam & F_PLANES) ? fs.planes.as<float>() + po : nullptr,
+                          (fam & F_TF32) ? fs.hi.as<float>() + po : nullptr, (fam & F_TF32) ? fs.lo.as<float>() + po : nullptr,
+                          (fam & F_BF16) ? fs.bh.as<uint16_t>() + po : nullptr, (fam & F_BF16) ? fs.bm.as<uint16_t>() + po : nullptr,
+                          (fam & F_FP16) ? fs.fh.as<uint16_t>() + po : nullptr, (fam & F_FP16LO) ? fs.fl.as<uint16_t>() + po : nullptr,
+                          fs.G.as<float>() + off, fs.cen.as<double>() + 4 * off, fs.Gh.as<float>() + off, fs.G2.as<float>() + off,
+                          fs.gres.as<float>() + 2 * off, fs.sig.as<float>() + 4 * off, ctx->st), "pack_frames");
+    return 0;
+}
+
+int pack_into(mdsctk_knn_ctx *ctx, FrameSet &fs, const float *xyz, long long off, long long n, int fam)
 {
     const int A = fs.A;
     ctx->tm.start(ctx->st);
@@ -197,27 +243,35 @@ int pack_into(mdsctk_knn_ctx *ctx, FrameSet &fs, const float *xyz, long long off
                        ctx->st), "H2D frames");
     ctx->stats.ms_upload += ctx->tm.stop(ctx->st);
     ctx->tm.start(ctx->st);
-    CK(launch_pack_frames(fs.raw.as<float>() + (size_t)off * A * 3, ctx->wnorm.as<double>(), n, A, fs.A_pad,
-                          fs.planes.as<float>() + (size_t)off * 3 * fs.A_pad,
-                          fs.hi.as<float>() + (size_t)off * 3 * fs.A_pad, fs.lo.as<float>() + (size_t)off * 3 * fs.A_pad,
-                          fs.bh.as<uint16_t>() + (size_t)off * 3 * fs.A_pad, fs.bm.as<uint16_t>() + (size_t)off * 3 * fs.A_pad,
-                          fs.fh.as<uint16_t>() + (size_t)off * 3 * fs.A_pad, fs.fl.as<uint16_t>() + (size_t)off * 3 * fs.A_pad,
-                          fs.G.as<float>() + off,
-                          fs.cen.as<double>() + 4 * off, fs.Gh.as<float>() + off, fs.G2.as<float>() + off,
-                          fs.gres.as<float>() + 2 * off, fs.sig.as<float>() + 4 * off, ctx->st), "pack_frames");
+    const int rc = pack_launch(ctx, fs, off, n, fam);
+    if (rc) return rc;
     ctx->stats.ms_pack += ctx->tm.stop(ctx->st);
+    fs.have |= fam | ((fam & F_FP16LO) ? F_FP16 : 0);
     return 0;
 }
 
-void choose_lists(const mdsctk_knn_ctx *ctx, int k1, bool single_list, int *keep, int *cap)
+// The sweep kernel of a query was chosen after the set was packed (set_option, or the fp16-overflow substitution):
+// write the missing operand planes from the raw frames, which are always resident.
+int ensure_families(mdsctk_knn_ctx *ctx, FrameSet &fs, int fam)
+{
+    const int missing = fam & ~fs.have;
+    if (!missing) return 0;
+    ctx->tm.start(ctx->st);
+    const int rc = pack_launch(ctx, fs, 0, fs.n, missing);
+    if (rc) return rc;
+    ctx->stats.ms_pack += ctx->tm.stop(ctx->st);
+    fs.have |= missing;
+    return 0;
+}
+
+void choose_lists(const mdsctk_knn_ctx *ctx, int rms_kernel, int k1, int *keep, int *cap)
 {
     // The admission threshold is the keep-th smallest approximate distance of the row, so `slack`
     // is what the adaptive re-score can fall back on when neighbours sit on a plateau of nearly
     // equal distances (thermal noise): measured on the 100k x 300 workload, slack >= 48 certifies
     // every row with the 1xFP16 certificate (>= 96 with the uniform noise bound of the 3x modes), C4's most
     // extended basin needs 2 k1 at k = 64, and the sweep costs ~4% more per extra 32 kept candidates.
-    (void)single_list;
-    long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(ctx->rms_kernel >= MDSCTK_KNN_RMS_TC_2XFP16 ? 64 : 96, 2LL * k1);
+    long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(rms_kernel >= MDSCTK_KNN_RMS_TC_2XFP16 ? 64 : 96, 2LL * k1);
     long long kp = ((long long)k1 + slack + 7) / 8 * 8;
     *keep = (int)kp;
     *cap = (int)((kp + 128 + 31) / 32 * 32);
@@ -245,64 +299,25 @@ double default_eps_scale(int rms_kernel, int n_atoms)
     }
 }
 
-int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, long long n_fit, int k1, int do_fit,
-            double *out_dist, int *out_idx)
+struct RmsPlan {
+    int rms_kernel, keep, cap, n_seg, H, k1, do_fit;
+    bool use_tc, oos;
+};
+
+// One row block of a query: sweep -> FP64 re-score + certificate -> exact rows for what could not be certified.
+// Results land at out_dist / out_idx rows [row_off, row_off + n_fit) of the context's output buffers.
+int rms_run_block(mdsctk_knn_ctx *ctx, FrameSet &fitset, const RmsPlan &P, long long fit_begin, long long n_fit, long long row_off)
 {
     const FrameSetView ref = ctx->ref.view(), fit = fitset.view();
-    if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
-    if (k1 < 1 || k1 > ref.n) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 must satisfy 1 <= k1 <= n_reference");
-    if (k1 > 2040) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 > 2040 is not supported");
-    if ((size_t)ref.A * 24 + 2048 * 12 > 200 * 1024)
-        return fail(ctx, MDSCTK_KNN_EINVAL, "n_atoms too large for the FP64 re-score kernel (max ~7500)");
     mdsctk_knn_stats &S = ctx->stats;
-    S.ms_sweep = S.ms_rescore = S.ms_fallback = S.ms_download = 0;
-    S.pairs = n_fit * ref.n; S.launches = 0; S.fallback_rows = 0; S.sweep_appends = 0; S.max_filter_err = 0;
-    S.max_filter_spread = 0;
-    if (ctx->gmax_dirty) {
-        CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
-        CK(launch_max_float(ref.G, ref.n, ctx->scalars.as<float>(), ctx->st), "max(G)");
-        CK(cudaMemcpyAsync(&ctx->g_ref_max, ctx->scalars.p, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H max(G)");
-        for (int part = 0; part < 2; ++part) {
-            CK(launch_max_float_strided(ref.gres + part, ref.n, 2, ctx->scalars.as<float>() + 1 + part, ctx->st), "max(gres)");
-            CK(cudaMemcpyAsync(&ctx->gres_ref_max[part], ctx->scalars.as<float>() + 1 + part, 4, cudaMemcpyDeviceToHost, ctx->st),
-               "D2H max(gres)");
-        }
-        CK(cudaStreamSynchronize(ctx->st), "sync max(G)");
-        ctx->gmax_dirty = false;
-    }
-    // 64 * sqrt(G) bounds every fp16 operand element (overflow at 65504): the DEFAULT kernel gives way to 3xTF32
-    // for such coordinates; an explicitly chosen fp16 kernel is refused below instead
-    int rms_kernel = ctx->rms_kernel;
-    if (!ctx->rms_kernel_set && rms_kernel >= MDSCTK_KNN_RMS_TC_3XFP16 && 64.0 * std::sqrt((double)ctx->g_ref_max) > 3.0e4)
-        rms_kernel = MDSCTK_KNN_RMS_TC_3XTF32;
-    S.rms_kernel = rms_kernel;
-
-    int keep, cap;
-    const bool use_tc = rms_kernel != MDSCTK_KNN_RMS_SIMT_FP32;
-    choose_lists(ctx, k1, !use_tc, &keep, &cap);
-    // tensor-core sweep: four private sub-lists per (row, segment), merged into one at the end of the segment
-    if (use_tc) cap = rms_tc_list_stride(keep);
-    const int n_seg = use_tc ? rms_tc_choose_segments(n_fit, ref.n, ctx->n_sms) : 1;
-    const int H = use_tc ? rms_tc_lists_per_segment() * n_seg : 1;
-    S.k_keep = keep;
-    S.lists_per_row = H;
-    if ((size_t)ref.A * 48 + (size_t)std::min(keep * H, 2048) * 2 * 28 + 64 * 80 > 220 * 1024 || keep > 2048)
-        return fail(ctx, MDSCTK_KNN_EINVAL, "k too large for the FP64 re-score kernel's shared memory");
+    const int k1 = P.k1, do_fit = P.do_fit, rms_kernel = P.rms_kernel, H = P.H;
     CandLists<float> cl;
-    CK(ctx->cand_key.reserve((size_t)n_fit * H * cap * 4), "cudaMalloc(cand_key)");
-    CK(ctx->cand_idx.reserve((size_t)n_fit * H * cap * 4), "cudaMalloc(cand_idx)");
-    CK(ctx->cand_cnt.reserve((size_t)n_fit * H * 4), "cudaMalloc(cand_cnt)");
-    CK(ctx->cand_tau.reserve((size_t)n_fit * H * 8), "cudaMalloc(cand_tau)");
-    CK(ctx->flags.reserve((size_t)n_fit * 4), "cudaMalloc(flags)");
-    CK(ctx->bad_rows.reserve((size_t)n_fit * 4), "cudaMalloc(bad_rows)");
-    CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
-    CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
-    CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
-    ctx->out_rows = n_fit; ctx->out_k1 = k1;
     cl.key = ctx->cand_key.as<float>(); cl.idx = ctx->cand_idx.as<int>(); cl.cnt = ctx->cand_cnt.as<int>();
-    cl.tau = ctx->cand_tau.as<float>(); cl.cap = cap; cl.keep = keep; cl.H = H;
+    cl.tau = ctx->cand_tau.as<float>(); cl.cap = P.cap; cl.keep = P.keep; cl.H = H;
     double *d_err = ctx->scalars.as<double>() + 1;   // {max |err|, max spread}
     int *d_nbad = ctx->scalars.as<int>() + 8;
+    double *o_dist = ctx->out_dist.as<double>() + (size_t)row_off * k1;
+    int *o_idx = ctx->out_idx.as<int>() + (size_t)row_off * k1;
     CK(cudaMemsetAsync(ctx->scalars.p, 0, 64, ctx->st), "memset scalars");
 
     // ---- sweep: all pairs -> k1+slack candidates per row ------------------------------------
@@ -312,11 +327,7 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
         CK(launch_rms_sweep_simt(fit, fit_begin, n_fit, ref, do_fit, cl, ctx->st), "rms_sweep_simt");
         break;
     default:
-        if (ctx->debug_tile_on) CK(ctx->debug_tile.reserve(128 * 432 * 4), "cudaMalloc(debug_tile)");
-        CK(ctx->row_tau.reserve((size_t)n_fit * 4), "cudaMalloc(row_tau)");
         CK(launch_fill_u32(ctx->row_tau.p, (size_t)n_fit, 0x7f800000u, ctx->st), "fill row_tau");  // +inf
-        const bool oos = &fitset != &ctx->ref;      // out-of-sample: the fit rows are not reference frames
-        if (oos) CK(ctx->own_tile.reserve((size_t)((n_fit + 255) / 256) * 4), "cudaMalloc(own_tile)");
         {
             const void *q_hi = fitset.hi.p, *q_lo = fitset.lo.p, *r_hi = ctx->ref.hi.p, *r_lo = ctx->ref.lo.p;
             if (rms_kernel == MDSCTK_KNN_RMS_TC_3XBF16) {
@@ -324,19 +335,17 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
             } else if (rms_kernel == MDSCTK_KNN_RMS_TC_3XFP16 || rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ||
                        rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16) {
                 q_hi = fitset.fh.p; q_lo = fitset.fl.p; r_hi = ctx->ref.fh.p; r_lo = ctx->ref.fl.p;
-                // 64 * sqrt(G) bounds every operand element; fp16 overflows at 65504
-                if (64.0 * std::sqrt((double)ctx->g_ref_max) > 3.0e4)
-                    return fail(ctx, MDSCTK_KNN_EINVAL, "coordinates too large for the fp16 kernels; use rms_kernel=1 (3xTF32)");
+                if (rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16) { q_lo = q_hi; r_lo = r_hi; }    // no second part: never read
             }
-            CK(launch_rms_sweep_tc(rms_kernel, fit, q_hi, q_lo, fit_begin, n_fit, ref, r_hi, r_lo, do_fit, n_seg, cl,
-                                   ctx->row_tau.as<float>(), ctx->g_ref_max, oos ? ctx->own_tile.as<int>() : nullptr,
+            CK(launch_rms_sweep_tc(rms_kernel, fit, q_hi, q_lo, fit_begin, n_fit, ref, r_hi, r_lo, do_fit, P.n_seg, cl,
+                                   ctx->row_tau.as<float>(), ctx->g_ref_max, P.oos ? ctx->own_tile.as<int>() : nullptr,
                                    ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
                "rms_sweep_tc");
         }
         break;
     }
     S.launches += 1;
-    S.ms_sweep = ctx->tm.stop(ctx->st);
+    S.ms_sweep += ctx->tm.stop(ctx->st);
     CK(cudaGetLastError(), "sweep kernel");
 
     // ---- FP64 re-score + certificate -----------------------------------------------------------
@@ -349,21 +358,27 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
                            : (rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ? ctx->gres_ref_max[1] : 0.0f);
     S.cert_gres = fit_part >= 0 ? (double)gres_ref : 0.0;
     CK(launch_rms_rescore(fit, fit_begin, n_fit, ref, ctx->wnorm.as<double>(), do_fit, cl, k1, eps_scale,
-                          ctx->g_ref_max, fit_part, rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ? 2 : 1, gres_ref, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(),
+                          ctx->g_ref_max, fit_part, rms_kernel == MDSCTK_KNN_RMS_TC_2XFP16 ? 2 : 1, gres_ref, o_dist, o_idx, ctx->flags.as<int>(),
                           d_err, d_nbad, ctx->bad_rows.as<int>(), ctx->st), "rms_rescore");
     S.launches += 1;
     struct { double pad, err, spread, done_max; int nbad; } host_sc;
     CK(cudaMemcpyAsync(&host_sc, ctx->scalars.p, sizeof(host_sc), cudaMemcpyDeviceToHost, ctx->st), "D2H scalars");
-    S.ms_rescore = ctx->tm.stop(ctx->st);
+    S.ms_rescore += ctx->tm.stop(ctx->st);
     CK(cudaGetLastError(), "rescore kernel");
-    S.max_filter_err = host_sc.err;
-    S.max_filter_spread = host_sc.spread;
-    S.rescored_max = (int)host_sc.done_max;
-    S.fallback_rows = host_sc.nbad;
+    S.max_filter_err = std::max(S.max_filter_err, host_sc.err);
+    S.max_filter_spread = std::max(S.max_filter_spread, host_sc.spread);
+    S.rescored_max = std::max(S.rescored_max, (int)host_sc.done_max);
+    S.fallback_rows += host_sc.nbad;
 
     // ---- rows whose certificate failed: exact FP64 rows + exact selection -------------------
-    const char *tcdbg = getenv("MDSCTK_TC_DEBUG");   // timing experiments that skip the QCP leave every row uncertified
-    if (tcdbg && (atoi(tcdbg) & 1)) host_sc.nbad = 0;
+#if MDSCTK_TC_EXPERIMENTS
+    if (tc_experiment_bits() & 1) host_sc.nbad = 0;   // timing experiments that skip the QCP leave every row uncertified
+#endif
+    if (ctx->force_exact) {
+        S.fallback_rows += n_fit - host_sc.nbad;
+        host_sc.nbad = (int)n_fit;
+        CK(launch_iota_i32(ctx->bad_rows.as<int>(), (int)n_fit, 0, 1, ctx->st), "iota(bad_rows)");
+    }
     if (host_sc.nbad > 0) {
         ctx->tm.start(ctx->st);
         const size_t row_bytes = (size_t)ref.n * 8;
@@ -374,20 +389,145 @@ int rms_run(mdsctk_knn_ctx *ctx, const FrameSet &fitset, long long fit_begin, lo
             CK(launch_rms_exact_rows(fit, ctx->bad_rows.as<int>() + off, fit_begin, nr, ref, ctx->wnorm.as<double>(),
                                      do_fit, ctx->rows_buf.as<double>(), ctx->st), "rms_exact_rows");
             CK(launch_select_rows_f64(ctx->rows_buf.as<double>(), nr, ref.n, k1, ctx->bad_rows.as<int>() + off, 10.0,
-                                      ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->st), "select_rows");
+                                      o_dist, o_idx, ctx->st), "select_rows");
             S.launches += 2;
         }
-        S.ms_fallback = ctx->tm.stop(ctx->st);
+        S.ms_fallback += ctx->tm.stop(ctx->st);
         CK(cudaGetLastError(), "fallback kernels");
     }
-    if (out_dist || out_idx) return mdsctk_knn_fetch(ctx, out_dist, out_idx);
+
+    // ---- audit: a sample of rows recomputed through the exact path must agree -------------------
+    // The certificate's accumulation-noise term is a measured bound, not a derived one; this
+    // check does not depend on it: full FP64 rows + exact selection for rows spread over the block, compared with
+    // what the filter + certificate produced.  Costs ~1 % of a block; a mismatch is an error, not a statistic.
+    const int na = ctx->force_exact ? 0 : (int)std::min<long long>(ctx->audit_rows, n_fit);
+    if (na > 0) {
+        ctx->tm.start(ctx->st);
+        CK(ctx->audit_ids.reserve((size_t)na * 4), "cudaMalloc(audit_ids)");
+        CK(ctx->audit_seq.reserve((size_t)na * 4), "cudaMalloc(audit_seq)");
+        CK(ctx->audit_dist.reserve((size_t)na * k1 * 8), "cudaMalloc(audit_dist)");
+        CK(ctx->audit_idx.reserve((size_t)na * k1 * 4), "cudaMalloc(audit_idx)");
+        const int stride = (int)std::max<long long>(1, n_fit / na);
+        const int start = (int)((fit_begin / 7 + row_off / 3) % stride);      // a different residue in every block
+        CK(launch_iota_i32(ctx->audit_ids.as<int>(), na, start, stride, ctx->st), "iota(audit_ids)");
+        CK(launch_iota_i32(ctx->audit_seq.as<int>(), na, 0, 1, ctx->st), "iota(audit_seq)");
+        int *d_mis = ctx->scalars.as<int>() + 12;
+        const size_t row_bytes = (size_t)ref.n * 8;
+        const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)na, ((size_t)256 << 20) / row_bytes));
+        CK(ctx->rows_buf.reserve((size_t)chunk * row_bytes), "cudaMalloc(rows_buf)");
+        for (int off = 0; off < na; off += chunk) {
+            const int nr = std::min(chunk, na - off);
+            CK(launch_rms_exact_rows(fit, ctx->audit_ids.as<int>() + off, fit_begin, nr, ref, ctx->wnorm.as<double>(),
+                                     do_fit, ctx->rows_buf.as<double>(), ctx->st), "rms_exact_rows(audit)");
+            CK(launch_select_rows_f64(ctx->rows_buf.as<double>(), nr, ref.n, k1, ctx->audit_seq.as<int>() + off, 10.0,
+                                      ctx->audit_dist.as<double>(), ctx->audit_idx.as<int>(), ctx->st), "select_rows(audit)");
+            S.launches += 2;
+        }
+        CK(launch_audit_compare(o_dist, o_idx, ctx->audit_ids.as<int>(), ctx->audit_dist.as<double>(), ctx->audit_idx.as<int>(),
+                                na, k1, d_mis, ctx->st), "audit_compare");
+        int mis = 0;
+        CK(cudaMemcpyAsync(&mis, d_mis, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H audit");
+        S.ms_fallback += ctx->tm.stop(ctx->st);
+        S.launches += 1;
+        S.audit_rows += na;
+        S.audit_mismatches += mis;
+    }
+    return 0;
+}
+
+// The row loop of knn_rms.cpp:231-293 on the GPU: the fit rows go through in row blocks of ctx->chunk_rows (the
+// reference's --block-size exists for the same reason: it bounds the working memory of a block of rows).
+int rms_run(mdsctk_knn_ctx *ctx, FrameSet &fitset, long long fit_begin, long long n_fit, int k1, int do_fit,
+            double *out_dist, int *out_idx)
+{
+    const FrameSetView ref = ctx->ref.view();
+    if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
+    if (k1 < 1 || k1 > ref.n) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 must satisfy 1 <= k1 <= n_reference");
+    if (k1 > 2040) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 > 2040 is not supported");
+    if ((size_t)ref.A * 24 + 2048 * 12 > 200 * 1024)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "n_atoms too large for the FP64 re-score kernel (max ~7500)");
+    mdsctk_knn_stats &S = ctx->stats;
+    S.ms_sweep = S.ms_rescore = S.ms_fallback = S.ms_download = 0;
+    S.pairs = n_fit * ref.n; S.launches = 0; S.fallback_rows = 0; S.sweep_appends = 0; S.max_filter_err = 0;
+    S.max_filter_spread = 0; S.rescored_max = 0; S.audit_rows = 0; S.audit_mismatches = 0;
+    CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
+    if (ctx->gmax_dirty) {
+        CK(launch_max_float(ref.G, ref.n, ctx->scalars.as<float>(), ctx->st), "max(G)");
+        CK(cudaMemcpyAsync(&ctx->g_ref_max, ctx->scalars.p, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H max(G)");
+        CK(cudaStreamSynchronize(ctx->st), "sync max(G)");
+    }
+    // 64 * sqrt(G) bounds every fp16 operand element (overflow at 65504): the DEFAULT kernel gives way to 3xTF32
+    // for such coordinates; an explicitly chosen fp16 kernel is refused instead
+    RmsPlan P;
+    P.rms_kernel = ctx->rms_kernel; P.k1 = k1; P.do_fit = do_fit;
+    const bool fp16_overflow = 64.0 * std::sqrt((double)ctx->g_ref_max) > 3.0e4;
+    if (P.rms_kernel >= MDSCTK_KNN_RMS_TC_3XFP16 && fp16_overflow) {
+        if (ctx->rms_kernel_set)
+            return fail(ctx, MDSCTK_KNN_EINVAL, "coordinates too large for the fp16 kernels; use rms_kernel=1 (3xTF32)");
+        P.rms_kernel = MDSCTK_KNN_RMS_TC_3XTF32;
+    }
+    S.rms_kernel = P.rms_kernel;
+    // operand planes of this kernel: packed at load time for the kernel selected then, otherwise written now
+    const int fam = families_of_kernel(P.rms_kernel);
+    int rc = ensure_families(ctx, ctx->ref, fam);
+    if (rc) return rc;
+    if (&fitset != &ctx->ref && (rc = ensure_families(ctx, fitset, fam)) != 0) return rc;
+    if (ctx->gmax_dirty) {
+        for (int part = 0; part < 2; ++part) {
+            CK(launch_max_float_strided(ref.gres + part, ref.n, 2, ctx->scalars.as<float>() + 1 + part, ctx->st), "max(gres)");
+            CK(cudaMemcpyAsync(&ctx->gres_ref_max[part], ctx->scalars.as<float>() + 1 + part, 4, cudaMemcpyDeviceToHost, ctx->st),
+               "D2H max(gres)");
+        }
+        CK(cudaStreamSynchronize(ctx->st), "sync max(gres)");
+        ctx->gmax_dirty = false;
+    }
+
+    const long long block = std::min<long long>(n_fit, std::max<long long>(256, ctx->chunk_rows));
+    P.use_tc = P.rms_kernel != MDSCTK_KNN_RMS_SIMT_FP32;
+    choose_lists(ctx, P.rms_kernel, k1, &P.keep, &P.cap);
+    // tensor-core sweep: four private sub-lists per (row, segment), merged into one at the end of the segment
+    if (P.use_tc) P.cap = rms_tc_list_stride(P.keep);
+    P.n_seg = P.use_tc ? rms_tc_choose_segments(block, ref.n, ctx->n_sms) : 1;
+    P.H = P.use_tc ? rms_tc_lists_per_segment() * P.n_seg : 1;
+    P.oos = &fitset != &ctx->ref;      // out-of-sample: the fit rows are not reference frames
+    S.k_keep = P.keep;
+    S.lists_per_row = P.H;
+    if ((size_t)ref.A * 48 + (size_t)std::min(P.keep * P.H, 2048) * 2 * 28 + 64 * 80 > 220 * 1024 || P.keep > 2048)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "k too large for the FP64 re-score kernel's shared memory");
+    CK(ctx->cand_key.reserve((size_t)block * P.H * P.cap * 4), "cudaMalloc(cand_key)");
+    CK(ctx->cand_idx.reserve((size_t)block * P.H * P.cap * 4), "cudaMalloc(cand_idx)");
+    CK(ctx->cand_cnt.reserve((size_t)block * P.H * 4), "cudaMalloc(cand_cnt)");
+    CK(ctx->cand_tau.reserve((size_t)block * P.H * 8), "cudaMalloc(cand_tau)");
+    CK(ctx->flags.reserve((size_t)block * 4), "cudaMalloc(flags)");
+    CK(ctx->bad_rows.reserve((size_t)block * 4), "cudaMalloc(bad_rows)");
+    CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
+    CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
+    if (P.use_tc) {
+        if (ctx->debug_tile_on) CK(ctx->debug_tile.reserve(128 * 432 * 4), "cudaMalloc(debug_tile)");
+        CK(ctx->row_tau.reserve((size_t)block * 4), "cudaMalloc(row_tau)");
+        if (P.oos) CK(ctx->own_tile.reserve((size_t)((block + 255) / 256) * 4), "cudaMalloc(own_tile)");
+    }
+    ctx->out_rows = n_fit; ctx->out_k1 = k1;
+    for (long long off = 0; off < n_fit; off += block) {
+        const long long nb = std::min(block, n_fit - off);
+        if ((rc = rms_run_block(ctx, fitset, P, fit_begin + off, nb, off)) != 0) return rc;
+    }
+    if (out_dist || out_idx) {
+        rc = mdsctk_knn_fetch(ctx, out_dist, out_idx);
+        if (rc) return rc;
+    }
+    if (S.audit_mismatches > 0) {
+        char b[200];
+        snprintf(b, sizeof b, "audit: %lld of %lld certified rows differ from their exact FP64 recomputation (set force_exact=1 "
+                 "and report this input)", S.audit_mismatches, S.audit_rows);
+        return fail(ctx, MDSCTK_KNN_EAUDIT, b);
+    }
     return 0;
 }
 
 // Euclidean knn_data through the tensor-core filter (data_tc.cu): pack -> sweep -> exact FP64 re-score
 // with certificate -> exact FP64 sweep of the rows that could not be certified.
-int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1,
-                double *out_dist, int *out_idx)
+int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1)
 {
     mdsctk_knn_stats &S = ctx->stats;
     const int dim = ctx->ddim, D_pad = data_tc_pad_dim(dim);
@@ -466,7 +606,6 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
     CK(ctx->row_tau.reserve((size_t)n_fit * 4), "cudaMalloc(row_tau)");
     CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
     CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
-    ctx->out_rows = n_fit; ctx->out_k1 = k1;
     cl.key = ctx->cand_key.as<float>(); cl.idx = ctx->cand_idx.as<int>(); cl.cnt = ctx->cand_cnt.as<int>();
     cl.tau = ctx->cand_tau.as<float>(); cl.cap = cap; cl.keep = keep; cl.H = n_seg;
     CK(cudaMemsetAsync(ctx->scalars.p, 0, 64, ctx->st), "memset scalars");
@@ -489,7 +628,7 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
     ctx->tm.start(ctx->st);
     S.cert_gres = one ? (double)ctx->dt_g_ref_max : 0.0;
     CK(launch_data_rescore(d_fit, ctx->d_ref.as<double>(), n_fit, dim, k1, cl, eps_rel, fit_norm, ctx->dt_scale,
-                           ctx->dt_rnorm_max, one ? fit_g : nullptr, ctx->dt_g_ref_max, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->flags.as<int>(), d_err,
+                           ctx->dt_rnorm_max, one ? fit_g : nullptr, ctx->dt_g_ref_max, (ctx->out_dist.as<double>() + (size_t)ctx->out_off * k1), (ctx->out_idx.as<int>() + (size_t)ctx->out_off * k1), ctx->flags.as<int>(), d_err,
                            d_nbad, ctx->bad_rows.as<int>(), ctx->st), "data_rescore");
     struct { double pad, err, spread, done_max; int nbad; } host_sc;
     CK(cudaMemcpyAsync(&host_sc, ctx->scalars.p, sizeof(host_sc), cudaMemcpyDeviceToHost, ctx->st), "D2H scalars");
@@ -520,23 +659,17 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
                              MDSCTK_KNN_EUCLIDEAN, fl, ctx->st), "data_sweep(fallback)");
         CK(launch_data_finalize(fl, nb, k1, ctx->fb_dist.as<double>(), ctx->fb_oidx.as<int>(), ctx->st), "data_finalize(fallback)");
         CK(launch_data_scatter_out(ctx->fb_dist.as<double>(), ctx->fb_oidx.as<int>(), ctx->bad_rows.as<int>(), nb, k1,
-                                   ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->st), "scatter rows");
+                                   (ctx->out_dist.as<double>() + (size_t)ctx->out_off * k1), (ctx->out_idx.as<int>() + (size_t)ctx->out_off * k1), ctx->st), "scatter rows");
         S.ms_fallback = ctx->tm.stop(ctx->st);
         CK(cudaGetLastError(), "data fallback kernels");
         S.launches += 4;
     }
-    if (out_dist || out_idx) return mdsctk_knn_fetch(ctx, out_dist, out_idx);
     return 0;
 }
 
-int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1,
-             int metric, double *out_dist, int *out_idx)
+int data_run_block(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1,
+                   int metric)
 {
-    if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
-    if (k1 < 1 || k1 > ctx->dn_ref) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 must satisfy 1 <= k1 <= n_reference");
-    if (k1 > 2040) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 > 2040 is not supported");
-    if (metric != MDSCTK_KNN_EUCLIDEAN && metric != MDSCTK_KNN_CORRELATION)
-        return fail(ctx, MDSCTK_KNN_EINVAL, "unknown metric");
     mdsctk_knn_stats &S = ctx->stats;
     S.ms_sweep = S.ms_rescore = S.ms_fallback = S.ms_download = 0;
     S.pairs = n_fit * ctx->dn_ref; S.launches = 0; S.fallback_rows = 0; S.max_filter_err = 0; S.cert_eps = 0;
@@ -547,7 +680,7 @@ int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long lon
                          (ctx->data_kernel >= 1 ||
                           (ctx->data_kernel < 0 && dim >= 8 && (double)n_fit * (double)ctx->dn_ref >= 2.5e7));
     if (want_tc) {
-        const int rc = data_run_tc(ctx, d_fit, fit_is_ref, fit_begin, n_fit, k1, out_dist, out_idx);
+        const int rc = data_run_tc(ctx, d_fit, fit_is_ref, fit_begin, n_fit, k1);
         if (rc != 1) return rc;        // 1: not applicable to this input -> exact sweep below
     }
     const double *fit_stats = nullptr, *ref_stats = nullptr;
@@ -580,7 +713,6 @@ int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long lon
     CK(ctx->cand_tau.reserve((size_t)n_fit * 8), "cudaMalloc(cand_tau)");
     CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
     CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
-    ctx->out_rows = n_fit; ctx->out_k1 = k1;
     cl.key = ctx->cand_key.as<double>(); cl.idx = ctx->cand_idx.as<int>(); cl.cnt = ctx->cand_cnt.as<int>();
     cl.tau = ctx->cand_tau.as<double>(); cl.cap = cap; cl.keep = keep; cl.H = 1;
     ctx->tm.start(ctx->st);
@@ -589,11 +721,49 @@ int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long lon
     S.ms_sweep = ctx->tm.stop(ctx->st);
     CK(cudaGetLastError(), "data sweep kernel");
     ctx->tm.start(ctx->st);
-    CK(launch_data_finalize(cl, n_fit, k1, ctx->out_dist.as<double>(), ctx->out_idx.as<int>(), ctx->st),
+    CK(launch_data_finalize(cl, n_fit, k1, (ctx->out_dist.as<double>() + (size_t)ctx->out_off * k1), (ctx->out_idx.as<int>() + (size_t)ctx->out_off * k1), ctx->st),
        "data_finalize");
     S.ms_rescore = ctx->tm.stop(ctx->st);
     CK(cudaGetLastError(), "data finalize kernel");
     S.launches += 2;
+    return 0;
+}
+
+// The row loop of knn_data.cpp:195-250: row blocks of ctx->chunk_rows fit rows, results in row order.
+int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1,
+             int metric, double *out_dist, int *out_idx)
+{
+    if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
+    if (k1 < 1 || k1 > ctx->dn_ref) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 must satisfy 1 <= k1 <= n_reference");
+    if (k1 > 2040) return fail(ctx, MDSCTK_KNN_EINVAL, "k1 > 2040 is not supported");
+    if (metric != MDSCTK_KNN_EUCLIDEAN && metric != MDSCTK_KNN_CORRELATION)
+        return fail(ctx, MDSCTK_KNN_EINVAL, "unknown metric");
+    CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
+    CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
+    ctx->out_rows = n_fit; ctx->out_k1 = k1;
+    const long long block = std::min<long long>(n_fit, std::max<long long>(256, ctx->chunk_rows));
+    mdsctk_knn_stats tot = ctx->stats;
+    tot.ms_sweep = tot.ms_rescore = tot.ms_fallback = tot.ms_download = 0;
+    tot.launches = 0; tot.fallback_rows = 0; tot.max_filter_err = 0; tot.max_filter_spread = 0; tot.rescored_max = 0;
+    const double pack0 = ctx->stats.ms_pack;
+    for (long long off = 0; off < n_fit; off += block) {
+        const long long nb = std::min(block, n_fit - off);
+        ctx->out_off = off;
+        const int rc = data_run_block(ctx, d_fit + (size_t)off * ctx->ddim, fit_is_ref, fit_begin + off, nb, k1, metric);
+        ctx->out_off = 0;
+        if (rc) return rc;
+        const mdsctk_knn_stats &B = ctx->stats;
+        tot.ms_sweep += B.ms_sweep; tot.ms_rescore += B.ms_rescore; tot.ms_fallback += B.ms_fallback;
+        tot.launches += B.launches; tot.fallback_rows += B.fallback_rows;
+        tot.max_filter_err = std::max(tot.max_filter_err, B.max_filter_err);
+        tot.max_filter_spread = std::max(tot.max_filter_spread, B.max_filter_spread);
+        tot.rescored_max = std::max(tot.rescored_max, B.rescored_max);
+        tot.cert_eps = B.cert_eps; tot.cert_gres = B.cert_gres; tot.k_keep = B.k_keep; tot.lists_per_row = B.lists_per_row;
+        tot.ms_pack = B.ms_pack;
+    }
+    (void)pack0;
+    tot.pairs = n_fit * ctx->dn_ref;
+    ctx->stats = tot;
     if (out_dist || out_idx) return mdsctk_knn_fetch(ctx, out_dist, out_idx);
     return 0;
 }
@@ -660,7 +830,7 @@ void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx)
                        &ctx->dt_ref_norm1, &ctx->dt_ref_g, &ctx->dt_fit_norm1, &ctx->dt_fit_g, &ctx->fb_rows, &ctx->fb_key,
                        &ctx->fb_idx, &ctx->fb_cnt, &ctx->fb_tau, &ctx->fb_dist, &ctx->fb_oidx, &ctx->c_idx, &ctx->c_dist,
                        &ctx->c_ints, &ctx->c_key, &ctx->c_val, &ctx->c_irow, &ctx->c_oval, &ctx->f_in, &ctx->f_ang, &ctx->f_sc,
-                       &ctx->s_int, &ctx->s_val, &ctx->s_vec, &ctx->s_basis, &ctx->s_rot, &ctx->s_small, &ctx->s_evec})
+                       &ctx->audit_ids, &ctx->audit_seq, &ctx->audit_dist, &ctx->audit_idx, &ctx->s_int, &ctx->s_val, &ctx->s_vec, &ctx->s_basis, &ctx->s_rot, &ctx->s_small, &ctx->s_evec})
         b2->release();
     ctx->tm.destroy();
     ctx->user_tm.destroy();
@@ -687,6 +857,14 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
         if (value < -1 || value > 2)
             return fail(ctx, MDSCTK_KNN_EINVAL, "data_kernel must be -1 (auto), 0 (exact), 1 (tensor, 3xFP16) or 2 (tensor, 1xFP16)");
         ctx->data_kernel = (int)value;
+    } else if (!strcmp(key, "chunk_rows")) {
+        if (value < 256) return fail(ctx, MDSCTK_KNN_EINVAL, "chunk_rows must be >= 256");
+        ctx->chunk_rows = value;
+    } else if (!strcmp(key, "audit_rows")) {
+        if (value < 0 || value > 65536) return fail(ctx, MDSCTK_KNN_EINVAL, "audit_rows out of range");
+        ctx->audit_rows = value;
+    } else if (!strcmp(key, "force_exact")) {
+        ctx->force_exact = value != 0;
     } else if (!strcmp(key, "debug_tile")) {
         ctx->debug_tile_on = value != 0;
     } else {
@@ -713,6 +891,9 @@ int mdsctk_knn_rms_alloc_reference(mdsctk_knn_ctx *ctx, long long n_total, int n
     int rc = upload_weights(ctx, mass, n_atoms);
     if (rc) return rc;
     CK(ctx->ref.alloc(n_total, n_atoms), "cudaMalloc(reference set)");
+    ctx->ref.have = 0;                                    // new frames are coming: nothing is packed yet
+    ctx->ref_pack_fam = families_of_kernel(ctx->rms_kernel);
+    CK(ctx->ref.reserve_families(ctx->ref_pack_fam), "cudaMalloc(reference operand planes)");
     ctx->stats.ms_upload = ctx->stats.ms_pack = 0;
     ctx->have_ref = true;
     ctx->gmax_dirty = true;
@@ -728,7 +909,7 @@ int mdsctk_knn_rms_pack_shard(mdsctk_knn_ctx *ctx, const float *xyz, long long f
     Bind b(ctx);
     ctx->gmax_dirty = true;
     if (n_frames == 0) return 0;
-    return pack_into(ctx, ctx->ref, xyz, frame_offset, n_frames);
+    return pack_into(ctx, ctx->ref, xyz, frame_offset, n_frames, ctx->ref_pack_fam);
 }
 
 int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_arrays, void **dev_ptrs,
@@ -736,22 +917,24 @@ int mdsctk_knn_rms_reference_arrays(mdsctk_knn_ctx *ctx, int max_arrays, int *n_
 {
     if (!ctx || !n_arrays) return MDSCTK_KNN_EINVAL;
     if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
-    *n_arrays = 14;
-    if (max_arrays < 14 || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 14 arrays");
-    dev_ptrs[0] = ctx->ref.raw.p;    bytes_per_frame[0] = (size_t)ctx->ref.A * 12;
-    dev_ptrs[1] = ctx->ref.planes.p; bytes_per_frame[1] = (size_t)ctx->ref.A_pad * 12;
-    dev_ptrs[2] = ctx->ref.G.p;      bytes_per_frame[2] = 4;
-    dev_ptrs[3] = ctx->ref.cen.p;    bytes_per_frame[3] = 32;
-    dev_ptrs[4] = ctx->ref.hi.p;     bytes_per_frame[4] = (size_t)ctx->ref.A_pad * 12;
-    dev_ptrs[5] = ctx->ref.lo.p;     bytes_per_frame[5] = (size_t)ctx->ref.A_pad * 12;
-    dev_ptrs[6] = ctx->ref.bh.p;     bytes_per_frame[6] = (size_t)ctx->ref.A_pad * 6;
-    dev_ptrs[7] = ctx->ref.bm.p;     bytes_per_frame[7] = (size_t)ctx->ref.A_pad * 6;
-    dev_ptrs[8] = ctx->ref.fh.p;     bytes_per_frame[8] = (size_t)ctx->ref.A_pad * 6;
-    dev_ptrs[9] = ctx->ref.fl.p;     bytes_per_frame[9] = (size_t)ctx->ref.A_pad * 6;
-    dev_ptrs[10] = ctx->ref.Gh.p;    bytes_per_frame[10] = 4;
-    dev_ptrs[11] = ctx->ref.G2.p;    bytes_per_frame[11] = 4;
-    dev_ptrs[12] = ctx->ref.gres.p;  bytes_per_frame[12] = 8;
-    dev_ptrs[13] = ctx->ref.sig.p;   bytes_per_frame[13] = 16;
+    // always: raw, G, cen, sig, Gh, G2, gres; then the operand planes of the families this set is packed with
+    struct { void *p; size_t b; } arr[16];
+    int na = 0;
+    const FrameSet &R = ctx->ref;
+    const size_t p4 = (size_t)R.A_pad * 12, p2 = (size_t)R.A_pad * 6;
+    arr[na++] = {R.raw.p, (size_t)R.A * 12};
+    arr[na++] = {R.G.p, 4}; arr[na++] = {R.cen.p, 32}; arr[na++] = {R.sig.p, 16};
+    arr[na++] = {R.Gh.p, 4}; arr[na++] = {R.G2.p, 4}; arr[na++] = {R.gres.p, 8};
+    const int fam = ctx->ref_pack_fam | ((ctx->ref_pack_fam & F_FP16LO) ? F_FP16 : 0);
+    if (fam & F_PLANES) arr[na++] = {R.planes.p, p4};
+    if (fam & F_TF32) { arr[na++] = {R.hi.p, p4}; arr[na++] = {R.lo.p, p4}; }
+    if (fam & F_BF16) { arr[na++] = {R.bh.p, p2}; arr[na++] = {R.bm.p, p2}; }
+    if (fam & F_FP16) arr[na++] = {R.fh.p, p2};
+    if (fam & F_FP16LO) arr[na++] = {R.fl.p, p2};
+    *n_arrays = na;
+    if (max_arrays < na || !dev_ptrs || !bytes_per_frame) return fail(ctx, MDSCTK_KNN_EINVAL, "need room for 16 arrays");
+    for (int i = 0; i < na; ++i) { dev_ptrs[i] = arr[i].p; bytes_per_frame[i] = arr[i].b; }
+    ctx->ref.have = fam;     // the caller is about to fill the other ranks' frames of exactly these arrays
     ctx->gmax_dirty = true;  // the caller is about to overwrite them (all-gather)
     return 0;
 }
@@ -787,7 +970,8 @@ int mdsctk_knn_rms_query(mdsctk_knn_ctx *ctx, const float *fit_xyz, long long n_
     if (n_fit <= 0) return fail(ctx, MDSCTK_KNN_EINVAL, "n_fit must be positive");
     Bind b(ctx);
     CK(ctx->fit.alloc(n_fit, ctx->ref.A), "cudaMalloc(fit set)");
-    int rc = pack_into(ctx, ctx->fit, fit_xyz, 0, n_fit);
+    ctx->fit.have = 0;
+    int rc = pack_into(ctx, ctx->fit, fit_xyz, 0, n_fit, families_of_kernel(ctx->rms_kernel));
     if (rc) return rc;
     return rms_run(ctx, ctx->fit, 0, n_fit, k1, do_fit, out_dist, out_idx);
 }
@@ -1130,6 +1314,27 @@ int mdsctk_knn_debug_fetch_tile(mdsctk_knn_ctx *ctx, float *out)
     if (!ctx->debug_tile.p) return fail(ctx, MDSCTK_KNN_ESTATE, "no debug tile captured");
     Bind b(ctx);
     CK(cudaMemcpy(out, ctx->debug_tile.p, 128 * 432 * 4, cudaMemcpyDeviceToHost), "D2H debug tile");
+    return 0;
+}
+
+int mdsctk_knn_debug_fetch_array(mdsctk_knn_ctx *ctx, int which, void *out, size_t out_capacity, size_t *n_bytes)
+{
+    if (!ctx || !n_bytes) return MDSCTK_KNN_EINVAL;
+    if (!ctx->have_ref) return fail(ctx, MDSCTK_KNN_ESTATE, "no reference set");
+    const FrameSet &R = ctx->ref;
+    const size_t n = (size_t)R.n, p4 = n * 3 * R.A_pad * 4, p2 = n * 3 * R.A_pad * 2;
+    struct { const DevBuf *b; size_t bytes; int fam; } tab[14] = {
+        {&R.raw, n * R.A * 12, 0}, {&R.G, n * 4, 0}, {&R.cen, n * 32, 0}, {&R.sig, n * 16, 0}, {&R.Gh, n * 4, F_FP16},
+        {&R.G2, n * 4, F_FP16LO}, {&R.gres, n * 8, F_FP16}, {&R.planes, p4, F_PLANES}, {&R.hi, p4, F_TF32}, {&R.lo, p4, F_TF32},
+        {&R.bh, p2, F_BF16}, {&R.bm, p2, F_BF16}, {&R.fh, p2, F_FP16}, {&R.fl, p2, F_FP16LO}};
+    if (which < 0 || which >= 14) return fail(ctx, MDSCTK_KNN_EINVAL, "debug_fetch_array: which must be 0..13");
+    if ((tab[which].fam & ~R.have) != 0 || !tab[which].b->p) return fail(ctx, MDSCTK_KNN_ESTATE, "that array is not packed for the current kernel");
+    *n_bytes = tab[which].bytes;
+    if (!out) return 0;
+    if (out_capacity < tab[which].bytes) return fail(ctx, MDSCTK_KNN_EINVAL, "debug_fetch_array: buffer too small");
+    Bind b(ctx);
+    CK(cudaStreamSynchronize(ctx->st), "sync");
+    CK(cudaMemcpy(out, tab[which].b->p, tab[which].bytes, cudaMemcpyDeviceToHost), "D2H array");
     return 0;
 }
 

@@ -20,7 +20,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef MDSCTK_TC_EXPERIMENTS
+#define MDSCTK_TC_EXPERIMENTS 0   // 1: the tcgen05 sweep honours the MDSCTK_TC_DEBUG timing-experiment bits (never in production)
+#endif
+
 namespace mdsctk {
+
+int tc_experiment_bits();         // MDSCTK_TC_DEBUG in experiment builds, 0 otherwise (rms_tc.cu)
 
 constexpr float kRmsHalfScale = 64.0f;  // FP16 operand planes hold 64 * sqrt(w) (x - c): keeps the lo part normal
 constexpr int kAtomPad = 16;  // A_pad = roundup(A, 16): SIMT k-chunk and 2 x UMMA_K(tf32)=8
@@ -159,5 +165,8 @@ cudaError_t launch_sincos(const double *angles, long long n, double *out, cudaSt
 cudaError_t launch_max_float(const float *v, long long n, float *out, cudaStream_t st);
 cudaError_t launch_max_float_strided(const float *v, long long n, int stride, float *out, cudaStream_t st);   // max v[i*stride]
 cudaError_t launch_fill_u32(void *p, size_t n, uint32_t v, cudaStream_t st);
+cudaError_t launch_iota_i32(int *p, int n, int start, int stride, cudaStream_t st);   // p[i] = start + i * stride
+cudaError_t launch_audit_compare(const double *out_dist, const int *out_idx, const int *row_ids, const double *ex_dist,
+                                 const int *ex_idx, int n_rows, int k1, int *mismatches, cudaStream_t st);
 
 }  // namespace mdsctk

@@ -5,8 +5,9 @@
 // layout of the contraction: AoS float[n][A][3] (nm) -> planes float[n][3][A_pad] holding
 // sqrt(m_a/M) * (x_a - c), G = sum (m_a/M)|x_a - c|^2, and the FP64 centroid for the re-score.
 // plus the TF32 hi/lo split planes of the tensor-core sweep.
-// plus the BF16 and FP16 split planes.  One warp per frame; HBM-bound: 12*A bytes read +
-// 60*A_pad written per frame.
+// plus the BF16 and FP16 split planes -- each operand family only when its pointer is given, so a run
+// writes just what its sweep kernel reads (the default 1xFP16 sweep: fh, 6*A_pad bytes per frame).
+// One warp per frame; HBM-bound: 12*A bytes read + 6*A_pad (default) .. 60*A_pad (all families) written.
 // For the reduced-precision FP16 sweeps (2xFP16 / 1xFP16) the kernel also records, in FP64, what the
 // rounding did to each frame: Gh = |fh/64|^2 and G2 = |(fh+fl)/64|^2 (norms of the structures the
 // tensor cores actually see) and the residual norms g1 = |x - fh/64|, g2 = |x - (fh+fl)/64| (nm,
@@ -54,8 +55,8 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
         cz += __shfl_xor_sync(0xffffffffu, cz, o);
     }
     const size_t pbase = (size_t)f * 3 * A_pad;
-    float *px = planes + pbase;
-    float *py = px + A_pad, *pz = py + A_pad;
+    float *px = planes ? planes + pbase : nullptr;   // every operand family is optional: only what the chosen sweep reads is written
+    float *py = px ? px + A_pad : nullptr, *pz = px ? px + 2 * A_pad : nullptr;
     double g = 0.0, gh = 0.0, g2n = 0.0, r1 = 0.0, r2 = 0.0;
     double t00 = 0.0, t01 = 0.0, t02 = 0.0, t11 = 0.0, t12 = 0.0, t22 = 0.0;   // gyration tensor of the weighted frame
     for (int a = lane; a < A_pad; a += 32) {
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
             ox = (float)tx; oy = (float)ty; oz = (float)tz;
             t00 += tx * tx; t01 += tx * ty; t02 += tx * tz; t11 += ty * ty; t12 += ty * tz; t22 += tz * tz;
         }
-        px[a] = ox; py[a] = oy; pz[a] = oz;
+        if (planes) { px[a] = ox; py[a] = oy; pz[a] = oz; }
         if (hi) {  // 3xTF32 operand split for the tensor-core sweep: x ~= hi + lo, both exact TF32 values
             const float hx = tf32_rn(ox), hy = tf32_rn(oy), hz = tf32_rn(oz);
             hi[pbase + a] = hx; hi[pbase + A_pad + a] = hy; hi[pbase + 2 * A_pad + a] = hz;
@@ -93,13 +94,17 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 const __half h = __float2half_rn(o[d]);
-                const __half l = __float2half_rn(o[d] - __half2float(h));
                 fh[pbase + d * A_pad + a] = h;
-                fl[pbase + d * A_pad + a] = l;
                 const double v1 = (double)__half2float(h) * (1.0 / kRmsHalfScale);
-                const double v2 = v1 + (double)__half2float(l) * (1.0 / kRmsHalfScale);
-                gh += v1 * v1; g2n += v2 * v2;
-                r1 += (t[d] - v1) * (t[d] - v1); r2 += (t[d] - v2) * (t[d] - v2);
+                gh += v1 * v1;
+                r1 += (t[d] - v1) * (t[d] - v1);
+                if (fl) {   // second part: only the 3xFP16 / 2xFP16 sweeps read it
+                    const __half l = __float2half_rn(o[d] - __half2float(h));
+                    fl[pbase + d * A_pad + a] = l;
+                    const double v2 = v1 + (double)__half2float(l) * (1.0 / kRmsHalfScale);
+                    g2n += v2 * v2;
+                    r2 += (t[d] - v2) * (t[d] - v2);
+                }
             }
         }
     }
@@ -115,11 +120,11 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
         t12 += __shfl_xor_sync(0xffffffffu, t12, o); t22 += __shfl_xor_sync(0xffffffffu, t22, o);
     }
     if (lane == 0) {
-        if (Gh) {
-            Gh[f] = (float)gh;
-            G2[f] = (float)g2n;
+        if (fh) {
             // residual norms rounded up: they are subtracted from lower bounds
-            gres[f] = make_float2(__double2float_ru(sqrt(r1)), __double2float_ru(sqrt(r2)));
+            Gh[f] = (float)gh;
+            gres[f].x = __double2float_ru(sqrt(r1));
+            if (fl) { G2[f] = (float)g2n; gres[f].y = __double2float_ru(sqrt(r2)); }
         }
         if (sig) {
             // singular values of the 3 x A frame matrix = sqrt of the eigenvalues of its gyration tensor (closed form
@@ -178,6 +183,45 @@ __global__ void max_float_kernel(const float *v, long long n, int stride, float 
 __global__ void fill_u32_kernel(uint32_t *p, size_t n, uint32_t v)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void iota_i32_kernel(int *p, int n, int start, int stride)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = start + i * stride;
+}
+
+cudaError_t launch_iota_i32(int *p, int n, int start, int stride, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    iota_i32_kernel<<<148, 256, 0, st>>>(p, n, start, stride);
+    return cudaGetLastError();
+}
+
+// Audit of certified rows against the exact path: counts rows whose neighbour indices differ or whose distances
+// differ by more than 1e-12 relative (the two FP64 paths sum the cross-covariance in different orders).
+__global__ void audit_compare_kernel(const double *out_dist, const int *out_idx, const int *row_ids, const double *ex_dist,
+                                     const int *ex_idx, int n_rows, int k1, int *mismatches)
+{
+    const int r = blockIdx.x;
+    if (r >= n_rows) return;
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    const size_t o = (size_t)row_ids[r] * k1, e = (size_t)r * k1;
+    for (int j = threadIdx.x; j < k1; j += blockDim.x) {
+        const double a = out_dist[o + j], b = ex_dist[e + j];
+        if (out_idx[o + j] != ex_idx[e + j] || !(fabs(a - b) <= 1e-12 * fmax(fabs(b), 1e-300) + 1e-300)) bad = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bad) atomicAdd(mismatches, 1);
+}
+
+cudaError_t launch_audit_compare(const double *out_dist, const int *out_idx, const int *row_ids, const double *ex_dist,
+                                 const int *ex_idx, int n_rows, int k1, int *mismatches, cudaStream_t st)
+{
+    if (n_rows <= 0) return cudaSuccess;
+    audit_compare_kernel<<<n_rows, 128, 0, st>>>(out_dist, out_idx, row_ids, ex_dist, ex_idx, n_rows, k1, mismatches);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fill_u32(void *p, size_t n, uint32_t v, cudaStream_t st)

@@ -697,6 +697,18 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     }
 }
 
+// Timing-experiment switches (MDSCTK_TC_DEBUG bits, TcArgs::dbg).  Several of them give INVALID results, so the
+// production library never reads the environment: they exist only in builds with -DMDSCTK_TC_EXPERIMENTS=1.
+int tc_experiment_bits()
+{
+#if MDSCTK_TC_EXPERIMENTS
+    const char *dbg = getenv("MDSCTK_TC_DEBUG");
+    return dbg ? atoi(dbg) : 0;
+#else
+    return 0;
+#endif
+}
+
 // Out-of-sample queries (knn_rms -f): the fit rows are not reference frames, so "start at the row's own tile" has
 // no meaning -- but the frames that can be near a fit frame have nearly its singular values (the von Neumann bound
 // again), so every fit super-tile starts at the reference tile whose mid frame is closest to the super-tile's mean
@@ -826,7 +838,9 @@ static cudaError_t launch_tc_mode(const CUtensorMap &mq_hi, const CUtensorMap &m
     if (cudaOccupancyMaxActiveClusters(&q, rms_sweep_tc_kernel<M>, &cfg) == cudaSuccess && q > 0 && q < max_pairs)
         max_pairs = q;                              // a GPC with an odd SM count cannot host every pair
     (void)cudaGetLastError();
-    if (const char *mp = getenv("MDSCTK_TC_MAX_PAIRS")) { const int v = atoi(mp); if (v > 0 && v < max_pairs) max_pairs = v; }   // experiments
+#if MDSCTK_TC_EXPERIMENTS
+    if (const char *mp = getenv("MDSCTK_TC_MAX_PAIRS")) { const int v = atoi(mp); if (v > 0 && v < max_pairs) max_pairs = v; }
+#endif
     const long long n_pairs = n_items < max_pairs ? n_items : max_pairs;
     cfg.gridDim = dim3((unsigned)(n_pairs * 2));
     return cudaLaunchKernelEx(&cfg, rms_sweep_tc_kernel<M>, mq_hi, mq_lo, mr_hi, mr_lo, a);
@@ -839,8 +853,7 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
 {
     if (n_fit <= 0) return cudaSuccess;
     if (cl.H != n_seg || cl.cap < cl.keep + tc::SUBS * tc::SUB_APP) return cudaErrorInvalidValue;
-    const char *dbg = getenv("MDSCTK_TC_DEBUG");
-    const int dbg_bits = dbg ? atoi(dbg) : 0;
+    const int dbg_bits = tc_experiment_bits();     // 0 unless built with -DMDSCTK_TC_EXPERIMENTS=1 (scripts/build_prof.sh)
     // 1xFP16, MDSCTK_TC_DEBUG bit 256: keep two of the three fit planes resident in shared memory when they fit.
     // Off by default: it cuts the L2->SM operand stream 2.2x but leaves room for only 3 ring stages at 300 atoms,
     // and the sweep is bound by the MMA <-> epilogue hand-over, not by the stream (measured 92-101 ms vs 84-89 ms).
@@ -876,8 +889,10 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
     // MDSCTK_TC_PROF=1: per-CTA clock sums {MMA warp: total, wait tmem_empty, wait full, passes |
     // epilogue warp 0: wait tmem_full, TMEM hold, post-release compute, merges}, printed to stderr
     static long long *d_prof = nullptr;
-    const char *pe = getenv("MDSCTK_TC_PROF");
-    const bool prof = MDSCTK_TC_PROF_BUILD && pe && atoi(pe) != 0;
+    bool prof = false;
+#if MDSCTK_TC_PROF_BUILD
+    if (const char *pe = getenv("MDSCTK_TC_PROF")) prof = atoi(pe) != 0;
+#endif
     a.prof = nullptr;
     if (prof) {
         if (!d_prof && cudaMalloc(&d_prof, 1024 * 8 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;

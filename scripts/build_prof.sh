@@ -8,7 +8,7 @@ for f in mdsctk_b200/csrc/*.cu; do
   o=scripts/probe/prof_obj/$(basename ${f%.cu}).o
   if [ "$f" -nt "$o" ] || [ mdsctk_b200/csrc/common.cuh -nt "$o" ] || [ "$(basename $f)" = rms_tc.cu ]; then
     nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -ccbin /usr/bin/g++ \
-         -DMDSCTK_TC_PROF_BUILD=1 -c $f -o $o &
+         -DMDSCTK_TC_PROF_BUILD=1 -DMDSCTK_TC_EXPERIMENTS=1 -c $f -o $o &
   fi
 done
 wait

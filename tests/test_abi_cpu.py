@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mdsctk_knn.h but not exported"
     assert sorted(api.SYMBOLS) == names
-    assert lib.mdsctk_knn_abi_version() == 1
+    assert lib.mdsctk_knn_abi_version() == 2
 
 
 def test_no_torch_types_in_abi():

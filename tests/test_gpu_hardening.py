@@ -1,0 +1,216 @@
+"""Parity hardening (round 2): what pins the GPU path where the reference ships no vectors.
+
+* the pack kernel's outputs directly against numpy (operand planes, rounded norms, rounding residuals,
+  singular values, centroids) -- not through the MMA;
+* adversarial frame sets through the DEFAULT kernel, each compared ROW FOR ROW with the exact FP64 path
+  (`force_exact`: full FP64 rows + exact radix selection, no filter, no certificate): one conformational basin,
+  extended chains (G > 100 nm^2), 60 and 1200 atoms, 1 % exact duplicate frames, the 10 000-frame trp-cage
+  out-of-sample trajectory (examples/trp-cage-outofsample.xtc against the 1000 reference frames);
+* the sampled exact-row audit that every query carries (stats.audit_rows / audit_mismatches);
+* row-block independence (chunk_rows), kernel switches after load (operand planes written on demand), k = 1024.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import mdsctk_b200
+    c = mdsctk_b200.KnnContext(0)
+    yield c
+    c.close()
+
+
+def query(ctx, xyz, mass, k, fit=None, **opts):
+    for key, v in opts.items():
+        ctx.set_option(key, v)
+    ctx.rms_set_reference(xyz, mass)
+    d, i = ctx.rms_query(k + 1, fit=fit)
+    return d, i, ctx.stats()
+
+
+def exact_vs_default(ctx, xyz, mass, k, fit=None, max_fallback=None):
+    d, i, st = query(ctx, xyz, mass, k, fit=fit, force_exact=0, rms_kernel=6)
+    assert st["audit_rows"] > 0 and st["audit_mismatches"] == 0
+    de, ie, ste = query(ctx, xyz, mass, k, fit=fit, force_exact=1)
+    ctx.set_option("force_exact", 0)
+    n_fit = d.shape[0]
+    assert ste["fallback_rows"] == n_fit
+    assert np.array_equal(i, ie), f"{(i != ie).any(axis=1).sum()} rows differ from the exact FP64 path"
+    assert np.allclose(d, de, rtol=1e-12, atol=0)
+    if max_fallback is not None:
+        assert st["fallback_rows"] <= max_fallback, st
+    return st
+
+
+def test_pack_outputs_against_numpy(ctx):
+    from mdsctk_b200 import synth
+    n, A = 3000, 300
+    xyz = synth.traj_frames(n, A, 4, 77)
+    mass = (12.0 + np.arange(A) % 5).astype(np.float32)           # unequal masses: weights matter
+    ctx.set_option("rms_kernel", 4)                                  # 3xFP16: both fp16 parts are packed
+    ctx.rms_set_reference(xyz, mass)
+    A_pad = (A + 15) // 16 * 16
+    w = mass.astype(np.float64) / mass.astype(np.float64).sum()
+    x = xyz.astype(np.float64)
+    c = np.einsum("a,fad->fd", w, x)
+    t = np.sqrt(w)[None, :, None] * (x - c[:, None, :])             # the FP64 operand sqrt(w) (x - c)
+    cen = ctx.debug_fetch_array("cen").reshape(n, 4)
+    assert np.abs(cen[:, :3] - c).max() < 1e-12
+    G = (t * t).sum(axis=(1, 2))
+    assert np.allclose(cen[:, 3], G, rtol=1e-12)
+    assert np.allclose(ctx.debug_fetch_array("G"), G, rtol=2e-7)
+    fh = ctx.debug_fetch_array("fh").reshape(n, 3, A_pad)
+    fl = ctx.debug_fetch_array("fl").reshape(n, 3, A_pad)
+    o = t.astype(np.float32) * np.float32(64.0)
+    h = o.astype(np.float16)
+    l = (o - h.astype(np.float32)).astype(np.float16)
+    gpu_h = np.transpose(fh[:, :, :A], (0, 2, 1))
+    gpu_l = np.transpose(fl[:, :, :A], (0, 2, 1))
+    # the centroid sums run in a different order: a coordinate may land on the other side of an fp16 tie once in a while
+    assert (gpu_h != h).mean() < 1e-5 and np.abs(gpu_h.astype(np.float32) - h.astype(np.float32)).max() <= np.abs(h.astype(np.float32)).max() * 2 ** -10
+    assert (gpu_l != l).mean() < 1e-3
+    assert (fh[:, :, A:] == 0).all() and (fl[:, :, A:] == 0).all()                 # zero padding up to A_pad
+    v1 = gpu_h.astype(np.float64) / 64.0
+    v2 = v1 + gpu_l.astype(np.float64) / 64.0
+    assert np.allclose(ctx.debug_fetch_array("Gh"), (v1 * v1).sum(axis=(1, 2)), rtol=2e-7)
+    assert np.allclose(ctx.debug_fetch_array("G2"), (v2 * v2).sum(axis=(1, 2)), rtol=2e-7)
+    gres = ctx.debug_fetch_array("gres").reshape(n, 2)
+    r1 = np.sqrt(((t - v1) ** 2).sum(axis=(1, 2))); r2 = np.sqrt(((t - v2) ** 2).sum(axis=(1, 2)))
+    assert (gres[:, 0] >= r1 * (1 - 1e-7)).all() and np.allclose(gres[:, 0], r1, rtol=1e-6)     # rounded UP
+    assert (gres[:, 1] >= r2 * (1 - 1e-7)).all() and np.allclose(gres[:, 1], r2, rtol=1e-6)
+    sig = ctx.debug_fetch_array("sig").reshape(n, 4)
+    sv = np.linalg.svd(t[:200], compute_uv=False)
+    assert np.allclose(sig[:200, :3], sv, rtol=1e-5, atol=1e-6) and (sig[:, 3] == 0).all()
+    # the other operand families appear when a kernel that reads them is selected (re-pack from the resident raw frames)
+    with pytest.raises(Exception):
+        ctx.debug_fetch_array("hi")
+    ctx.set_option("rms_kernel", 1)
+    ctx.rms_query(5, fit_range=(0, 256), fetch=False)
+    hi = ctx.debug_fetch_array("hi").reshape(n, 3, A_pad)
+    lo = ctx.debug_fetch_array("lo").reshape(n, 3, A_pad)
+    t32 = np.transpose(t.astype(np.float32), (0, 2, 1))
+    assert np.abs(hi[:, :, :A] + lo[:, :, :A] - t32).max() <= np.abs(t32).max() * 2 ** -20
+    assert (hi.view(np.uint32) & 0x1FFF == 0).all()                                 # exact TF32 values
+    ctx.set_option("rms_kernel", 6)
+
+
+def test_row_blocks_and_kernel_switches_give_identical_lists(ctx, trpcage):
+    xyz, mass = trpcage
+    d0, i0, _ = query(ctx, xyz, mass, 10, rms_kernel=6, chunk_rows=131072)
+    d1, i1, st = query(ctx, xyz, mass, 10, chunk_rows=256)                       # 4 row blocks
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1) and st["audit_rows"] == 4 * 8
+    ctx.set_option("chunk_rows", 131072)
+    for kern in (4, 3, 1, 5, 0, 6):                                               # planes of each family written on demand
+        ctx.set_option("rms_kernel", kern)
+        d, i = ctx.rms_query(11)
+        assert ctx.stats()["rms_kernel"] == kern
+        assert np.array_equal(i, i0) and np.array_equal(d, d0), kern
+    pts = np.fromfile(os.path.join(DATA, "swissroll.pts"), dtype=np.float64).reshape(-1, 3)
+    ctx.data_set_reference(pts)
+    da, ia = ctx.data_query(11)
+    ctx.set_option("chunk_rows", 300)
+    db, ib = ctx.data_query(11)
+    ctx.set_option("chunk_rows", 131072)
+    assert np.array_equal(da, db) and np.array_equal(ia, ib)
+
+
+def test_k_1024_both_tools(ctx):
+    """k = 1024 (examples/mld/figure-11.bash:41) against the oracle."""
+    from mdsctk_b200 import synth
+    from oracle import binding as ob
+    import mdsctk_b200
+    n = 6000
+    xyz = synth.traj_frames(n, 60, 3, 5)
+    mass = synth.traj_masses(60)
+    d, i = mdsctk_b200.knn_rms(xyz, mass, 1024, ctx=ctx)
+    rows = np.arange(0, n, 97)
+    do, io = ob.knn_rms(xyz, mass, 1024, fit=xyz[rows], mode=1)
+    assert np.array_equal(i[rows], io) and np.allclose(d[rows], do, rtol=1e-9, atol=0)
+    pts = synth.phipsi_rows(20000, 64, 8)
+    ctx.set_option("data_kernel", 2)
+    d, i = mdsctk_b200.knn_data(pts, 1024, ctx=ctx)
+    ctx.set_option("data_kernel", -1)
+    rows = np.arange(0, 20000, 401)
+    do, io = ob.knn_data(pts, 1024, fit=pts[rows])
+    assert np.array_equal(i[rows], io) and np.array_equal(d[rows], do)
+
+
+def _gen(n, A, basins, seed):
+    from mdsctk_b200 import synth
+    from concurrent.futures import ThreadPoolExecutor
+    out = np.empty((n, A, 3), np.float32)
+    step = 8192
+    with ThreadPoolExecutor(8) as ex:
+        list(ex.map(lambda b: synth.traj_frames(n, A, basins, seed, b, min(step, n - b), out=out[b:b + step]), range(0, n, step)))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["single_basin", "extended_G100", "atoms60", "atoms1200", "duplicates"])
+def test_adversarial_sets_equal_the_exact_path(ctx, kind):
+    from mdsctk_b200 import synth
+    n, k = 50_000, 32
+    if kind == "single_basin":                      # nothing is far: every accumulator batch is live
+        xyz = _gen(n, 300, 1, 11)
+    elif kind == "extended_G100":                   # 4x the bond length: G ~ 120 nm^2 (7x the largest G of C3 / C4)
+        xyz = np.round(_gen(n, 300, 6, 12) * np.float32(4.0) * 1000.0).astype(np.float32) * np.float32(0.001)
+    elif kind == "atoms60":
+        xyz = _gen(n, 60, 5, 13)
+    elif kind == "atoms1200":
+        n = 20_000
+        xyz = _gen(n, 1200, 4, 14)
+    else:                                           # 1 % exact duplicates: zero distances and exact ties
+        xyz = _gen(n, 300, 8, 15)
+        rng = np.random.default_rng(3)
+        dst, src = rng.choice(n, n // 100, replace=False), rng.integers(0, n, n // 100)
+        xyz[dst] = xyz[src]
+    mass = synth.traj_masses(xyz.shape[1])
+    st = exact_vs_default(ctx, xyz, mass, k, max_fallback=n // 20)
+    if kind == "extended_G100":
+        G = ctx.debug_fetch_array("G")
+        assert G.max() > 100.0
+    print(kind, {key: st[key] for key in ("ms_sweep", "ms_rescore", "ms_fallback", "fallback_rows", "rescored_max", "max_filter_err",
+                                           "max_filter_spread", "cert_eps", "cert_gres", "audit_rows")})
+
+
+def test_trpcage_out_of_sample_10000_rows_equal_the_exact_path(ctx, trpcage):
+    """knn_rms -f trp-cage-outofsample.xtc -r trp-cage.xtc: 10 000 fit rows x 1000 landmarks, every row against the exact
+    path and a row sample against the oracle (FP64 Kabsch and the reference's float chain)."""
+    from oracle import binding as ob
+    ref, mass = trpcage
+    fit = ob.read_xtc(os.path.join(DATA, "trp-cage-outofsample.xtc"))
+    assert fit.shape == (10000, 60, 3)
+    exact_vs_default(ctx, ref, mass, 10, fit=fit, max_fallback=50)
+    d, i, _ = query(ctx, ref, mass, 10, fit=fit)
+    rows = np.arange(0, 10000, 7)
+    d1, i1 = ob.knn_rms(ref, mass, 10, fit=fit[rows], mode=1)
+    assert np.array_equal(i[rows, 1:], i1) and np.allclose(d[rows, 1:], d1, rtol=1e-9, atol=0)
+    d0, i0 = ob.knn_rms(ref, mass, 10, fit=fit[rows], mode=0)
+    assert (np.abs(d[rows, 1:] - d0) <= 1e-4 * d0).all()
+    assert (i[rows, 1:] != i0).sum() <= 8                       # near-ties inside the 1e-4 tolerance only
+
+
+def test_c3_full_size_2000_random_rows_against_the_oracle():
+    """C3 (100k x 300, k=32): 2000 random rows vs the FP64 Kabsch oracle, 256 vs the reference's float chain, all frames."""
+    import mdsctk_b200
+    from mdsctk_b200 import synth
+    from oracle import binding as ob
+    n, k = 100_000, 32
+    xyz = _gen(n, 300, 16, 20260117)
+    mass = synth.traj_masses(300)
+    with mdsctk_b200.KnnContext(0) as c:
+        dist, idx = mdsctk_b200.knn_rms(xyz, mass, k, ctx=c)
+        st = c.stats()
+    assert st["audit_mismatches"] == 0 and st["audit_rows"] == 8
+    rows = np.sort(np.random.default_rng(2026).choice(n, 2000, replace=False))
+    d1, i1 = ob.knn_rms(xyz, mass, k, fit=xyz[rows], mode=1)
+    assert np.array_equal(idx[rows], i1)
+    assert (np.abs(dist[rows] - d1) <= 1e-9 * d1).all()
+    d0, i0 = ob.knn_rms(xyz, mass, k, fit=xyz[rows[:256]], mode=0)
+    assert (np.abs(dist[rows[:256]] - d0) <= 1e-4 * d0).all()

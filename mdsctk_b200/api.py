@@ -41,7 +41,7 @@ class Stats(C.Structure):
                 ("sweep_appends", C.c_longlong), ("max_filter_err", C.c_double), ("max_filter_spread", C.c_double),
                 ("cert_eps", C.c_double), ("rms_kernel", C.c_int), ("k_keep", C.c_int), ("lists_per_row", C.c_int),
                 ("rescored_max", C.c_int), ("cert_gres", C.c_double), ("audit_rows", C.c_longlong),
-                ("audit_mismatches", C.c_longlong)]
+                ("audit_mismatches", C.c_longlong), ("sweep_version", C.c_int)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

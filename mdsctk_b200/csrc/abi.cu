@@ -144,6 +144,7 @@ struct mdsctk_knn_ctx {
     long long chunk_rows = 131072;   // fit rows per internal row block of a query (bounds the candidate-list memory)
     long long audit_rows = 8;        // certified rows per row block recomputed exactly and compared (0 = off)
     bool force_exact = false;        // every row through the exact FP64 path (test hook)
+    int sweep_version = 2;           // 1xFP16 sweep: 2 = rms_tc2.cu where the fit tile fits (default), 1 = rms_tc.cu
     DevBuf audit_ids, audit_seq, audit_dist, audit_idx;
     float g_ref_max = 0.f;
     float gres_ref_max[2] = {0.f, 0.f};   // largest rounding residual norm of the reference set (1 / 2 fp16 parts)
@@ -340,10 +341,19 @@ int rms_run_block(mdsctk_knn_ctx *ctx, FrameSet &fitset, const RmsPlan &P, long 
                 q_hi = fitset.fh.p; q_lo = fitset.fl.p; r_hi = ctx->ref.fh.p; r_lo = ctx->ref.fl.p;
                 if (rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16) { q_lo = q_hi; r_lo = r_hi; }    // no second part: never read
             }
-            CK(launch_rms_sweep_tc(rms_kernel, fit, q_hi, q_lo, fit_begin, n_fit, ref, r_hi, r_lo, do_fit, P.n_seg, cl,
-                                   ctx->row_tau.as<float>(), ctx->g_ref_max, P.oos ? ctx->own_tile.as<int>() : nullptr,
-                                   ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
-               "rms_sweep_tc");
+            if (rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16 && ctx->sweep_version != 1 && rms_tc2_supported(ref.A_pad)) {
+                CK(launch_rms_sweep_tc2(fit, fit_begin, n_fit, ref, do_fit, P.n_seg, cl, ctx->row_tau.as<float>(), ctx->g_ref_max,
+                                        P.oos ? ctx->own_tile.as<int>() : nullptr,
+                                        ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
+                   "rms_sweep_tc2");
+                S.sweep_version = 2;
+            } else {
+                CK(launch_rms_sweep_tc(rms_kernel, fit, q_hi, q_lo, fit_begin, n_fit, ref, r_hi, r_lo, do_fit, P.n_seg, cl,
+                                       ctx->row_tau.as<float>(), ctx->g_ref_max, P.oos ? ctx->own_tile.as<int>() : nullptr,
+                                       ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
+                   "rms_sweep_tc");
+                S.sweep_version = 1;
+            }
         }
         break;
     }
@@ -375,7 +385,7 @@ int rms_run_block(mdsctk_knn_ctx *ctx, FrameSet &fitset, const RmsPlan &P, long 
 
     // ---- rows whose certificate failed: exact FP64 rows + exact selection -------------------
 #if MDSCTK_TC_EXPERIMENTS
-    if (tc_experiment_bits() & 1) host_sc.nbad = 0;   // timing experiments that skip the QCP leave every row uncertified
+    if (tc_experiment_bits() & (1 | 64)) host_sc.nbad = 0;   // timing experiments that skip the QCP leave every row uncertified
 #endif
     if (ctx->force_exact) {
         S.fallback_rows += n_fit - host_sc.nbad;
@@ -469,7 +479,7 @@ int rms_run(mdsctk_knn_ctx *ctx, FrameSet &fitset, long long fit_begin, long lon
             return fail(ctx, MDSCTK_KNN_EINVAL, "coordinates too large for the fp16 kernels; use rms_kernel=1 (3xTF32)");
         P.rms_kernel = MDSCTK_KNN_RMS_TC_3XTF32;
     }
-    S.rms_kernel = P.rms_kernel;
+    S.rms_kernel = P.rms_kernel; S.sweep_version = 0;
     // operand planes of this kernel: packed at load time for the kernel selected then, otherwise written now
     const int fam = families_of_kernel(P.rms_kernel);
     int rc = ensure_families(ctx, ctx->ref, fam);
@@ -866,6 +876,9 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
     } else if (!strcmp(key, "audit_rows")) {
         if (value < 0 || value > 65536) return fail(ctx, MDSCTK_KNN_EINVAL, "audit_rows out of range");
         ctx->audit_rows = value;
+    } else if (!strcmp(key, "sweep_version")) {
+        if (value != 1 && value != 2) return fail(ctx, MDSCTK_KNN_EINVAL, "sweep_version must be 1 or 2");
+        ctx->sweep_version = (int)value;
     } else if (!strcmp(key, "force_exact")) {
         ctx->force_exact = value != 0;
     } else if (!strcmp(key, "debug_tile")) {
@@ -1259,6 +1272,7 @@ int mdsctk_knn_spectral_decomp(mdsctk_knn_ctx *ctx, int n, const int *pcol, cons
        "spectral_lanczos");
     S.ms_sweep = ctx->tm.stop(ctx->st);
     if (n_converged) *n_converged = nconv;
+    if (nconv < 0) return fail(ctx, MDSCTK_KNN_ESTATE, "spectral_decomp: the operator has fewer than nev independent directions");
     S.launches = nspmv; S.rescored_max = nrestart;
     ctx->tm.start(ctx->st);
     CK(cudaMemcpyAsync(evecs, ctx->s_evec.p, (size_t)nev * n * 8, cudaMemcpyDeviceToHost, ctx->st), "D2H eigenvectors");

@@ -79,6 +79,14 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
                                 long long fit_begin, long long n_fit, const FrameSetView &ref, const void *ref_hi,
                                 const void *ref_lo, int do_fit, int n_seg, CandLists<float> cl, float *row_tau,
                                 float g_ref_max, int *own_tile_scratch, float *debug_tile, int n_sms, cudaStream_t st);
+// Second-generation 1xFP16 sweep (rms_tc2.cu): fit tile resident in shared memory + TMEM, reference-only ring, pass
+// director.  Same lists / arguments as launch_rms_sweep_tc with mode 6; supported when the fit tile fits (A_pad <= 304).
+bool rms_tc2_supported(int A_pad);
+cudaError_t launch_rms_sweep_tc2(const FrameSetView &fit, long long fit_begin, long long n_fit, const FrameSetView &ref, int do_fit,
+                                 int n_seg, CandLists<float> cl, float *row_tau, float g_ref_max, int *own_tile_scratch,
+                                 float *debug_tile, int n_sms, cudaStream_t st);
+cudaError_t launch_rms_guess_own_tile(const float4 *q_sig, long long q_begin, long long n_q, const float4 *r_sig, long long n_r,
+                                      int *own_tile, cudaStream_t st);
 int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms);
 int rms_tc_lists_per_segment();
 int rms_tc_list_stride(int keep);

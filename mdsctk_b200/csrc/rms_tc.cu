@@ -763,6 +763,15 @@ __global__ void __launch_bounds__(256) rms_guess_own_tile_kernel(const float4 *q
     }
 }
 
+cudaError_t launch_rms_guess_own_tile(const float4 *q_sig, long long q_begin, long long n_q, const float4 *r_sig, long long n_r,
+                                      int *own_tile, cudaStream_t st)
+{
+    const long long n_qt = (n_q + tc::UMMA_M - 1) / tc::UMMA_M;
+    if (n_qt <= 0) return cudaSuccess;
+    rms_guess_own_tile_kernel<<<(unsigned)n_qt, 256, 0, st>>>(q_sig, q_begin, n_q, r_sig, n_r, own_tile);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- host side ----
 // planes[n][3][A_pad] as a 3-D tensor ordered (atom, frame, plane); box = 64 bytes of atoms x `rows`
 // frames x 3 planes, so one TMA op lands the three plane tiles back to back as [plane][frame][atoms].

@@ -86,17 +86,21 @@ __global__ void sigma_kernel(int n, const int *__restrict__ ptr, const int *__re
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
     const int b = ptr[v], m = min(ptr[v + 1] - b, k_a);
-    // ascending-order sum of the first m values (the reference sorts them before adding): selection by repeated minimum
-    double s = 0.0, last = -1.0;
-    int taken = 0;
-    while (taken < m) {
-        double cur = 1.0e308;
-        for (int i = 0; i < m; ++i) { const double x = M[adj_pos[b + i]]; if (x > last && x < cur) cur = x; }
-        int mult = 0;
-        for (int i = 0; i < m; ++i) if (M[adj_pos[b + i]] == cur) ++mult;
-        for (int i = 0; i < mult; ++i) s += cur;
-        taken += mult;
-        last = cur;
+    // ascending-order sum of the first m values (the reference sorts them before adding): m selections of the next
+    // (value, position) pair in lexicographic order -- always m iterations, whatever the values (duplicates, infinities);
+    // NaNs compare false everywhere, are never selected, and poison the sum as they do in the reference
+    double s = 0.0, lastv = -__longlong_as_double(0x7ff0000000000000LL);
+    int lasti = -1;
+    for (int t = 0; t < m; ++t) {
+        double cur = 0.0;
+        int ci = -1;
+        for (int i = 0; i < m; ++i) {
+            const double x = M[adj_pos[b + i]];
+            if ((x > lastv || (x == lastv && i > lasti)) && (ci < 0 || x < cur)) { cur = x; ci = i; }
+        }
+        if (ci < 0) { s += __longlong_as_double(0x7ff8000000000000LL); break; }
+        s += cur;
+        lastv = cur; lasti = ci;
     }
     sigma[v] = s / (double)k_a;
 }
@@ -350,7 +354,25 @@ cudaError_t spectral_lanczos(int n, const int *ptr, const int *adj_other, const 
             SP_CK(dots(w, 1, w, &b2));
             const double beta = std::sqrt(std::max(b2, 0.0));
             beta_m = beta;
-            if (!(beta > 1e-14)) { mm = j + 1; beta_m = 0.0; break; }     // invariant subspace: the basis is complete
+            if (!(beta > 1e-14)) {
+                // invariant subspace (a disconnected component, or fewer distinct directions than basis vectors): the
+                // recurrence has nothing to continue with.  Carry on from a fresh random vector orthogonal to the basis
+                // (its coupling to the previous vector is exactly the zero beta), so that the basis still reaches ncv
+                // vectors and all nev pairs come out; only when no such direction is left is the basis truly complete.
+                beta_m = 0.0;
+                if (j + 1 >= m) break;
+                init_vector_kernel<<<grid_for(n), spk::BLOCK, 0, st>>>(w, n, 0x5eedULL + 977ULL * (unsigned long long)(j + 1) + 131071ULL * (unsigned long long)restarts);
+                double r0 = 0.0, r1 = 0.0;
+                SP_CK(dots(w, 1, w, &r0));
+                for (int pass = 0; pass < 2; ++pass) {
+                    SP_CK(dots(V, j + 1, w, h2.data()));
+                    SP_CK(subtract(V, j + 1, h2.data(), w));
+                }
+                SP_CK(dots(w, 1, w, &r1));
+                if (!(r1 > 1e-16 * r0)) { mm = j + 1; break; }
+                scale_copy_kernel<<<grid_for(n), spk::BLOCK, 0, st>>>(w, n, 1.0 / std::sqrt(r1), w);
+                continue;
+            }
             scale_copy_kernel<<<grid_for(n), spk::BLOCK, 0, st>>>(w, n, 1.0 / beta, w);
         }
         // Ritz problem of the leading mm x mm block
@@ -359,10 +381,14 @@ cudaError_t spectral_lanczos(int n, const int *ptr, const int *adj_other, const 
         small_sym_eig(mm, Tm, theta, S);      // ascending; eigenvectors in columns of S (mm x mm row-major)
         const int want = std::min(nev, mm);
         int conv = 0;
+        // ARPACK's test with tol = machine epsilon (dsaupd, mdsctk.cpp:869-893): |r| <= tol * max(eps^(2/3), |theta|), plus
+        // the rounding floor eps * |A| below which no residual estimate means anything (small eigenvalues converge too)
+        double anorm = 0.0;
+        for (int i = 0; i < mm; ++i) anorm = std::max(anorm, std::fabs(theta[i]));
         for (int e = 0; e < want; ++e) {
             const int c = mm - 1 - e;
             const double r = std::fabs(beta_m * S[(size_t)(mm - 1) * mm + c]);
-            if (r <= tol * std::max(std::fabs(theta[c]), 1e-300)) ++conv;
+            if (r <= tol * std::max(std::fabs(theta[c]), 3.7e-11) + 4.5e-16 * anorm) ++conv;
         }
         *n_conv = conv;
         if (conv >= want || restarts >= max_restarts || mm < m) {
@@ -383,6 +409,7 @@ cudaError_t spectral_lanczos(int n, const int *ptr, const int *adj_other, const 
                 SP_CK(dots(W, 1, W, &r2));
                 residuals[e] = std::sqrt(std::max(r2, 0.0)) / std::fabs(evals[e]);
             }
+            if (want < nev) *n_conv = -1;      // fewer independent directions than requested pairs: the caller reports it
             break;
         }
         // thick restart: keep the k largest Ritz pairs and the residual vector

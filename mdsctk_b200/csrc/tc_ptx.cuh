@@ -35,6 +35,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Strictly non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is incomplete)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must trap, not hang the GPU.  try_wait suspends the thread in
 // hardware for up to the hint (ns) per poll, so the loop costs few issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag)
@@ -91,6 +104,12 @@ __device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *ma
         " [%0], [%1, {%3, %4, %5}], [%2], %6;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
+}
+// L2 prefetch of a tensor box (no shared-memory destination, no barrier): the sweep's producer warms the reference
+// tile it will stream a few passes later, so the ring's copies hit L2 instead of paying an HBM round trip each
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1,
                                                 uint64_t policy)
@@ -212,6 +231,124 @@ __device__ __forceinline__ void tc_mma2_lo(uint32_t d_tmem, uint32_t a_lo, uint3
             : "memory");
     }
 }
+// A operand in TENSOR MEMORY (the .ts form): a_tmem = TMEM address of this k-step's [128 lanes x 8 columns] block of
+// packed 16-bit pairs (lane = row of A in each CTA of the pair, column j = K elements 2j, 2j+1), B from shared memory.
+__device__ __forceinline__ void tc_mma2_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(acc), "r"(kDescHiSw64)
+        : "memory");
+}
+// One shared-memory stage of the resident-tile sweep (rms_tc2.cu) as ONE straight-line block: two k-steps x three
+// fit planes = six M=256 N=144 MMAs.  a0..a2: descriptor low words of the planes' A tiles at the first k-step (the second
+// is 32 bytes further, + 2), b: of the reference half-tile; d0: accumulator region of plane 0 (planes 1, 2 at + 144,
+// + 288 columns); acc0 = 0 starts a new accumulation.  Everything the tensor pipe needs differs from these by constants,
+// so the issuing thread spends ~2 instructions per MMA (it has 72 clk per MMA before it becomes the bottleneck).
+__device__ __forceinline__ void tc2_issue_stage_ss(uint32_t d0, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b, uint32_t idesc,
+                                                   uint32_t acc0)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b32 hi, d1, d2, x0, x1, x2, y;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b32 hi, 0x80004020;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 q, %0, %0;\n\t"
+        "add.u32 d1, %0, 144;\n\t"
+        "add.u32 d2, %0, 288;\n\t"
+        "add.u32 y, %4, 2;\n\t"
+        "add.u32 x0, %1, 2;\n\t"
+        "add.u32 x1, %2, 2;\n\t"
+        "add.u32 x2, %3, 2;\n\t"
+        "mov.b64 db, {%4, hi};\n\t"
+        "mov.b64 da, {%1, hi};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+        "mov.b64 da, {%2, hi};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [d1], da, db, %5, p;\n\t"
+        "mov.b64 da, {%3, hi};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [d2], da, db, %5, p;\n\t"
+        "mov.b64 db, {y, hi};\n\t"
+        "mov.b64 da, {x0, hi};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, q;\n\t"
+        "mov.b64 da, {x1, hi};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [d1], da, db, %5, q;\n\t"
+        "mov.b64 da, {x2, hi};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [d2], da, db, %5, q;\n\t"
+        "}"
+        ::"r"(d0), "r"(a0), "r"(a1), "r"(a2), "r"(b), "r"(idesc), "r"(acc0)
+        : "memory");
+}
+// Same with the three A operands in tensor memory (t0..t2: TMEM addresses of the first k-step, the second 8 columns
+// further); two = 0: only the first k-step exists (odd number of k-steps).
+__device__ __forceinline__ void tc2_issue_stage_ts(uint32_t d0, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t b, uint32_t idesc,
+                                                   uint32_t acc0, uint32_t two)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b32 hi, d1, d2, x0, x1, x2, y;\n\t"
+        ".reg .b64 db;\n\t"
+        "mov.b32 hi, 0x80004020;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "add.u32 d1, %0, 144;\n\t"
+        "add.u32 d2, %0, 288;\n\t"
+        "add.u32 y, %4, 2;\n\t"
+        "add.u32 x0, %1, 8;\n\t"
+        "add.u32 x1, %2, 8;\n\t"
+        "add.u32 x2, %3, 8;\n\t"
+        "mov.b64 db, {%4, hi};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %5, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [d1], [%2], db, %5, p;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [d2], [%3], db, %5, p;\n\t"
+        "mov.b64 db, {y, hi};\n\t"
+        "setp.eq.u32 p, %0, %0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [x0], db, %5, p;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [d1], [x1], db, %5, p;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [d2], [x2], db, %5, p;\n\t"
+        "}"
+        ::"r"(d0), "r"(t0), "r"(t1), "r"(t2), "r"(b), "r"(idesc), "r"(acc0), "r"(two)
+        : "memory");
+}
+// eight consecutive 32-bit columns of this thread's TMEM lane <- registers (operand staging; complete after tc_wait_st)
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// cluster-scope acquire wait: pairs with mbarrier.arrive.release.cluster of the peer CTA (data published through
+// distributed shared memory before the arrive is visible after the wait)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity, int tag)
+{
+    uint32_t polls = 0;
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (++polls > 200000000u) {
+            printf("tcgen05 sweep: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v)
+{
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+
 // four consecutive accumulator columns of this thread's TMEM lane -> v[c][0..3] (valid after tc_wait_ld)
 __device__ __forceinline__ void tc_ld4(uint32_t taddr, float (&v)[9][4], int c)
 {

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <iostream>
 #include <thread>
 
 namespace mdsctk_cli {
@@ -138,24 +139,50 @@ bool decode_frame(const unsigned char *p, int natoms, float *out)
 }
 
 struct MassEntry { const char *name; float mass; };
-const MassEntry kMassTable[] = {
-    {"Cl", 35.45300f}, {"Br", 79.90000f}, {"Na", 22.98970f}, {"Mg", 24.30500f}, {"Ca", 40.08000f},
-    {"Fe", 55.84700f}, {"Zn", 65.37000f}, {"Cu", 63.54600f}, {"Si", 28.08000f}, {"Al", 26.98150f},
+// element symbols in upper case (PDB / GRO atom names are upper case); values of GROMACS' atommass.dat
+const MassEntry kTwoLetter[] = {
+    {"CL", 35.45300f}, {"BR", 79.90000f}, {"NA", 22.98970f}, {"MG", 24.30500f}, {"CA", 40.08000f},
+    {"FE", 55.84700f}, {"ZN", 65.37000f}, {"CU", 63.54600f}, {"SI", 28.08000f}, {"AL", 26.98150f}, {"MN", 54.93800f}};
+const MassEntry kOneLetter[] = {
     {"H", 1.00790f},   {"C", 12.01070f},  {"N", 14.00670f},  {"O", 15.99940f},  {"S", 32.06500f},
     {"P", 30.97380f},  {"F", 18.99840f},  {"B", 10.81100f},  {"I", 126.90450f}, {"K", 39.10200f}};
 
-float mass_of(std::string name)
+std::string upper_trim(const std::string &in)
 {
+    std::string out;
+    for (char ch : in)
+        if (!std::isspace((unsigned char)ch)) out.push_back((char)std::toupper((unsigned char)ch));
+    return out;
+}
+
+bool lookup(const MassEntry *tab, size_t n, const std::string &sym, float *m)
+{
+    for (size_t i = 0; i < n; ++i)
+        if (sym == tab[i].name) { *m = tab[i].mass; return true; }
+    return false;
+}
+
+// Mass of an atom from what a PDB / GRO file says about it (the reference gets it from GROMACS' atommass lookup,
+// knn_rms.cpp:150-153).  `element`: the PDB element columns 77-78 when present; `two_letter`: the name is known to
+// start with a two-letter element symbol (PDB: the name starts in column 13; GRO: residue name == atom name, i.e. an
+// ion) -- that is what tells calcium "CA  " from the alpha carbon " CA ".  Unknown names get carbon's mass, with a
+// warning, instead of silently changing the centring.
+float mass_of(const std::string &raw_name, const std::string &element, bool two_letter)
+{
+    float m = 0.f;
+    const std::string el = upper_trim(element);
+    if (!el.empty() && (lookup(kTwoLetter, sizeof kTwoLetter / sizeof *kTwoLetter, el, &m) ||
+                        lookup(kOneLetter, sizeof kOneLetter / sizeof *kOneLetter, el, &m)))
+        return m;
+    std::string name = upper_trim(raw_name);
     size_t b = 0;
-    while (b < name.size() && (std::isspace((unsigned char)name[b]) || std::isdigit((unsigned char)name[b]))) ++b;
+    while (b < name.size() && std::isdigit((unsigned char)name[b])) ++b;     // "1HD1" style hydrogens
     name = name.substr(b);
-    float m = 12.011f;  // unknown names
-    size_t best = 0;
-    for (const auto &e : kMassTable) {
-        const size_t l = std::strlen(e.name);
-        if (l > best && name.compare(0, l, e.name) == 0) { best = l; m = e.mass; }
-    }
-    return m;
+    if (two_letter && name.size() >= 2 && lookup(kTwoLetter, sizeof kTwoLetter / sizeof *kTwoLetter, name.substr(0, 2), &m)) return m;
+    if (!name.empty() && lookup(kOneLetter, sizeof kOneLetter / sizeof *kOneLetter, name.substr(0, 1), &m)) return m;
+    static int warned = 0;
+    if (warned++ < 8) std::cerr << "WARNING: no mass known for atom name '" << raw_name << "': using 12.011 (give --mass-file)" << std::endl;
+    return 12.011f;
 }
 
 }  // namespace
@@ -224,14 +251,17 @@ bool read_topology_masses(const std::string &path, std::vector<float> *mass, std
         const int n = std::atoi(line.c_str());
         for (int i = 0; i < n && std::getline(f, line); ++i) {
             if (line.size() < 15) break;
-            mass->push_back(mass_of(line.substr(10, 5)));
+            // residue name == atom name: a monoatomic ion ("NA", "CL", "ZN", "CA" the calcium ion, ...)
+            mass->push_back(mass_of(line.substr(10, 5), "", upper_trim(line.substr(5, 5)) == upper_trim(line.substr(10, 5))));
         }
     } else {
         while (std::getline(f, line)) {
             if (line.compare(0, 6, "ENDMDL") == 0) break;   // first model only
             if (line.compare(0, 4, "ATOM") != 0 && line.compare(0, 6, "HETATM") != 0) continue;
             if (line.size() < 16) continue;
-            mass->push_back(mass_of(line.substr(12, 4)));
+            // a name that starts in column 13 is a two-letter element unless it is a four-character hydrogen name
+            const bool col13 = std::isalpha((unsigned char)line[12]) && !(line[12] == 'H' && line[15] != ' ');
+            mass->push_back(mass_of(line.substr(12, 4), line.size() >= 78 ? line.substr(76, 2) : std::string(), col13));
         }
     }
     if (mass->empty()) { *err = "no atoms found in " + path; return false; }

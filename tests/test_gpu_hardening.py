@@ -220,5 +220,5 @@ def test_c3_full_size_2000_random_rows_against_the_oracle():
     own = np.abs(d0 - d1[:256]) / d1[:256]
     same = i0 == i1[:256]
     assert (rel0 <= 1e-4).mean() > 0.99 and rel0.max() < 1e-3
-    assert (rel0 <= np.maximum(1e-4, own + 1e-8))[same].all()
+    assert (rel0 <= np.maximum(1e-4, 1.001 * own + 1e-7))[same].all()
     print("float chain vs GPU: max rel", rel0.max(), "chain's own max deviation from FP64", own[same].max(), "slots within 1e-4:", (rel0 <= 1e-4).mean())

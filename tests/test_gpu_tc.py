@@ -47,6 +47,33 @@ def test_tmem_accumulators_match_numpy(ctx, trpcage, kern, rtol):
     assert err.max() < rtol, f"max scaled error {err.max()}"
 
 
+@pytest.mark.parametrize("atoms,version", [(300, 2), (300, 1), (256, 2), (290, 2), (33, 2)])
+def test_tmem_accumulators_1xfp16_resident_tile(ctx, atoms, version):
+    """The default sweep (rms_tc2.cu) keeps the fit tile in shared memory and, beyond 256 atoms, its trailing k-steps in
+    TMEM (tcgen05.mma with the A operand in tensor memory): raw accumulators against numpy on the fp16-rounded operands."""
+    from mdsctk_b200 import synth
+    xyz = synth.traj_frames(400, atoms, 2, 9)
+    mass = (12.0 + np.arange(atoms) % 3).astype(np.float32)
+    ctx.set_option("rms_kernel", TC_F1)
+    ctx.set_option("sweep_version", version)
+    ctx.set_option("debug_tile", 1)
+    try:
+        ctx.rms_set_reference(xyz, mass)
+        ctx.rms_query(11)
+        assert ctx.stats()["sweep_version"] == version
+        tile = ctx.debug_fetch_tile()
+    finally:
+        ctx.set_option("debug_tile", 0)
+        ctx.set_option("sweep_version", 2)
+        ctx.set_option("rms_kernel", 0)
+    P = packed_planes(xyz, mass)
+    H = (P.astype(np.float32) * np.float32(64)).astype(np.float16).astype(np.float64) / 64.0      # what the tensor cores see
+    want = np.einsum("qna,jnb->qabj", H[:128], H[:48]).reshape(128, 9, 48)
+    scale = np.einsum("qna,jnb->qabj", np.abs(H[:128]), np.abs(H[:48])).reshape(128, 9, 48)
+    err = np.abs(tile - want) / scale.max()
+    assert err.max() < 5e-6, f"max scaled error {err.max()}"          # fp32 accumulation only: the operands are exact
+
+
 @pytest.mark.parametrize("kern", [TC_3X, TC_1X, TC_BF, TC_F3, TC_F2, TC_F1])
 @pytest.mark.parametrize("k", [10, 100])
 def test_trpcage_knn_rms_tc(ctx, trpcage, kern, k):

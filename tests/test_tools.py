@@ -148,3 +148,37 @@ def test_knn_data_tool_bit_identical(tmp_path):
     assert rc == 0, out
     dist, idx = read_like_make_sysparse(tmp_path / "distances.dat", tmp_path / "indices.dat", 10)
     assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
+
+
+def test_topology_masses_two_letter_elements_and_alpha_carbons(tmp_path):
+    """PDB / GRO atom names are upper case: " CA " (alpha carbon, column 14) is carbon, "CA  " (column 13) calcium;
+    ions and metals get their own masses (element columns 77-78 when present); nothing falls back silently."""
+    import subprocess
+    from mdsctk_b200 import build
+    build.build_tools()
+    tool = os.path.join(ROOT, "mdsctk_b200", "bin", "topology_masses")
+    pdb = tmp_path / "t.pdb"
+    pdb.write_text(
+        "ATOM      1  N   MET A   1      27.340  24.430   2.614  1.00  9.67           N  \n"
+        "ATOM      2  CA  MET A   1      26.266  25.413   2.842  1.00 10.38           C  \n"
+        "ATOM      3 HD11 LEU A   2      26.266  25.413   2.842  1.00 10.38\n"
+        "ATOM      4  SD  MET A   1      26.266  25.413   2.842  1.00 10.38\n"
+        "HETATM    5 CA    CA A 101      26.266  25.413   2.842  1.00 10.38          CA  \n"
+        "HETATM    6 ZN    ZN A 102      26.266  25.413   2.842  1.00 10.38\n"
+        "HETATM    7 FE   HEM A 103      26.266  25.413   2.842  1.00 10.38\n"
+        "HETATM    8 CL    CL A 104      26.266  25.413   2.842  1.00 10.38\n"
+        "HETATM    9 NA    NA A 105      26.266  25.413   2.842  1.00 10.38          NA  \n"
+        "HETATM   10 MG    MG A 106      26.266  25.413   2.842  1.00 10.38\n"
+        "END\n")
+    out = subprocess.run([tool, str(pdb)], capture_output=True, text=True, check=True).stdout.split()
+    got = [float(x) for x in out]
+    want = [14.0067, 12.0107, 1.0079, 32.065, 40.08, 65.37, 55.847, 35.453, 22.9897, 24.305]
+    assert np.allclose(got, want, atol=1e-3), got
+    gro = tmp_path / "t.gro"
+    gro.write_text("ions\n    4\n    1MET     CA    1   0.100   0.200   0.300\n    2CA      CA    2   0.100   0.200   0.300\n"
+                   "    3ZN      ZN    3   0.100   0.200   0.300\n    4ALA    HB1    4   0.100   0.200   0.300\n   1.0 1.0 1.0\n")
+    out = subprocess.run([tool, str(gro)], capture_output=True, text=True, check=True).stdout.split()
+    assert np.allclose([float(x) for x in out], [12.0107, 40.08, 65.37, 1.0079], atol=1e-3), out
+    # the trp-cage topology of the reference's examples: N / CA / C backbone only
+    out = subprocess.run([tool, os.path.join(DATA, "trp-cage.pdb")], capture_output=True, text=True, check=True).stdout.split()
+    assert len(out) == 60 and sorted(set(out)) == ["12.01070", "14.00670"]

@@ -7,6 +7,7 @@
 // (mdsctk.cpp:330-360 arithmetic kept operation for operation in FP64 on the GPU).
 #include "../../include/mdsctk_knn.h"
 #include "options.hpp"
+#include "replicate_nccl.hpp"
 
 #include <cuda_runtime.h>
 
@@ -124,12 +125,23 @@ int main(int argc, char *argv[])
     cudaGetDeviceCount(&ndev);
     ngpus = std::max(1, std::min(ngpus, std::max(ndev, 1)));
     std::vector<mdsctk_knn_ctx *> ctx(ngpus, nullptr);
-    for (int g = 0; g < ngpus; ++g) {
+    for (int g = 0; g < ngpus; ++g)
         if (mdsctk_knn_create(&ctx[g], g) != 0) { std::cout << "ERROR: " << mdsctk_knn_last_error(nullptr) << std::endl; return 5; }
-        if (mdsctk_knn_data_set_reference(ctx[g], ref.data(), n_ref, vector_size) != 0) {
-            std::cout << "ERROR: " << mdsctk_knn_last_error(ctx[g]) << std::endl;
-            return 5;
-        }
+    {
+        // every GPU uploads its own shard of the reference rows, NCCL replicates them (replicate_nccl.hpp)
+        std::string rerr;
+        double nccl_ms = 0.0;
+        const bool ok = replicate_reference_nccl(
+            ngpus, n_ref,
+            [&](int g, ShardRange s) {
+                int rc = mdsctk_knn_data_alloc_reference(ctx[g], n_ref, vector_size);
+                if (rc == 0 && s.count > 0) rc = mdsctk_knn_data_upload_shard(ctx[g], ref.data() + (size_t)s.begin * vector_size, s.begin, s.count);
+                return rc;
+            },
+            [&](int g, void **ptrs, size_t *bpr, int *na) { return mdsctk_knn_data_reference_arrays(ctx[g], 16, na, ptrs, bpr); },
+            [&](int g) { return mdsctk_knn_last_error(ctx[g]); }, &rerr, &nccl_ms);
+        if (!ok) { std::cout << "ERROR: " << rerr << std::endl; return 5; }
+        if (ngpus > 1) std::cout << "Reference rows uploaded on " << ngpus << " GPUs and replicated with NCCL in " << nccl_ms << " ms." << std::endl;
     }
     const int metric = corr ? MDSCTK_KNN_CORRELATION : MDSCTK_KNN_EUCLIDEAN;
     if (!sort) {

@@ -14,6 +14,7 @@
 // reference writes an uninitialised index vector), and two options are new: --gpus, --mass-file.
 #include "../../include/mdsctk_knn.h"
 #include "options.hpp"
+#include "replicate_nccl.hpp"
 #include "trajectory.hpp"
 
 #include <cuda_runtime.h>
@@ -36,33 +37,21 @@ struct Gpu {
 
 bool replicate_reference(std::vector<Gpu> &gpus, const float *xyz, long long n, int natoms, const float *mass)
 {
-    // GPU 0 packs; the others receive the packed arrays peer-to-peer (NVLink), no second H2D / pack.
-    if (mdsctk_knn_rms_set_reference(gpus[0].ctx, xyz, n, natoms, mass) != 0) {
-        std::cout << "ERROR: " << mdsctk_knn_last_error(gpus[0].ctx) << std::endl;
-        return false;
-    }
-    void *src[16];
-    size_t bpf[16];
-    int na = 0;
-    if (gpus.size() > 1 && mdsctk_knn_rms_reference_arrays(gpus[0].ctx, 16, &na, src, bpf) != 0) return false;
-    for (size_t g = 1; g < gpus.size(); ++g) {
-        void *dst[16];
-        size_t b2[16];
-        int nb = 0;
-        if (mdsctk_knn_rms_alloc_reference(gpus[g].ctx, n, natoms, mass) != 0 ||
-            mdsctk_knn_rms_reference_arrays(gpus[g].ctx, 16, &nb, dst, b2) != 0 || nb != na) {
-            std::cout << "ERROR: " << mdsctk_knn_last_error(gpus[g].ctx) << std::endl;
-            return false;
-        }
-        for (int a = 0; a < na; ++a) {
-            cudaError_t e = cudaMemcpyPeer(dst[a], gpus[g].dev, src[a], gpus[0].dev, bpf[a] * (size_t)n);
-            if (e != cudaSuccess) {
-                std::cout << "ERROR: cudaMemcpyPeer: " << cudaGetErrorString(e) << std::endl;
-                return false;
-            }
-        }
-    }
-    return true;
+    // every GPU uploads + packs its own shard of the reference frames, NCCL replicates the packed arrays (replicate_nccl.hpp)
+    std::string err;
+    double nccl_ms = 0.0;
+    const bool ok = replicate_reference_nccl(
+        (int)gpus.size(), n,
+        [&](int g, ShardRange s) {
+            int rc = mdsctk_knn_rms_alloc_reference(gpus[g].ctx, n, natoms, mass);
+            if (rc == 0 && s.count > 0) rc = mdsctk_knn_rms_pack_shard(gpus[g].ctx, xyz + (size_t)s.begin * natoms * 3, s.begin, s.count);
+            return rc;
+        },
+        [&](int g, void **ptrs, size_t *bpf, int *na) { return mdsctk_knn_rms_reference_arrays(gpus[g].ctx, 16, na, ptrs, bpf); },
+        [&](int g) { return mdsctk_knn_last_error(gpus[g].ctx); }, &err, &nccl_ms);
+    if (!ok) std::cout << "ERROR: " << err << std::endl;
+    else if (gpus.size() > 1) std::cout << "Reference set packed on " << gpus.size() << " GPUs and replicated with NCCL in " << nccl_ms << " ms." << std::endl;
+    return ok;
 }
 
 }  // namespace

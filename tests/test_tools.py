@@ -182,3 +182,40 @@ def test_topology_masses_two_letter_elements_and_alpha_carbons(tmp_path):
     # the trp-cage topology of the reference's examples: N / CA / C backbone only
     out = subprocess.run([tool, os.path.join(DATA, "trp-cage.pdb")], capture_output=True, text=True, check=True).stdout.split()
     assert len(out) == 60 and sorted(set(out)) == ["12.01070", "14.00670"]
+
+
+def _n_gpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+        return sum(1 for ln in out.splitlines() if ln.startswith("GPU "))
+    except (OSError, subprocess.SubprocessError):
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", [2, 4])
+def test_tools_with_several_gpus_write_identical_files(tmp_path, gpus):
+    """knn_rms / knn_data --gpus N: every GPU packs its own shard, NCCL replicates the packed reference set, fit rows
+    are sharded (knn_rms.cpp:268-279: rows are independent) -- the files must be byte-identical to the one-GPU run."""
+    if _n_gpus() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    outs = {}
+    for g in (1, gpus):
+        d = tmp_path / f"g{g}"
+        d.mkdir()
+        rc, out = run("knn_rms", "-k", "10", "-g", str(g), "-p", os.path.join(DATA, "trp-cage.pdb"),
+                      "-r", os.path.join(DATA, "trp-cage.xtc"), cwd=d)
+        assert rc == 0, out
+        if g > 1:
+            assert "replicated with NCCL" in out
+        rc, out = run("knn_rms", "-k", "10", "-g", str(g), "-p", os.path.join(DATA, "trp-cage.pdb"),
+                      "-r", os.path.join(DATA, "trp-cage.xtc"), "-f", os.path.join(DATA, "trp-cage-outofsample.xtc"),
+                      "-d", "oos_d.dat", "-i", "oos_i.dat", cwd=d)
+        assert rc == 0, out
+        rc, out = run("knn_data", "-k", "10", "-v", "3", "-g", str(g), "-r", os.path.join(DATA, "swissroll.pts"),
+                      "-d", "sw_d.dat", "-i", "sw_i.dat", cwd=d)
+        assert rc == 0, out
+        outs[g] = {f: (d / f).read_bytes() for f in ("distances.dat", "indices.dat", "oos_d.dat", "oos_i.dat", "sw_d.dat", "sw_i.dat")}
+    for f, blob in outs[1].items():
+        assert blob == outs[gpus][f], f
+    assert len(outs[1]["oos_i.dat"]) == 10000 * 10 * 4

@@ -200,6 +200,12 @@ class Dist:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
+            # connection set-up happens on the first collective: keep it out of every timed all-gather
+            t = torch.ones(1 << 20, dtype=torch.uint8, device=self.dev)
+            g = torch.empty(world << 20, dtype=torch.uint8, device=self.dev)
+            dist.all_gather_into_tensor(g, t)
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
 
     def barrier(self):
         self.torch.cuda.synchronize()

@@ -157,7 +157,8 @@ struct mdsctk_knn_ctx {
     DevBuf dt_ref_hi, dt_ref_lo, dt_ref_norm, dt_fit_hi, dt_fit_lo, dt_fit_norm;
     DevBuf dt_ref_norm1, dt_ref_g, dt_fit_norm1, dt_fit_g;   // one-part filter: norms of the hi parts, rounding residual norms
     float dt_g_ref_max = 0.f;
-    DevBuf fb_rows, fb_key, fb_idx, fb_cnt, fb_tau, fb_dist, fb_oidx;
+    DevBuf fb_rows, fb_key, fb_idx, fb_cnt, fb_tau, fb_dist, fb_oidx, fb_stats;
+    int dt_metric = MDSCTK_KNN_EUCLIDEAN;   // metric the packed filter operands were built for
     bool dpack_dirty = true;
     double dt_scale = 1.0, dt_ref_maxabs = 0.0;
     float dt_rnorm_max = 0.f;
@@ -540,17 +541,31 @@ int rms_run(mdsctk_knn_ctx *ctx, FrameSet &fitset, long long fit_begin, long lon
 
 // Euclidean knn_data through the tensor-core filter (data_tc.cu): pack -> sweep -> exact FP64 re-score
 // with certificate -> exact FP64 sweep of the rows that could not be certified.
-int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1)
+int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long long fit_begin, long long n_fit, int k1,
+                int metric, const double *fit_stats, const double *ref_stats)
 {
+    // correlation metric (knn_data -c): the same filter on the standardised rows (unit vectors: |z_x - z_y|^2 is four times
+    // the squared correlation distance), exact re-score with correlation_distance's own arithmetic
+    const bool corr = metric == MDSCTK_KNN_CORRELATION;
+    if (ctx->dt_metric != metric) { ctx->dpack_dirty = true; ctx->dt_metric = metric; }
     mdsctk_knn_stats &S = ctx->stats;
     const int dim = ctx->ddim, D_pad = data_tc_pad_dim(dim);
     const long long n_ref = ctx->dn_ref;
     CK(ctx->scalars.reserve(64), "cudaMalloc(scalars)");
     ctx->tm.start(ctx->st);
     if (ctx->dpack_dirty) {
-        CK(launch_data_maxabs(ctx->d_ref.as<double>(), (size_t)n_ref * dim, ctx->scalars.as<double>(), ctx->st), "maxabs");
-        CK(cudaMemcpyAsync(&ctx->dt_ref_maxabs, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, ctx->st), "D2H maxabs");
-        CK(cudaStreamSynchronize(ctx->st), "sync maxabs");
+        if (corr) {
+            int bad = 0;
+            CK(launch_data_stats_check(ref_stats, n_ref, ctx->scalars.as<int>() + 12, ctx->st), "stats check");
+            CK(cudaMemcpyAsync(&bad, ctx->scalars.as<int>() + 12, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H stats check");
+            CK(cudaStreamSynchronize(ctx->st), "sync stats check");
+            if (bad) return 1;                       // constant / non-finite rows: the exact sweep handles them
+            ctx->dt_ref_maxabs = 1.0;                // standardised rows are unit vectors
+        } else {
+            CK(launch_data_maxabs(ctx->d_ref.as<double>(), (size_t)n_ref * dim, ctx->scalars.as<double>(), ctx->st), "maxabs");
+            CK(cudaMemcpyAsync(&ctx->dt_ref_maxabs, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, ctx->st), "D2H maxabs");
+            CK(cudaStreamSynchronize(ctx->st), "sync maxabs");
+        }
         // power-of-two scale that puts the largest reference value near 1024 (fp16 keeps 11 bits below it)
         int e = 0;
         if (ctx->dt_ref_maxabs > 0.0 && std::isfinite(ctx->dt_ref_maxabs)) e = 10 - (int)std::ceil(std::log2(ctx->dt_ref_maxabs));
@@ -563,7 +578,7 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
         CK(ctx->dt_ref_norm1.reserve((size_t)(n_ref + 512) * 4), "cudaMalloc(ref norm1)");
         CK(cudaMemsetAsync(ctx->dt_ref_norm1.p, 0, (size_t)(n_ref + 512) * 4, ctx->st), "memset ref norm1");
         CK(ctx->dt_ref_g.reserve((size_t)n_ref * 4), "cudaMalloc(ref g)");
-        CK(launch_data_pack(ctx->d_ref.as<double>(), n_ref, dim, D_pad, ctx->dt_scale, ctx->dt_ref_hi.p, ctx->dt_ref_lo.p,
+        CK(launch_data_pack(ctx->d_ref.as<double>(), n_ref, dim, D_pad, ctx->dt_scale, corr ? ref_stats : nullptr, ctx->dt_ref_hi.p, ctx->dt_ref_lo.p,
                             ctx->dt_ref_norm.as<float>(), ctx->dt_ref_norm1.as<float>(), ctx->dt_ref_g.as<float>(), ctx->st),
            "data_pack(ref)");
         CK(launch_max_float(ctx->dt_ref_norm.as<float>(), n_ref, ctx->scalars.as<float>() + 4, ctx->st), "max(norm)");
@@ -585,16 +600,25 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
         fit_g = ctx->dt_ref_g.as<float>() + fit_begin;
     } else {
         double fit_max = 0.0;
-        CK(launch_data_maxabs(d_fit, (size_t)n_fit * dim, ctx->scalars.as<double>(), ctx->st), "maxabs(fit)");
-        CK(cudaMemcpyAsync(&fit_max, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, ctx->st), "D2H maxabs");
-        CK(cudaStreamSynchronize(ctx->st), "sync maxabs");
+        if (corr) {
+            int bad = 0;
+            CK(launch_data_stats_check(fit_stats, n_fit, ctx->scalars.as<int>() + 12, ctx->st), "stats check(fit)");
+            CK(cudaMemcpyAsync(&bad, ctx->scalars.as<int>() + 12, 4, cudaMemcpyDeviceToHost, ctx->st), "D2H stats check");
+            CK(cudaStreamSynchronize(ctx->st), "sync stats check");
+            if (bad) return 1;
+            fit_max = 1.0;
+        } else {
+            CK(launch_data_maxabs(d_fit, (size_t)n_fit * dim, ctx->scalars.as<double>(), ctx->st), "maxabs(fit)");
+            CK(cudaMemcpyAsync(&fit_max, ctx->scalars.p, 8, cudaMemcpyDeviceToHost, ctx->st), "D2H maxabs");
+            CK(cudaStreamSynchronize(ctx->st), "sync maxabs");
+        }
         if (!(fit_max * ctx->dt_scale < 3.0e4)) return 1;   // would overflow fp16: the caller takes the exact path
         CK(ctx->dt_fit_hi.reserve((size_t)n_fit * D_pad * 2), "cudaMalloc(fit hi)");
         CK(ctx->dt_fit_lo.reserve((size_t)n_fit * D_pad * 2), "cudaMalloc(fit lo)");
         CK(ctx->dt_fit_norm.reserve((size_t)(n_fit + 512) * 4), "cudaMalloc(fit norm)");
         CK(ctx->dt_fit_norm1.reserve((size_t)(n_fit + 512) * 4), "cudaMalloc(fit norm1)");
         CK(ctx->dt_fit_g.reserve((size_t)n_fit * 4), "cudaMalloc(fit g)");
-        CK(launch_data_pack(d_fit, n_fit, dim, D_pad, ctx->dt_scale, ctx->dt_fit_hi.p, ctx->dt_fit_lo.p,
+        CK(launch_data_pack(d_fit, n_fit, dim, D_pad, ctx->dt_scale, corr ? fit_stats : nullptr, ctx->dt_fit_hi.p, ctx->dt_fit_lo.p,
                             ctx->dt_fit_norm.as<float>(), ctx->dt_fit_norm1.as<float>(), ctx->dt_fit_g.as<float>(), ctx->st),
            "data_pack(fit)");
         fit_hi = ctx->dt_fit_hi.p; fit_lo = ctx->dt_fit_lo.p; fit_norm = ctx->dt_fit_norm.as<float>();
@@ -641,7 +665,8 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
     ctx->tm.start(ctx->st);
     S.cert_gres = one ? (double)ctx->dt_g_ref_max : 0.0;
     CK(launch_data_rescore(d_fit, ctx->d_ref.as<double>(), n_fit, dim, k1, cl, eps_rel, fit_norm, ctx->dt_scale,
-                           ctx->dt_rnorm_max, one ? fit_g : nullptr, ctx->dt_g_ref_max, (ctx->out_dist.as<double>() + (size_t)ctx->out_off * k1), (ctx->out_idx.as<int>() + (size_t)ctx->out_off * k1), ctx->flags.as<int>(), d_err,
+                           ctx->dt_rnorm_max, one ? fit_g : nullptr, ctx->dt_g_ref_max, corr ? fit_stats : nullptr, corr ? ref_stats : nullptr,
+                           (ctx->out_dist.as<double>() + (size_t)ctx->out_off * k1), (ctx->out_idx.as<int>() + (size_t)ctx->out_off * k1), ctx->flags.as<int>(), d_err,
                            d_nbad, ctx->bad_rows.as<int>(), ctx->st), "data_rescore");
     struct { double pad, err, spread, done_max; int nbad; } host_sc;
     CK(cudaMemcpyAsync(&host_sc, ctx->scalars.p, sizeof(host_sc), cudaMemcpyDeviceToHost, ctx->st), "D2H scalars");
@@ -668,8 +693,14 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
         CandLists<double> fl;
         fl.key = ctx->fb_key.as<double>(); fl.idx = ctx->fb_idx.as<int>(); fl.cnt = ctx->fb_cnt.as<int>();
         fl.tau = ctx->fb_tau.as<double>(); fl.cap = fcap; fl.keep = fkeep; fl.H = 1;
-        CK(launch_data_sweep(ctx->fb_rows.as<double>(), nullptr, nb, ctx->d_ref.as<double>(), nullptr, n_ref, dim,
-                             MDSCTK_KNN_EUCLIDEAN, fl, ctx->st), "data_sweep(fallback)");
+        const double *fb_stats = nullptr;
+        if (corr) {
+            CK(ctx->fb_stats.reserve((size_t)nb * 16), "cudaMalloc(fb_stats)");
+            CK(launch_data_rowstats(ctx->fb_rows.as<double>(), nb, dim, ctx->fb_stats.as<double>(), ctx->st), "data_rowstats(fallback)");
+            fb_stats = ctx->fb_stats.as<double>();
+        }
+        CK(launch_data_sweep(ctx->fb_rows.as<double>(), fb_stats, nb, ctx->d_ref.as<double>(), corr ? ref_stats : nullptr, n_ref, dim,
+                             metric, fl, ctx->st), "data_sweep(fallback)");
         CK(launch_data_finalize(fl, nb, k1, ctx->fb_dist.as<double>(), ctx->fb_oidx.as<int>(), ctx->st), "data_finalize(fallback)");
         CK(launch_data_scatter_out(ctx->fb_dist.as<double>(), ctx->fb_oidx.as<int>(), ctx->bad_rows.as<int>(), nb, k1,
                                    (ctx->out_dist.as<double>() + (size_t)ctx->out_off * k1), (ctx->out_idx.as<int>() + (size_t)ctx->out_off * k1), ctx->st), "scatter rows");
@@ -688,14 +719,6 @@ int data_run_block(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, lo
     S.pairs = n_fit * ctx->dn_ref; S.launches = 0; S.fallback_rows = 0; S.max_filter_err = 0; S.cert_eps = 0;
     const int dim = ctx->ddim;
     S.max_filter_spread = 0; S.rescored_max = 0; S.lists_per_row = 1;
-    // tensor-core filter: Euclidean metric; by default only where the contraction is worth staging
-    const bool want_tc = metric == MDSCTK_KNN_EUCLIDEAN &&
-                         (ctx->data_kernel >= 1 ||
-                          (ctx->data_kernel < 0 && dim >= 8 && (double)n_fit * (double)ctx->dn_ref >= 2.5e7));
-    if (want_tc) {
-        const int rc = data_run_tc(ctx, d_fit, fit_is_ref, fit_begin, n_fit, k1);
-        if (rc != 1) return rc;        // 1: not applicable to this input -> exact sweep below
-    }
     const double *fit_stats = nullptr, *ref_stats = nullptr;
     if (metric == MDSCTK_KNN_CORRELATION) {
         if (ctx->dstats_dirty) {
@@ -714,6 +737,13 @@ int data_run_block(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, lo
             fit_stats = ctx->d_fit_stats.as<double>();
             S.launches++;
         }
+    }
+    // tensor-core filter (both metrics: correlation = Euclidean on the standardised rows); by default only where the
+    // contraction is worth staging
+    const bool want_tc = ctx->data_kernel >= 1 || (ctx->data_kernel < 0 && dim >= 8 && (double)n_fit * (double)ctx->dn_ref >= 2.5e7);
+    if (want_tc) {
+        const int rc = data_run_tc(ctx, d_fit, fit_is_ref, fit_begin, n_fit, k1, metric, fit_stats, ref_stats);
+        if (rc != 1) return rc;        // 1: not applicable to this input -> exact sweep below
     }
     const long long slack = ctx->slack >= 0 ? ctx->slack : 8;
     const int keep = (int)(((long long)k1 + slack + 7) / 8 * 8);
@@ -841,7 +871,7 @@ void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx)
     ctx->out_dist.release(); ctx->out_idx.release(); ctx->debug_tile.release(); ctx->row_tau.release(); ctx->own_tile.release();
     for (DevBuf *b2 : {&ctx->dt_ref_hi, &ctx->dt_ref_lo, &ctx->dt_ref_norm, &ctx->dt_fit_hi, &ctx->dt_fit_lo, &ctx->dt_fit_norm,
                        &ctx->dt_ref_norm1, &ctx->dt_ref_g, &ctx->dt_fit_norm1, &ctx->dt_fit_g, &ctx->fb_rows, &ctx->fb_key,
-                       &ctx->fb_idx, &ctx->fb_cnt, &ctx->fb_tau, &ctx->fb_dist, &ctx->fb_oidx, &ctx->c_idx, &ctx->c_dist,
+                       &ctx->fb_idx, &ctx->fb_cnt, &ctx->fb_tau, &ctx->fb_dist, &ctx->fb_oidx, &ctx->fb_stats, &ctx->c_idx, &ctx->c_dist,
                        &ctx->c_ints, &ctx->c_key, &ctx->c_val, &ctx->c_irow, &ctx->c_oval, &ctx->f_in, &ctx->f_ang, &ctx->f_sc,
                        &ctx->audit_ids, &ctx->audit_seq, &ctx->audit_dist, &ctx->audit_idx, &ctx->s_int, &ctx->s_val, &ctx->s_vec, &ctx->s_basis, &ctx->s_rot, &ctx->s_small, &ctx->s_evec})
         b2->release();

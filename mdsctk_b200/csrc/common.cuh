@@ -127,8 +127,10 @@ cudaError_t launch_data_finalize(CandLists<double> cl, long long n_fit, int k1, 
 // Vector path, tensor-core filter + exact FP64 re-score (data_tc.cu).
 cudaError_t launch_data_maxabs(const double *v, size_t n, double *out, cudaStream_t st);
 // norm1 / gres (may be NULL): |hi|^2 (scaled units) and |x - hi/scale| (input units, rounded up) for the one-part filter
-cudaError_t launch_data_pack(const double *rows, long long n, int dim, int D_pad, double scale, void *hi, void *lo,
-                             float *norm, float *norm1, float *gres, cudaStream_t st);
+// stats != NULL: pack the STANDARDISED rows (v - mean) / (spread sqrt(dim - 1)) (correlation metric)
+cudaError_t launch_data_pack(const double *rows, long long n, int dim, int D_pad, double scale, const double *stats, void *hi,
+                             void *lo, float *norm, float *norm1, float *gres, cudaStream_t st);
+cudaError_t launch_data_stats_check(const double *stats, long long n, int *bad, cudaStream_t st);   // rows with a zero / non-finite spread
 int data_tc_pad_dim(int dim);
 int data_tc_list_stride(int keep);
 int data_tc_choose_segments(long long n_fit, long long n_ref, int n_sms);
@@ -139,8 +141,8 @@ cudaError_t launch_data_sweep_tc(const void *fit_hi, const void *fit_lo, const f
                                  int one_part, int n_sms, cudaStream_t st);
 cudaError_t launch_data_rescore(const double *fit, const double *ref, long long n_fit, int dim, int k1, CandLists<float> cl,
                                 double eps_rel, const float *q_norm, double scale, float r_norm_max, const float *q_g,
-                                float g_ref_max, double *out_dist, int *out_idx, int *flags, double *err_stats, int *n_bad,
-                                int *bad_rows, cudaStream_t st);
+                                float g_ref_max, const double *fit_stats, const double *ref_stats, double *out_dist, int *out_idx,
+                                int *flags, double *err_stats, int *n_bad, int *bad_rows, cudaStream_t st);
 cudaError_t launch_data_gather_rows(const double *src, const int *ids, int n_rows, int dim, double *dst, cudaStream_t st);
 cudaError_t launch_data_scatter_out(const double *d_src, const int *i_src, const int *ids, int n_rows, int k1, double *d_dst,
                                     int *i_dst, cudaStream_t st);

@@ -70,9 +70,12 @@ cudaError_t launch_data_maxabs(const double *v, size_t n, double *out, cudaStrea
 }
 
 // one warp per row
+// stats != NULL (knn_data -c): the packed row is the STANDARDISED row z = (v - mean) / (spread sqrt(dim - 1)) -- a unit
+// vector whose Euclidean distances are the correlation distances: |z_x - z_y|^2 = 2 - 2 r = 4 ((1 - r) / 2), the square
+// of twice what correlation_distance (mdsctk.cpp:337-360) returns.  So the Euclidean tensor filter serves both metrics.
 __global__ void __launch_bounds__(256) data_pack_kernel(const double *__restrict__ rows, long long n, int dim, int D_pad,
-                                                        double scale, __half *__restrict__ hi, __half *__restrict__ lo,
-                                                        float *__restrict__ norm, float *__restrict__ norm1,
+                                                        double scale, const double *__restrict__ stats, __half *__restrict__ hi,
+                                                        __half *__restrict__ lo, float *__restrict__ norm, float *__restrict__ norm1,
                                                         float *__restrict__ gres)
 {
     const int lane = threadIdx.x & 31;
@@ -80,10 +83,12 @@ __global__ void __launch_bounds__(256) data_pack_kernel(const double *__restrict
     if (r >= n) return;
     const double *v = rows + (size_t)r * dim;
     double nn = 0.0, n1 = 0.0, r1 = 0.0;
+    const double mean = stats ? stats[2 * r] : 0.0;
+    const double mul = stats ? scale / (stats[2 * r + 1] * sqrt((double)dim - 1.0)) : scale;
     for (int x = lane; x < D_pad; x += 32) {
         float h = 0.0f, l = 0.0f;
         if (x < dim) {
-            const double sv = v[x] * scale;
+            const double sv = (v[x] - mean) * mul;
             nn += sv * sv;
             const __half hh = __float2half_rn((float)sv);
             h = __half2float(hh);
@@ -109,12 +114,30 @@ __global__ void __launch_bounds__(256) data_pack_kernel(const double *__restrict
     }
 }
 
-cudaError_t launch_data_pack(const double *rows, long long n, int dim, int D_pad, double scale, void *hi, void *lo,
-                             float *norm, float *norm1, float *gres, cudaStream_t st)
+cudaError_t launch_data_pack(const double *rows, long long n, int dim, int D_pad, double scale, const double *stats, void *hi,
+                             void *lo, float *norm, float *norm1, float *gres, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    data_pack_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(rows, n, dim, D_pad, scale, static_cast<__half *>(hi),
+    data_pack_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(rows, n, dim, D_pad, scale, stats, static_cast<__half *>(hi),
                                                                static_cast<__half *>(lo), norm, norm1, gres);
+    return cudaGetLastError();
+}
+
+// rows whose spread is zero or not finite (constant rows, NaNs): correlation_distance divides by it, and such inputs
+// are left to the exact FP64 sweep, which reproduces whatever the reference's arithmetic makes of them
+__global__ void data_stats_check_kernel(const double *__restrict__ stats, long long n, int *bad)
+{
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const double sp = stats[2 * r + 1], mean = stats[2 * r];
+        if (!(sp > 0.0) || !(sp < 1.0e300) || !(fabs(mean) < 1.0e300)) atomicAdd(bad, 1);
+    }
+}
+
+cudaError_t launch_data_stats_check(const double *stats, long long n, int *bad, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(int), st);
+    if (e != cudaSuccess || n <= 0) return e;
+    data_stats_check_kernel<<<296, 256, 0, st>>>(stats, n, bad);
     return cudaGetLastError();
 }
 
@@ -488,6 +511,7 @@ struct DataRescoreArgs {
     float inv_scale2, r_norm_max;
     const float *q_g;                 // one-part filter: residual norm |x - hi/s| of every fit row (input units), else NULL
     float g_ref_max;                  // ... and the largest one of the reference set
+    const double *fit_stats, *ref_stats;   // correlation metric: (mean, spread) per row, else NULL (Euclidean)
     double *out_dist;
     int *out_idx, *flags, *n_bad, *bad_rows;
     double *err_stats;
@@ -547,6 +571,11 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
 
     const double nq = (double)a.q_norm[q] * (double)a.inv_scale2;
     const double grd = a.q_g ? (double)a.q_g[q] + (double)a.g_ref_max : 0.0;
+    // correlation metric: exact key = 4 * correlation_distance^2 (the squared distance of the standardised rows the filter
+    // contracted; the factor 4 is exact), computed in the reference's own order: sum (reference[x] - rmean) (fitting[x] - fmean)
+    // left to right, then (1 - sum / ((n - 1) rs fs)) / 2 clamped at 0 (mdsctk.cpp:353-358; "reference" = the fit row)
+    const bool corr = a.fit_stats != nullptr;
+    const double fm = corr ? a.fit_stats[2 * q] : 0.0, fs = corr ? a.fit_stats[2 * q + 1] : 1.0;
     const double eps_max = a.eps_rel * (nq + (double)a.r_norm_max * (double)a.inv_scale2);
     double eps = eps_max;
     int done = 0;
@@ -566,12 +595,25 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
             __syncthreads();
             if (threadIdx.x < nb) {
                 const double *rc = s_chunk + threadIdx.x * (DCHUNK + 1);
-                for (int x = 0; x < w; ++x) {
-                    const double d = __dsub_rn(fq[x0 + x], rc[x]);
-                    sum = __dadd_rn(sum, __dmul_rn(d, d));
+                if (!corr) {
+                    for (int x = 0; x < w; ++x) {
+                        const double d = __dsub_rn(fq[x0 + x], rc[x]);
+                        sum = __dadd_rn(sum, __dmul_rn(d, d));
+                    }
+                } else {
+                    const double rm = a.ref_stats[2 * (size_t)u_i[done + threadIdx.x]];
+                    for (int x = 0; x < w; ++x)
+                        sum = __dadd_rn(sum, __dmul_rn(__dsub_rn(fq[x0 + x], fm), __dsub_rn(rc[x], rm)));
                 }
             }
             __syncthreads();
+        }
+        if (corr && threadIdx.x < nb) {
+            const double rs = a.ref_stats[2 * (size_t)u_i[done + threadIdx.x] + 1];
+            const double den = __dmul_rn(__dmul_rn(__dsub_rn((double)D, 1.0), fs), rs);
+            double v = __ddiv_rn(__dsub_rn(1.0, __ddiv_rn(sum, den)), 2.0);
+            if (v < 0.0) v = 0.0;
+            sum = 4.0 * v;
         }
         if (threadIdx.x < nb) {
             u_key[done + threadIdx.x] = sum;
@@ -632,7 +674,7 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
     if (total == 0 && threadIdx.x == 0) s_ok = 0;
     // the CPU tool takes sqrt of every entry before it sorts; sqrt is monotone, ties keep index order
     for (int j = threadIdx.x; j < k1; j += blockDim.x) {
-        a.out_dist[(size_t)q * k1 + j] = sqrt(s_d[j]);
+        a.out_dist[(size_t)q * k1 + j] = sqrt(corr ? 0.25 * s_d[j] : s_d[j]);
         a.out_idx[(size_t)q * k1 + j] = s_i[j];
     }
     if (threadIdx.x == 0) {
@@ -656,11 +698,12 @@ __global__ void __launch_bounds__(128) data_rescore_kernel(DataRescoreArgs a)
 
 cudaError_t launch_data_rescore(const double *fit, const double *ref, long long n_fit, int dim, int k1, CandLists<float> cl,
                                 double eps_rel, const float *q_norm, double scale, float r_norm_max, const float *q_g,
-                                float g_ref_max, double *out_dist, int *out_idx, int *flags, double *err_stats, int *n_bad,
-                                int *bad_rows, cudaStream_t st)
+                                float g_ref_max, const double *fit_stats, const double *ref_stats, double *out_dist, int *out_idx,
+                                int *flags, double *err_stats, int *n_bad, int *bad_rows, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
     DataRescoreArgs a;
+    a.fit_stats = fit_stats; a.ref_stats = ref_stats;
     a.fit = fit; a.ref = ref; a.n_fit = n_fit; a.dim = dim; a.k1 = k1; a.cl = cl; a.eps_rel = eps_rel; a.q_norm = q_norm;
     a.inv_scale2 = (float)(1.0 / (scale * scale)); a.r_norm_max = r_norm_max; a.out_dist = out_dist; a.out_idx = out_idx;
     a.q_g = q_g; a.g_ref_max = g_ref_max;

@@ -120,3 +120,46 @@ def test_one_part_filter_gives_the_same_bytes():
         dist, idx = mdsctk_b200.knn_data(rows[:3000], 20, fit_rows=rows[5000:5400], ctx=c)
         d, i = ob.knn_data(rows[:3000], 20, fit=rows[5000:5400])
         assert np.array_equal(idx, i) and np.array_equal(dist, d)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_correlation_metric_on_the_tensor_path_is_bit_exact(ctx, kernel):
+    """knn_data -c (knn_data.cpp:104-106, correlation_distance mdsctk.cpp:337-360): the Euclidean tensor filter on the
+    standardised rows + exact FP64 re-score with the reference's own arithmetic must reproduce the oracle's bytes, in
+    sample and out of sample, and agree with the exact FP64 sweep; constant rows send the query to the exact sweep."""
+    import mdsctk_b200
+    from mdsctk_b200 import synth
+    from oracle import binding as ob
+    rng = np.random.default_rng(4)
+    rows = synth.phipsi_rows(20000, 128, 16) * rng.uniform(0.5, 3.0, (20000, 1)) + rng.normal(0, 2.0, (20000, 1))   # per-row scale and offset
+    ctx.set_option("data_kernel", kernel)
+    try:
+        dist, idx = mdsctk_b200.knn_data(rows, 24, correlation=True, ctx=ctx)
+        st = ctx.stats()
+        assert st["lists_per_row"] >= 1 and st["k_keep"] > 25 and st["fallback_rows"] < 400      # the tensor path ran
+        sample = np.concatenate([np.arange(0, 128), np.arange(19900, 20000)])
+        d, i = ob.knn_data(rows, 24, fit=rows[sample], metric=1)
+        assert np.array_equal(idx[sample], i) and np.array_equal(dist[sample], d)
+        fit = synth.phipsi_rows(3000, 128, 16, seed=77) * 1.7 - 0.3
+        dist_o, idx_o = mdsctk_b200.knn_data(rows, 24, fit_rows=fit, correlation=True, ctx=ctx)
+        d, i = ob.knn_data(rows, 24, fit=fit[:200], metric=1)
+        assert np.array_equal(idx_o[:200], i) and np.array_equal(dist_o[:200], d)
+        ctx.set_option("data_kernel", 0)
+        dist0, idx0 = mdsctk_b200.knn_data(rows[:6000], 24, correlation=True, ctx=ctx)
+        ctx.set_option("data_kernel", kernel)
+        dist1, idx1 = mdsctk_b200.knn_data(rows[:6000], 24, correlation=True, ctx=ctx)
+        assert ctx.stats()["lists_per_row"] >= 1
+        assert np.array_equal(idx0, idx1) and np.array_equal(dist0, dist1)
+        # the Euclidean metric right after it on the same context: the packed operands are rebuilt for the metric
+        dist_e, idx_e = mdsctk_b200.knn_data(rows[:6000], 24, ctx=ctx)
+        d, i = ob.knn_data(rows[:6000], 24, fit=rows[:100])
+        assert np.array_equal(idx_e[:100], i) and np.array_equal(dist_e[:100], d)
+        # a constant row has zero spread: correlation_distance divides by it -- exact sweep, whatever it makes of it
+        bad = rows[:6000].copy()
+        bad[17] = 3.0
+        dist_b, idx_b = mdsctk_b200.knn_data(bad, 24, correlation=True, ctx=ctx)
+        ctx.set_option("data_kernel", 0)
+        dist_b0, idx_b0 = mdsctk_b200.knn_data(bad, 24, correlation=True, ctx=ctx)
+        assert np.array_equal(idx_b, idx_b0) and np.array_equal(dist_b, dist_b0, equal_nan=True)
+    finally:
+        ctx.set_option("data_kernel", 1)

@@ -195,6 +195,16 @@ int mdsctk_knn_csc_fetch(mdsctk_knn_ctx *ctx, int *irow, double *val);
 int mdsctk_knn_spectral_decomp(mdsctk_knn_ctx *ctx, int n, const int *pcol, const int *irow, const double *val, int k_sigma,
                                double sigma, int nev, double *evals, double *evecs, double *residuals, double *avg_sigma, int *n_converged);
 
+/* Same with auto_decomp_sparse's -K / --k-perplexity (auto_decomp_sparse.cpp:153-173): k_perplexity > 0 replaces the mean
+ * sigmas by ENTROPIC ones (entropic_affinity_sigmas, mdsctk.cpp:388-565): per frame the bandwidth whose Gaussian over its first
+ * k_sigma sorted distances has perplexity k_perplexity (1 < k_perplexity < k_sigma <= 256).  sigmas: host double[n] or NULL,
+ * receives the per-frame sigmas that were used.  Every frame is solved from the midpoint of its bracket (the reference chains
+ * warm starts through the frames in order of their K-th distance), so sigmas agree with it to the solver's tolerance
+ * (|perplexity error| < 1e-10), not to the last bit. */
+int mdsctk_knn_spectral_decomp_ex(mdsctk_knn_ctx *ctx, int n, const int *pcol, const int *irow, const double *val, int k_sigma,
+                                  double sigma, double k_perplexity, int nev, double *evals, double *evecs, double *residuals,
+                                  double *avg_sigma, int *n_converged, double *sigmas);
+
 /* ---- producers of knn_data's input: backbone phi/psi angles and their sin/cos embedding -------------
  * xyz: host, float[n_frames][n_atoms][3] (nm), backbone atoms N-CA-C only, one chain
  * (bb_xtc_to_phipsi.cpp:106-122).  T = 2*(n_atoms/3) - 2 angles per frame (radians, torsion() of

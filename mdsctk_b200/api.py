@@ -26,7 +26,7 @@ SYMBOLS = [
     "mdsctk_knn_fetch", "mdsctk_knn_rms_rows", "mdsctk_knn_timer_start", "mdsctk_knn_timer_stop",
     "mdsctk_knn_debug_fetch_tile", "mdsctk_knn_csc_build_sym", "mdsctk_knn_csc_build_general", "mdsctk_knn_csc_fetch",
     "mdsctk_knn_phipsi", "mdsctk_knn_sincos", "mdsctk_knn_data_rows", "mdsctk_knn_spectral_decomp",
-    "mdsctk_knn_debug_fetch_array",
+    "mdsctk_knn_debug_fetch_array", "mdsctk_knn_spectral_decomp_ex",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library():
     L.mdsctk_knn_csc_fetch.argtypes = [vp, ip, dp]
     L.mdsctk_knn_data_rows.argtypes = [vp, dp, ll, C.c_int, dp]
     L.mdsctk_knn_spectral_decomp.argtypes = [vp, C.c_int, ip, ip, dp, C.c_int, C.c_double, C.c_int, dp, dp, dp, dp, ip]
+    L.mdsctk_knn_spectral_decomp_ex.argtypes = [vp, C.c_int, ip, ip, dp, C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, dp, dp, ip, dp]
     L.mdsctk_knn_phipsi.argtypes = [vp, fp, ll, C.c_int, dp, dp]
     L.mdsctk_knn_sincos.argtypes = [vp, dp, ll, dp]
     _LIB = L
@@ -257,19 +258,21 @@ class KnnContext:
                  "data_rows")
         return out
 
-    def spectral_decomp(self, pcol, irow, val, nev, k_sigma=0, sigma=0.0):
-        """auto_decomp_sparse (k_sigma > 0) / decomp_sparse (k_sigma = 0): (evals[nev] largest first, evecs[nev, n],
-        residuals[nev], average sigma, converged pairs)."""
+    def spectral_decomp(self, pcol, irow, val, nev, k_sigma=0, sigma=0.0, k_perplexity=0.0, want_sigmas=False):
+        """auto_decomp_sparse (k_sigma > 0, -K k_perplexity) / decomp_sparse (k_sigma = 0): (evals[nev] largest first,
+        evecs[nev, n], residuals[nev], average sigma, converged pairs[, sigmas[n]])."""
         pcol = np.ascontiguousarray(pcol, dtype=np.int32)
         irow = np.ascontiguousarray(irow, dtype=np.int32)
         val = np.ascontiguousarray(val, dtype=np.float64)
         n = pcol.size - 1
         ev, vec, res = np.empty(nev), np.empty((nev, n)), np.empty(nev)
         avg, nconv = C.c_double(0.0), C.c_int(0)
-        self._ck(self._L.mdsctk_knn_spectral_decomp(self._h, n, _ptr(pcol, C.c_int), _ptr(irow, C.c_int), _ptr(val, C.c_double),
-                                                    int(k_sigma), float(sigma), int(nev), _ptr(ev, C.c_double), _ptr(vec, C.c_double),
-                                                    _ptr(res, C.c_double), C.byref(avg), C.byref(nconv)), "spectral_decomp")
-        return ev, vec, res, avg.value, nconv.value
+        sig = np.empty(n) if want_sigmas else None
+        self._ck(self._L.mdsctk_knn_spectral_decomp_ex(self._h, n, _ptr(pcol, C.c_int), _ptr(irow, C.c_int), _ptr(val, C.c_double),
+                                                       int(k_sigma), float(sigma), float(k_perplexity), int(nev), _ptr(ev, C.c_double),
+                                                       _ptr(vec, C.c_double), _ptr(res, C.c_double), C.byref(avg), C.byref(nconv),
+                                                       _ptr(sig, C.c_double)), "spectral_decomp")
+        return (ev, vec, res, avg.value, nconv.value) + ((sig,) if want_sigmas else ())
 
     def phipsi(self, xyz, want_angles=True, want_sincos=True):
         """Backbone torsions (bb_xtc_to_phipsi) and their sin/cos embedding (angles_to_sincos) of N-CA-C frames."""

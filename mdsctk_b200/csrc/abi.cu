@@ -1254,9 +1254,19 @@ int mdsctk_knn_csc_fetch(mdsctk_knn_ctx *ctx, int *irow, double *val)
 int mdsctk_knn_spectral_decomp(mdsctk_knn_ctx *ctx, int n, const int *pcol, const int *irow, const double *val, int k_sigma,
                                double sigma, int nev, double *evals, double *evecs, double *residuals, double *avg_sigma, int *n_converged)
 {
+    return mdsctk_knn_spectral_decomp_ex(ctx, n, pcol, irow, val, k_sigma, sigma, 0.0, nev, evals, evecs, residuals, avg_sigma, n_converged,
+                                         nullptr);
+}
+
+int mdsctk_knn_spectral_decomp_ex(mdsctk_knn_ctx *ctx, int n, const int *pcol, const int *irow, const double *val, int k_sigma,
+                                  double sigma, double k_perplexity, int nev, double *evals, double *evecs, double *residuals,
+                                  double *avg_sigma, int *n_converged, double *sigmas)
+{
     if (!ctx) return MDSCTK_KNN_EINVAL;
     if (!pcol || !irow || !val || !evals || !evecs || !residuals || n < 2 || nev < 1 || nev >= n)
         return fail(ctx, MDSCTK_KNN_EINVAL, "spectral_decomp: need n >= 2, 1 <= nev < n and non-NULL arrays");
+    if (k_perplexity != 0.0 && (!(k_perplexity > 1.0) || k_sigma < 2 || k_sigma > 256 || !(k_perplexity < (double)k_sigma)))
+        return fail(ctx, MDSCTK_KNN_EINVAL, "spectral_decomp: entropic affinities need 1 < k_perplexity < k_sigma <= 256");
     const int nnz = pcol[n];
     if (nnz < 0) return fail(ctx, MDSCTK_KNN_EINVAL, "spectral_decomp: bad pcol");
     Bind b(ctx);
@@ -1285,10 +1295,12 @@ int mdsctk_knn_spectral_decomp(mdsctk_knn_ctx *ctx, int n, const int *pcol, cons
        "spectral adjacency");
     double avg = 0.0;
     if (k_sigma > 0 || sigma > 0.0) {
-        CK(launch_spectral_affinity(n, d_pcol, d_irow, d_ptr, d_pos, k_sigma, sigma, d_M, d_sigma, d_dinv, ctx->st), "spectral affinity");
+        CK(launch_spectral_affinity(n, d_pcol, d_irow, d_ptr, d_pos, k_sigma, sigma, k_perplexity, d_M, d_sigma, d_dinv, ctx->st),
+           "spectral affinity");
         std::vector<double> hs((size_t)n);
         CK(cudaMemcpyAsync(hs.data(), d_sigma, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->st), "D2H sigma");
         CK(cudaStreamSynchronize(ctx->st), "sync sigma");
+        if (sigmas) memcpy(sigmas, hs.data(), (size_t)n * 8);
         for (int i = 0; i < n; ++i) avg += hs[(size_t)i];       // auto_decomp_sparse.cpp:199-201
         avg /= (double)n;
     }

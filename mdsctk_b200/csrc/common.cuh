@@ -160,8 +160,8 @@ cudaError_t exclusive_scan(const int *in, int *out, long long n, int *tmp, cudaS
 cudaError_t launch_spectral_adjacency(int n, int nnz, const int *pcol, const int *irow, int *deg_ptr, int *n_as_row, int *cur,
                                       int *scan_tmp, int *adj_other, int *adj_pos,
                                       cudaError_t (*scan)(const int *, int *, long long, int *, cudaStream_t), cudaStream_t st);
-cudaError_t launch_spectral_affinity(int n, const int *pcol, const int *irow, const int *ptr, const int *adj_pos, int k_a, double sigma0, double *M,
-                                     double *sigma, double *dinv, cudaStream_t st);
+cudaError_t launch_spectral_affinity(int n, const int *pcol, const int *irow, const int *ptr, const int *adj_pos, int k_a, double sigma0,
+                                     double perplexity, double *M, double *sigma, double *dinv, cudaStream_t st);
 cudaError_t launch_spectral_spmv(int n, const int *ptr, const int *adj_other, const int *adj_pos, const double *M, const double *x,
                                  double *y, cudaStream_t st);
 cudaError_t spectral_lanczos(int n, const int *ptr, const int *adj_other, const int *adj_pos, const double *M, int nev, int ncv,

@@ -105,6 +105,80 @@ __global__ void sigma_kernel(int n, const int *__restrict__ ptr, const int *__re
     sigma[v] = s / (double)k_a;
 }
 
+// Entropic affinities (auto_decomp_sparse -K, entropic_affinity_sigmas / entropic_affinity_sigma, mdsctk.cpp:388-565): for
+// every frame the bandwidth whose Gaussian over the frame's first k_a (sorted) distances has perplexity K, i.e. the
+// root in b = log beta of  e(b) = beta m1(b) + log m0(b) - log K,  m0 = sum exp(-d^2 beta), m1 = sum d^2 exp(-d^2 beta) / m0;
+// sigma = 1 / sqrt(2 beta).  Same bracket [B_lower, B_upper], same safeguarded Newton iteration (bisection whenever the
+// function or its gradient misbehaves, or the step leaves the bracket; a forced bisection every 20 steps), same stopping
+// rules (|e| < 1e-10, bracket narrower than 10 sqrt(eps)).  One thread per frame.  The reference walks the frames in the
+// order of their K-th distance and starts each from the previous frame's solution, falling back to the bracket's midpoint
+// when that lies outside -- a warm start only; here every frame starts from its midpoint (frames are independent), so the
+// two agree to the iteration's tolerance, not to the last bit.  Frames with fewer than two entries keep the mean sigma.
+constexpr int ENTROPIC_MAX_K = 256;
+
+__global__ void entropic_sigma_kernel(int n, const int *__restrict__ ptr, const int *__restrict__ adj_pos, const double *__restrict__ M,
+                                      int k_a, double logK, double logN, double p1, double *__restrict__ sigma)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int b0 = ptr[v], k = min(min(ptr[v + 1] - b0, k_a), ENTROPIC_MAX_K);
+    if (k < 2) return;
+    double a2[ENTROPIC_MAX_K];                        // squared distances, ascending (the reference sorts sorted_A[x])
+    for (int i = 0; i < k; ++i) {
+        const double d = M[adj_pos[b0 + i]];
+        int j = i - 1;
+        while (j >= 0 && a2[j] > d * d) { a2[j + 1] = a2[j]; --j; }
+        a2[j + 1] = d * d;
+    }
+    const double N = (double)k_a, logNK = logN - logK;
+    double BU = log((2.0 * log(p1 * (N - 1.0) / (1.0 - p1))) / (a2[1] - a2[0]));
+    const double bL1 = log((2.0 * logNK / (1.0 - (1.0 / N))) / (a2[k - 1] - a2[0]));
+    const double bL2 = log((2.0 * sqrt(logNK)) / sqrt(a2[k - 1] * a2[k - 1] - a2[0] * a2[0]));
+    double BL = bL1 > bL2 ? bL1 : bL2;
+    const double tol = 1e-10, realmin = 2.225074e-308, eps = 1.4901161193847656e-08;   // sqrt(2^-52), getEPS()
+    double b = 0.5 * (BL + BU);
+    int it = 1;
+    for (int guard = 0; guard < 100000; ++guard) {
+        const double bE = exp(b);
+        double m0 = 0.0;
+        for (int x = 0; x < k; ++x) m0 += exp(-a2[x] * bE);
+        bool pbm = false;
+        double e, m1 = 0.0;
+        if (m0 < realmin) {
+            e = -logK;
+            pbm = true;
+        } else {
+            for (int x = 0; x < k; ++x) m1 += exp(-a2[x] * bE) * (a2[x] / m0);
+            e = bE * m1 + log(m0) - logK;
+        }
+        if (fabs(e) < tol) break;
+        if (BU - BL < 10.0 * eps) break;
+        if (e < 0.0 && b <= BU) BU = b;
+        else if (e > 0.0 && b >= BL) BL = b;
+        pbm = pbm || e < -logK || e > logN - logK;
+        double g = 0.0;
+        if (!pbm) {
+            if (it == 20) { b = 0.5 * (BL + BU); it = 1; continue; }
+            double m2 = 0.0;
+            for (int x = 0; x < k; ++x) m2 += exp(-a2[x] * bE) * (a2[x] / m0) * a2[x];
+            g = bE * bE * (m1 * m1 - m2);
+            if (g == 0.0) pbm = true;
+        }
+        if (pbm) {
+            double esum = 0.0;
+            for (int x = 0; x < k; ++x) esum += exp(-a2[x] * exp(BL)) + exp(-a2[x] * exp(BU));
+            if (esum < 2.0 * sqrt(realmin)) break;
+            b = 0.5 * (BL + BU);
+            it = 1;
+            continue;
+        }
+        b += -e / g;
+        if (b < BL || b > BU) { b = 0.5 * (BL + BU); it = 0; }
+        ++it;
+    }
+    sigma[v] = 1.0 / sqrt(2.0 * exp(b));
+}
+
 __global__ void affinity_kernel(int n, const int *__restrict__ pcol, const int *__restrict__ irow, const double *__restrict__ sigma,
                                 double *__restrict__ M)
 {
@@ -287,10 +361,23 @@ __global__ void fill_double_kernel(double *v, int n, double x)
 
 // k_a > 0: per-frame sigmas (auto_decomp_sparse); else the global sigma0 (decomp_sparse.cpp:157-158)
 cudaError_t launch_spectral_affinity(int n, const int *pcol, const int *irow, const int *ptr, const int *adj_pos, int k_a, double sigma0,
-                                     double *M, double *sigma, double *dinv, cudaStream_t st)
+                                     double perplexity, double *M, double *sigma, double *dinv, cudaStream_t st)
 {
     if (k_a > 0) sigma_kernel<<<grid_for(n), spk::BLOCK, 0, st>>>(n, ptr, adj_pos, M, k_a, sigma);
     else fill_double_kernel<<<grid_for(n), spk::BLOCK, 0, st>>>(sigma, n, sigma0);
+    if (k_a > 0 && perplexity > 0.0) {
+        // p1(N, log K), entropic_affinity_sigmas (mdsctk.cpp:515-524)
+        const double N = (double)k_a, logK = std::log(perplexity), logN = std::log(N);
+        double p1;
+        if (logK > std::log(std::sqrt(2.0 * N))) {
+            p1 = 3.0 / 4.0;
+        } else {
+            p1 = 1.0 / 4.0;
+            for (int x = 0; x < 100; x++) p1 -= (-p1 * std::log(p1 / N) - logK) / (-std::log(p1 / N) + 1.0);
+            p1 = 1.0 - (p1 / 2.0);
+        }
+        entropic_sigma_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, ptr, adj_pos, M, k_a, logK, logN, p1, sigma);
+    }
     affinity_kernel<<<grid_for(n), spk::BLOCK, 0, st>>>(n, pcol, irow, sigma, M);
     degree_kernel<<<grid_for(n), spk::BLOCK, 0, st>>>(n, ptr, adj_pos, M, dinv);
     normalise_kernel<<<grid_for(n), spk::BLOCK, 0, st>>>(n, pcol, irow, dinv, M);

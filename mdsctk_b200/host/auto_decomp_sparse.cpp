@@ -8,6 +8,9 @@
 #include "options.hpp"
 #include "spectral_tool.hpp"
 
+#include <cmath>
+#include <cstdlib>
+
 using namespace mdsctk_cli;
 
 int main(int argc, char *argv[])
@@ -42,18 +45,22 @@ int main(int argc, char *argv[])
     if (!po.count("k-sigma")) { std::cout << "ERROR: --k-sigma not supplied." << std::endl << std::endl; optsOK = false; }
     if (!po.count("nevals")) { std::cout << "ERROR: --nevals not supplied." << std::endl << std::endl; optsOK = false; }
     if (!optsOK) return -1;
-    if (po.count("k-perplexity")) {
-        std::cout << "ERROR: --k-perplexity (entropic affinities) is not supported by this build" << std::endl;
-        return 6;
+    double K = 0.0;
+    const bool pSet = po.count("k-perplexity") != 0;
+    if (pSet) {
+        K = std::atof(po.str("k-perplexity").c_str());
+        if (std::ceil(K) > (double)k_a)                                   // auto_decomp_sparse.cpp:104-110
+            std::cout << "WARNING: --k-perplexity (" << K << ") is higher than --k-sigma (" << k_a << ")" << std::endl;
     }
     if (k_a < 1) { std::cout << "ERROR: --k-sigma must be positive." << std::endl; return -1; }
     std::cout << "Running with the following options:" << std::endl;
     std::cout << "k-sigma =        " << k_a << std::endl;
+    if (pSet) std::cout << "k-perplexity =   " << K << std::endl;
     std::cout << "nevals =         " << nev << std::endl;
     std::cout << "ssm-file =       " << po.str("ssm-file") << std::endl;
     std::cout << "residuals-file = " << po.str("residuals-file") << std::endl;
     std::cout << "evals-file =     " << po.str("evals-file") << std::endl;
     std::cout << "evecs-file =     " << po.str("evecs-file") << std::endl;
     std::cout << std::endl;
-    return run_spectral_tool(po.str("ssm-file"), po.str("evals-file"), po.str("evecs-file"), po.str("residuals-file"), k_a, 0.0, nev);
+    return run_spectral_tool(po.str("ssm-file"), po.str("evals-file"), po.str("evecs-file"), po.str("residuals-file"), k_a, 0.0, nev, K);
 }

@@ -22,7 +22,7 @@ inline double sqrt_machine_eps()          // getEPS(), mdsctk.cpp:285-290
 }
 
 inline int run_spectral_tool(const std::string &ssm_filename, const std::string &evals_filename, const std::string &evecs_filename,
-                             const std::string &residuals_filename, int k_sigma, double sigma, int nev)
+                             const std::string &residuals_filename, int k_sigma, double sigma, int nev, double k_perplexity = 0.0)
 {
     std::ifstream ssm(ssm_filename.c_str(), std::ios::binary);
     if (!ssm) { std::cout << "ERROR: cannot read " << ssm_filename << std::endl; return 3; }
@@ -48,8 +48,8 @@ inline int run_spectral_tool(const std::string &ssm_filename, const std::string 
     std::vector<double> d((size_t)nev), Z((size_t)nev * n), res((size_t)nev);
     double avg_sigma = 0.0;
     int nconv = 0;
-    if (mdsctk_knn_spectral_decomp(ctx, n, pcol.data(), irow.data(), val.data(), k_sigma, sigma, nev, d.data(), Z.data(), res.data(),
-                                   &avg_sigma, &nconv) != 0) {
+    if (mdsctk_knn_spectral_decomp_ex(ctx, n, pcol.data(), irow.data(), val.data(), k_sigma, sigma, k_perplexity, nev, d.data(), Z.data(),
+                                      res.data(), &avg_sigma, &nconv, nullptr) != 0) {
         std::cout << "ERROR: " << mdsctk_knn_last_error(ctx) << std::endl;
         return 5;
     }

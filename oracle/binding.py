@@ -56,6 +56,8 @@ def lib():
         L.oracle_knn_data_sparse.argtypes = [lp, ip, dp, C.c_longlong, lp, ip, dp, C.c_longlong, C.c_int, dp, ip]
         L.oracle_affinity.argtypes = [C.c_int, ip, ip, dp, C.c_int]
         L.oracle_affinity.restype = C.c_double
+        L.oracle_entropic_affinity_sigmas.argtypes = [C.c_int, C.c_int, C.c_double, dp, dp]
+        L.oracle_entropic_affinity_sigmas.restype = None
         L.oracle_sym_eigs_largest.argtypes = [C.c_int, ip, ip, dp, C.c_int, dp, dp, dp]
         L.oracle_phipsi.argtypes = [fp, C.c_longlong, C.c_int, dp]
         L.oracle_phipsi.restype = None
@@ -255,6 +257,14 @@ def knn_data_sparse(ref, k, fit=None):
 
 def _i(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def entropic_sigmas(sorted_dist, K):
+    """entropic_affinity_sigmas (auto_decomp_sparse -K): sorted_dist [n, k] ascending rows -> sigma[n]."""
+    a = np.ascontiguousarray(sorted_dist, dtype=np.float64)
+    s = np.empty(a.shape[0])
+    lib().oracle_entropic_affinity_sigmas(a.shape[0], a.shape[1], float(K), _d(a), _d(s))
+    return s
 
 
 def affinity(pcol, irow, val, k_a):

@@ -89,6 +89,8 @@ int oracle_max_threads(void);
 /* make_sysparse (make_sysparse.cpp:245-329): symmetric CSC from the kNN files; returns nnz (csc.c). */
 /* auto_decomp_sparse (spectral.c): affinity stage, sp_dsymv, dense eigen-solve standing in for ARPACK */
 double oracle_affinity(int n, const int *pcol, const int *irow, double *M, int k_a);
+/* auto_decomp_sparse -K: entropic_affinity_sigmas (mdsctk.cpp:498-565); A = n rows of k sorted distances */
+void oracle_entropic_affinity_sigmas(int n, int k, double K, const double *A, double *s);
 void oracle_sp_dsymv(int n, const int *irow, const int *pcol, const double *A, const double *v, double *w);
 int oracle_sym_eigs_largest(int n, const int *pcol, const int *irow, const double *M, int nev, double *evals, double *evecs,
                             double *residuals);

@@ -2,7 +2,7 @@
  *
  * Affinity stage: auto_decomp_sparse.cpp:150-198, loop for loop (including its sigma quirk: the values of a
  * frame are collected in CSC traversal order, truncated to the FIRST k_a, and the sum is divided by k_a even
- * when fewer are present).  The -K (entropic affinity) branch is not restated.
+ * when fewer are present).  The -K branch (entropic affinities) is restated below, warm-start chain included.
  * Eigen-solve: the reference calls ARPACK (dsaupd/dseupd, mode 1, which = "LA", tol = machine eps, ncv =
  * 10*nev+1; mdsctk.cpp:857-924) -- a third-party Fortran library that is not vendored and not installed here
  * (CMakeLists.txt finds it with find_library, no version pin; arpack-ng 3.x API).  ARPACK's implicitly
@@ -69,6 +69,103 @@ double oracle_affinity(int n, const int *pcol, const int *irow, double *M, int k
     avg /= (double)n;
     free(sigma_a); free(d_a); free(cnt);
     return avg;
+}
+
+/* entropic_affinity_sigma, mdsctk.cpp:388-496: root of e(b) = beta m1 + log m0 - log K in b = log beta by Newton steps
+ * safeguarded with bisection of the bracket [B_lower, B_upper]; A = the frame's k sorted distances. */
+static double entropic_sigma(const double *A, int k, double b0, double logK, double logN, double B_lower, double B_upper)
+{
+    const int maxit = 20;
+    const double tol = 1e-10, realmin = 2.225074e-308;
+    double eps = 1.0;
+    do { eps /= 2.0; } while (1.0 + (eps / 2.0) != 1.0);
+    eps = sqrt(eps);
+    double b = (b0 < B_lower || b0 > B_upper) ? (B_lower + B_upper) / 2.0 : b0;
+    double *ed2 = (double *)malloc(sizeof(double) * (size_t)k), *m1v = (double *)malloc(sizeof(double) * (size_t)k);
+    int i = 1;
+    for (;;) {
+        const double bE = exp(b);
+        int pbm = 0;
+        double e, g = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+        for (int x = 0; x < k; x++) ed2[x] = exp(-(A[x] * A[x]) * bE);
+        for (int x = 0; x < k; x++) m0 += ed2[x];
+        if (m0 < realmin) {
+            e = -logK;
+            pbm = 1;
+        } else {
+            for (int x = 0; x < k; x++) m1v[x] = ed2[x] * ((A[x] * A[x]) / m0);
+            for (int x = 0; x < k; x++) m1 += m1v[x];
+            e = bE * m1 + log(m0) - logK;
+        }
+        if (fabs(e) < tol) break;
+        if (B_upper - B_lower < 10.0 * eps) break;
+        if (e < 0.0 && b <= B_upper) B_upper = b;
+        else if (e > 0.0 && b >= B_lower) B_lower = b;
+        pbm = pbm || e < -logK || e > logN - logK;
+        if (!pbm) {
+            if (i == maxit) { b = (B_lower + B_upper) / 2.0; i = 1; continue; }
+            for (int x = 0; x < k; x++) m2 += m1v[x] * (A[x] * A[x]);
+            g = (bE * bE) * (m1 * m1 - m2);
+            if (g == 0) pbm = 1;
+        }
+        if (pbm) {
+            double esqd_sum = 0.0;
+            for (int x = 0; x < k; x++) esqd_sum += exp(-(A[x] * A[x]) * exp(B_lower)) + exp(-(A[x] * A[x]) * exp(B_upper));
+            if (esqd_sum < 2.0 * sqrt(realmin)) break;
+            b = (B_lower + B_upper) / 2.0;
+            i = 1;
+            continue;
+        }
+        b += -e / g;
+        if (b < B_lower || b > B_upper) { b = (B_lower + B_upper) / 2.0; i = 0; }
+        i++;
+    }
+    free(ed2); free(m1v);
+    return 1.0 / sqrt(2.0 * exp(b));
+}
+
+static int cmp_kth(const void *a, const void *b)
+{
+    const double *x = (const double *)a, *y = (const double *)b;
+    if (x[0] < y[0]) return -1;
+    if (x[0] > y[0]) return 1;
+    return (x[1] > y[1]) - (x[1] < y[1]);
+}
+
+/* entropic_affinity_sigmas, mdsctk.cpp:498-565.  A: n rows of k sorted distances (row-major); s[n] out.  The frames are
+ * visited in ascending order of their ceil(K)-th distance, each started from the previous frame's solution. */
+void oracle_entropic_affinity_sigmas(int n, int k, double K, const double *A, double *s)
+{
+    const int Ki = (int)ceil(K);
+    const double N = (double)k, logK = log(K), logN = log(N), logNK = logN - logK;
+    double p1;
+    if (logK > log(sqrt(2.0 * N))) {
+        p1 = 3.0 / 4.0;
+    } else {
+        p1 = 1.0 / 4.0;
+        for (int x = 0; x < 100; x++) p1 -= (-p1 * log(p1 / N) - logK) / (-log(p1 / N) + 1.0);
+        p1 = 1.0 - (p1 / 2.0);
+    }
+    double *BL = (double *)malloc(sizeof(double) * (size_t)n), *BU = (double *)malloc(sizeof(double) * (size_t)n);
+    double *order = (double *)malloc(sizeof(double) * 2 * (size_t)n);
+    for (int x = 0; x < n; x++) {
+        const double *a = A + (size_t)x * k;
+        BU[x] = log((2.0 * log(p1 * (N - 1.0) / (1.0 - p1))) / (a[1] * a[1] - a[0] * a[0]));
+        const double bL1 = log((2.0 * logNK / (1.0 - (1.0 / N))) / (a[k - 1] * a[k - 1] - a[0] * a[0]));
+        const double bL2 = log((2.0 * sqrt(logNK)) / sqrt((a[k - 1] * a[k - 1]) * (a[k - 1] * a[k - 1]) - (a[0] * a[0]) * (a[0] * a[0])));
+        BL[x] = bL1 > bL2 ? bL1 : bL2;
+        order[2 * x] = a[Ki - 1];
+        order[2 * x + 1] = (double)x;
+    }
+    qsort(order, (size_t)n, 2 * sizeof(double), cmp_kth);
+    int j = (int)order[1];
+    double b0 = (BL[j] + BU[j]) / 2.0;
+    for (int t = 0; t < n; t++) {
+        j = (int)order[2 * t + 1];
+        s[j] = entropic_sigma(A + (size_t)j * k, k, b0, logK, logN, BL[j], BU[j]);
+        b0 = log((1.0 / s[j]) * (1.0 / s[j]) / 2.0);
+    }
+    free(BL); free(BU); free(order);
 }
 
 /* w = A v for the symmetric matrix stored as its upper triangle in CSC (sp_dsymv, mdsctk.cpp:293-313) */

@@ -146,3 +146,67 @@ def test_auto_decomp_sparse_tool_end_to_end(tmp_path):
     assert np.allclose(ev, want_ev, rtol=2e-6)                # the reference prints 6 significant digits
     assert (res < 1e-8).all()
     assert ("Average sigma: %g" % avg) in p.stdout
+
+
+def first_k_sorted(pcol, irow, val, k_a):
+    """sorted_A of auto_decomp_sparse.cpp:153-165: per frame the first k_a values in CSC traversal order, sorted."""
+    n = len(pcol) - 1
+    lists = [[] for _ in range(n)]
+    for x in range(n):
+        for y in range(pcol[x], pcol[x + 1]):
+            lists[x].append(val[y])
+            lists[irow[y]].append(val[y])
+    return [sorted(l[:k_a]) for l in lists]
+
+
+def perplexity(dist, sigma):
+    p = np.exp(-np.asarray(dist) ** 2 / (2.0 * sigma * sigma))
+    p /= p.sum()
+    return float(np.exp(-(p * np.log(p)).sum()))
+
+
+def test_oracle_entropic_sigmas_have_the_requested_perplexity():
+    """entropic_affinity_sigmas (mdsctk.cpp:498-565): the Gaussian over a frame's sorted distances with the returned
+    sigma has perplexity K -- a known-answer property of the restatement, warm-start chain included."""
+    from oracle import binding as ob
+    rng = np.random.default_rng(1)
+    for k, K in ((32, 10.0), (12, 4.5), (64, 30.0)):
+        a = np.sort(rng.random((500, k)) * rng.uniform(0.5, 4.0, (500, 1)) + 0.1, axis=1)
+        s = ob.entropic_sigmas(a, K)
+        got = np.array([perplexity(a[i], s[i]) for i in range(500)])
+        assert np.abs(got - K).max() < 1e-7 * K
+
+
+@pytest.mark.gpu
+def test_gpu_entropic_affinities_match_the_oracle(tmp_path):
+    """auto_decomp_sparse -K: per-frame entropic sigmas on the GPU (independent frames, midpoint start) against the
+    oracle's sequential warm-start chain, the perplexity property itself, and the tool's option."""
+    import mdsctk_b200
+    from oracle import binding as ob
+    n, k, k_a, K, nev = 900, 16, 16, 6.0, 4
+    pcol, irow, val = knn_graph(n, k, seed=7)
+    rows = first_k_sorted(pcol, irow, val, k_a)
+    assert all(len(r) == k_a for r in rows)                     # every frame has k_a entries: the reference's precondition
+    want = ob.entropic_sigmas(np.array(rows), K)
+    with mdsctk_b200.KnnContext(0) as ctx:
+        ev, vec, res, avg, nconv, sig = ctx.spectral_decomp(pcol, irow, val, nev, k_sigma=k_a, k_perplexity=K, want_sigmas=True)
+        ev0, _, _, avg0, _ = ctx.spectral_decomp(pcol, irow, val, nev, k_sigma=k_a)
+    assert np.abs(sig - want).max() < 1e-8 * want.max()
+    got = np.array([perplexity(rows[i], sig[i]) for i in range(n)])
+    assert np.abs(got - K).max() < 1e-7 * K
+    assert abs(avg - want.mean()) < 1e-8 * avg and abs(avg - avg0) > 1e-3 * avg0      # not the mean-distance sigmas
+    assert nconv == nev and res.max() < 1e-9 and ev[0] > ev[-1] > 0
+    # the same matrix by numpy with the oracle's sigmas
+    col = np.repeat(np.arange(n), np.diff(pcol))
+    m = np.exp(-(val * val) / (2.0 * want[col] * want[irow]))
+    deg = np.zeros(n); np.add.at(deg, col, m); np.add.at(deg, irow, m)
+    a = dense(pcol, irow, m / np.sqrt(deg[col] * deg[irow]))
+    assert np.allclose(ev, np.linalg.eigvalsh(a)[::-1][:nev], rtol=1e-8)
+    # the tool
+    with open(tmp_path / "distances.ssm", "wb") as f:
+        np.array([n], dtype=np.int32).tofile(f); pcol.astype(np.int32).tofile(f); irow.astype(np.int32).tofile(f); val.tofile(f)
+    p = subprocess.run([os.path.join(BIN, "auto_decomp_sparse"), "-k", str(k_a), "-K", str(K), "-n", str(nev)], capture_output=True,
+                       text=True, cwd=tmp_path)
+    assert p.returncode == 0, p.stdout
+    assert "k-perplexity =   6" in p.stdout and ("Average sigma: %g" % avg) in p.stdout
+    assert np.allclose(np.loadtxt(tmp_path / "eigenvalues.dat"), ev, rtol=2e-6)

@@ -138,7 +138,7 @@ struct mdsctk_knn_ctx {
     long long cert_scale_ppm = 1000000;
     // RMSD state
     FrameSet ref, fit;
-    DevBuf wnorm;  // double[A]
+    DevBuf wnorm;  // double[2A]: m_a / M, then sqrt(m_a / M)
     bool have_ref = false, gmax_dirty = true;
     int ref_pack_fam = F_FP16;   // operand families every shard of the current reference set is packed with (fixed at alloc)
     long long chunk_rows = 131072;   // fit rows per internal row block of a query (bounds the candidate-list memory)
@@ -214,8 +214,12 @@ int upload_weights(mdsctk_knn_ctx *ctx, const float *mass, int A)
     for (int i = 0; i < A; i++) M += (double)mass[i];
     if (!(M > 0.0)) return fail(ctx, MDSCTK_KNN_EINVAL, "masses must sum to a positive number");
     for (int i = 0; i < A; i++) w[i] = (double)mass[i] / M;
-    CK(ctx->wnorm.reserve((size_t)A * 8), "cudaMalloc(weights)");
-    CK(cudaMemcpyAsync(ctx->wnorm.p, w.data(), (size_t)A * 8, cudaMemcpyHostToDevice, ctx->st), "H2D weights");
+    // [A] weights m/M followed by [A] of their square roots (pack.cu scales every atom by sqrt(w): one FP64 sqrt per atom
+    // and frame was a third of the pack kernel's time)
+    w.resize(2 * (size_t)A);
+    for (int i = 0; i < A; i++) w[(size_t)A + i] = std::sqrt(w[i]);
+    CK(ctx->wnorm.reserve((size_t)A * 16), "cudaMalloc(weights)");
+    CK(cudaMemcpyAsync(ctx->wnorm.p, w.data(), (size_t)A * 16, cudaMemcpyHostToDevice, ctx->st), "H2D weights");
     CK(cudaStreamSynchronize(ctx->st), "sync weights");
     return 0;
 }

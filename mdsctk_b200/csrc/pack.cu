@@ -27,7 +27,7 @@ __device__ __forceinline__ float tf32_rn(float x)
 }
 
 __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restrict__ raw,
-                                                          const double *__restrict__ wnorm,  // m_a / M (FP64)
+                                                          const double *__restrict__ wnorm,  // [2A]: m_a / M, then sqrt(m_a / M) (FP64)
                                                           long long n, int A, int A_pad,
                                                           float *__restrict__ planes, float *__restrict__ hi,
                                                           float *__restrict__ lo, __nv_bfloat16 *__restrict__ bh,
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
             const double dx = (double)x[3 * a + 0] - cx, dy = (double)x[3 * a + 1] - cy,
                          dz = (double)x[3 * a + 2] - cz;
             g += w * (dx * dx + dy * dy + dz * dz);
-            const double s = sqrt(w);
+            const double s = wnorm[A + a];               // sqrt(w), precomputed (abi.cu upload_weights)
             tx = s * dx; ty = s * dy; tz = s * dz;
             ox = (float)tx; oy = (float)ty; oz = (float)tz;
             t00 += tx * tx; t01 += tx * ty; t02 += tx * tz; t11 += ty * ty; t12 += ty * tz; t22 += tz * tz;

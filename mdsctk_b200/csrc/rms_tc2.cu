@@ -339,7 +339,7 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     const int ng = min(2, nkc - kc);
                     int s1 = s + 1; uint32_t ph1 = ph;
                     if (s1 == nst) { s1 = 0; ph1 ^= 1; }
-                    if (a.dbg & 4096) {
+                    if (!(a.dbg & 4096)) {               // suspending waits (hardware sleeps the warp until the barrier flips)
                         mbar_wait(&c.bar_empty[s], ph ^ 1, 1);
                         if (ng > 1) mbar_wait(&c.bar_empty[s1], ph1 ^ 1, 1);
                     } else {
@@ -514,6 +514,9 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                                     else issue_stage(ring_lo + (uint32_t)sB * (B_STAGE >> 4), ks0 + 2, 1u, ks0 + 3 < nks);
                                 }
                                 tc_commit2_mc(&c.bar_empty[sB], 3);
+#if MDSCTK_TC_PROF_BUILD
+                                if (a.prof) { *reinterpret_cast<volatile long long *>(&c.t_commit[sB]) = clock64(); }
+#endif
                             }
                             if (last_group) {
                                 if (heavy) tc_commit2_mc(&c.bar_tmem_full, 3);
@@ -726,7 +729,7 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 if (lane == 0) {
                     uint32_t polls = 0;
                     while ((msg = ld_volatile_u32(&c.mailbox)) == last_msg) {
-                        __nanosleep(64);
+                        __nanosleep(a.dbg & 512 ? 64 : 400);      // a heavy pass starts with >= 4k clk of MMAs: no hurry, and idle warps should not burn power
                         if (++polls > 400000000u) { printf("rms_sweep_tc2: mailbox timeout block=%d warp=%d last=%x\n", blockIdx.x, warp, last_msg); __trap(); }
                     }
                 }

@@ -10,7 +10,8 @@ import re
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 G, OUT = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0,
+        "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
 KEEP = ("gpu__time_duration", "sm__cycles_elapsed.avg.per_second", "dram__bytes", "dram__throughput", "lts__t_sector_hit_rate", "lts__t_bytes.sum",
         "l1tex__m_xbar2l1tex_read_bytes", "pipe_tensor", "sm__issue_active", "pipe_fma_cycles", "pipe_fp64", "launch__", "sm__throughput",
         "smsp__inst_executed.sum", "sm__warps_active", "smsp__average_warp", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__inst_executed.sum",
@@ -52,7 +53,11 @@ for f in sorted(os.listdir(G)):
     dur, rd, wr = val("gpu__time_duration.sum"), val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
     summ = {"kernel": name, "capture": m.group(1), "duration_ms": dur * 1e3 if dur else None,
             "dram_bytes_per_launch": (rd or 0) + (wr or 0), "dram_GBps": ((rd or 0) + (wr or 0)) / dur / 1e9 if dur else None,
-            "tensor_pipe_active_pct_of_elapsed": next((float(v["value"]) for k, v in met.items() if "pipe_tensor_cycles_active" in k and "pct_of_peak_sustained_elapsed" in k), None),
+            "sm_clock_GHz": float(met["sm__cycles_elapsed.avg.per_second"]["value"]) if "sm__cycles_elapsed.avg.per_second" in met else None,
+            "tensor_pipe_active_pct_of_elapsed": float(met["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]["value"])
+            if "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed" in met else None,
+            "issue_active_pct": float(met["sm__issue_active.avg.pct_of_peak_sustained_elapsed"]["value"])
+            if "sm__issue_active.avg.pct_of_peak_sustained_elapsed" in met else None,
             "l2_to_sm_bytes": val("l1tex__m_xbar2l1tex_read_bytes.sum")}
     json.dump({"summary": summ, "metrics": met}, open(os.path.join(OUT, f"ncu_{m.group(1)}_r02.json"), "w"), indent=1)
     traffic[m.group(1)] = summ["dram_bytes_per_launch"]

@@ -381,6 +381,10 @@ def run_rms(D, wl, args, rms_kernel=-1, steps=None, warmup=None, want_e2e=True, 
         return None
     pairs = float(n_total) * float(n_total)
     kern = st["rms_kernel"]
+    kname = KERNEL_NAMES[kern]
+    if kern == 6 and st.get("sweep_version") == 2:
+        kname = ("rms_sweep_tc2_kernel (tcgen05 cta_group::2 kind::f16, 1xFP16 contraction, fit tile resident in shared memory + TMEM, "
+                 "reference-only TMA ring, pass director; QCP bounds + streaming top-k; FP64 re-score with the rounded-structure triangle bound)")
     peaks = measured_peaks(kern)
     sweep_tflops = (count * float(n_total) * FLOP_PER_PAIR * steps) / (sweep_ms * 1e-3) / 1e12      # one GPU's rows / its time
     res = {
@@ -391,14 +395,15 @@ def run_rms(D, wl, args, rms_kernel=-1, steps=None, warmup=None, want_e2e=True, 
                    "parallelism": f"row-sharded x{world}, reference replicated by one NCCL all-gather per array",
                    "l2": "inputs larger than L2 (fp16 reference planes %.0f MB + raw %.0f MB vs 126 MB L2)" %
                          (n_total * 3 * 304 * 2 / 1e6, n_total * ATOMS * 12 / 1e6),
-                   "kernel": KERNEL_NAMES[kern], "k_keep": st["k_keep"], "fallback_rows": fallback_rows,
+                   "kernel": kname, "k_keep": st["k_keep"], "fallback_rows": fallback_rows,
+                   "audit_rows": st["audit_rows"], "audit_mismatches": st["audit_mismatches"],
                    "max_filter_err_nm2": err, "cert_eps_nm2": st["cert_eps"], "cert_gres_nm": st["cert_gres"],
                    "rescored_max": st["rescored_max"], "allgather_ms": allgather_ms, "allgather_bytes_per_gpu": gathered_bytes,
                    "h2d_ms": st0["ms_upload"], "pack_ms": st0["ms_pack"], "host_generation_s": round(gen_s, 1)},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": sweep_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                      "frac": sweep_tflops / peaks["tflops"], "traffic": measured_traffic(wl["key"]),
-                     "mma_per_flop": {0: 1, 2: 1, 5: 2, 6: 1}.get(kern, 3), "kernel": KERNEL_NAMES[kern].split(" ")[0],
+                     "mma_per_flop": {0: 1, 2: 1, 5: 2, 6: 1}.get(kern, 3), "kernel": kname.split(" ")[0],
                      "flop_per_pair": FLOP_PER_PAIR, "peak_source": peaks["source"],
                      "sweep_ms_per_step": sweep_ms / steps, "post_ms_per_step": post_ms / steps,
                      "step_frac": pairs * FLOP_PER_PAIR * steps / (dev_ms * 1e-3) / 1e12 / world / peaks["tflops"]},

@@ -144,6 +144,10 @@ struct mdsctk_knn_ctx {
     long long chunk_rows = 131072;   // fit rows per internal row block of a query (bounds the candidate-list memory)
     long long audit_rows = 8;        // certified rows per row block recomputed exactly and compared (0 = off)
     bool force_exact = false;        // every row through the exact FP64 path (test hook)
+    // ring-stage-ordered copy of the reference fp16 planes (rms_tc2.cu).  Off by default: measured neutral (C3 63.3 vs 63.6 ms,
+    // C4 block 866 vs 873 ms) -- the ring's copy latency does not come from the 72 strided rows of a stage -- and it costs 1.9 GB
+    bool ref_tiled_on = false, ref_tiled_dirty = true;
+    DevBuf ref_tiled;
     int sweep_version = 2;           // 1xFP16 sweep: 2 = rms_tc2.cu where the fit tile fits (default), 1 = rms_tc.cu
     DevBuf audit_ids, audit_seq, audit_dist, audit_idx;
     float g_ref_max = 0.f;
@@ -349,7 +353,8 @@ int rms_run_block(mdsctk_knn_ctx *ctx, FrameSet &fitset, const RmsPlan &P, long 
             if (rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16 && ctx->sweep_version != 1 && rms_tc2_supported(ref.A_pad)) {
                 CK(launch_rms_sweep_tc2(fit, fit_begin, n_fit, ref, do_fit, P.n_seg, cl, ctx->row_tau.as<float>(), ctx->g_ref_max,
                                         P.oos ? ctx->own_tile.as<int>() : nullptr,
-                                        ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr, ctx->n_sms, ctx->st),
+                                        ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr,
+                                        ctx->ref_tiled_on ? ctx->ref_tiled.p : nullptr, ctx->n_sms, ctx->st),
                    "rms_sweep_tc2");
                 S.sweep_version = 2;
             } else {
@@ -498,37 +503,72 @@ int rms_run(mdsctk_knn_ctx *ctx, FrameSet &fitset, long long fit_begin, long lon
         }
         CK(cudaStreamSynchronize(ctx->st), "sync max(gres)");
         ctx->gmax_dirty = false;
+        ctx->ref_tiled_dirty = true;
+    }
+    if (P.rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16 && ctx->sweep_version != 1 && ctx->ref_tiled_on && rms_tc2_supported(ref.A_pad) &&
+        (ctx->ref_tiled_dirty || !ctx->ref_tiled.p)) {
+        ctx->tm.start(ctx->st);
+        CK(ctx->ref_tiled.reserve(rms_tc2_tiled_bytes(ref.n, ref.A_pad)), "cudaMalloc(ref_tiled)");
+        CK(launch_rms_tc2_tile_reference(ref.fh, ref.n, ref.A_pad, ctx->ref_tiled.p, ctx->st), "tile_reference");
+        ctx->stats.ms_pack += ctx->tm.stop(ctx->st);
+        ctx->ref_tiled_dirty = false;
     }
 
-    const long long block = std::min<long long>(n_fit, std::max<long long>(256, ctx->chunk_rows));
     P.use_tc = P.rms_kernel != MDSCTK_KNN_RMS_SIMT_FP32;
+    // Row blocks: at most chunk_rows rows, balanced, and -- for the persistent tensor-core sweep, whose work items are 256-row
+    // super-tiles taken by the SM pairs in waves -- a whole number of waves each, so that only the last block of a query has a
+    // partial wave (the segment count of every block is chosen for ITS item count: rms_tc_choose_segments).
+    long long block = std::min<long long>(n_fit, std::max<long long>(256, ctx->chunk_rows));
+    if (n_fit > block) {
+        const long long n_blocks = (n_fit + block - 1) / block;
+        block = (n_fit + n_blocks - 1) / n_blocks;
+        if (P.use_tc) {
+            const long long wave = (long long)std::max(1, ctx->n_sms / 2) * 256;
+            if (block >= wave) block = (block + wave - 1) / wave * wave;
+        }
+    }
     choose_lists(ctx, P.rms_kernel, k1, &P.keep, &P.cap);
     // tensor-core sweep: four private sub-lists per (row, segment), merged into one at the end of the segment
     if (P.use_tc) P.cap = rms_tc_list_stride(P.keep);
-    P.n_seg = P.use_tc ? rms_tc_choose_segments(block, ref.n, ctx->n_sms) : 1;
-    P.H = P.use_tc ? rms_tc_lists_per_segment() * P.n_seg : 1;
     P.oos = &fitset != &ctx->ref;      // out-of-sample: the fit rows are not reference frames
+    auto plan_block = [&](long long nb, RmsPlan *Pb) {
+        *Pb = P;
+        Pb->n_seg = P.use_tc ? rms_tc_choose_segments(nb, ref.n, ctx->n_sms) : 1;
+        Pb->H = P.use_tc ? rms_tc_lists_per_segment() * Pb->n_seg : 1;
+    };
+    size_t max_lists = 0, max_rows = 0;
+    int max_H = 1;
+    for (long long off = 0; off < n_fit; off += block) {
+        const long long nb = std::min(block, n_fit - off);
+        RmsPlan Pb;
+        plan_block(nb, &Pb);
+        max_lists = std::max(max_lists, (size_t)nb * Pb.H);
+        max_rows = std::max(max_rows, (size_t)nb);
+        max_H = std::max(max_H, Pb.H);
+    }
     S.k_keep = P.keep;
-    S.lists_per_row = P.H;
-    if ((size_t)ref.A * 48 + (size_t)std::min(P.keep * P.H, 2048) * 2 * 28 + 64 * 80 > 220 * 1024 || P.keep > 2048)
+    S.lists_per_row = max_H;
+    if ((size_t)ref.A * 48 + (size_t)std::min(P.keep * max_H, 2048) * 2 * 28 + 64 * 80 > 220 * 1024 || P.keep > 2048)
         return fail(ctx, MDSCTK_KNN_EINVAL, "k too large for the FP64 re-score kernel's shared memory");
-    CK(ctx->cand_key.reserve((size_t)block * P.H * P.cap * 4), "cudaMalloc(cand_key)");
-    CK(ctx->cand_idx.reserve((size_t)block * P.H * P.cap * 4), "cudaMalloc(cand_idx)");
-    CK(ctx->cand_cnt.reserve((size_t)block * P.H * 4), "cudaMalloc(cand_cnt)");
-    CK(ctx->cand_tau.reserve((size_t)block * P.H * 8), "cudaMalloc(cand_tau)");
-    CK(ctx->flags.reserve((size_t)block * 4), "cudaMalloc(flags)");
-    CK(ctx->bad_rows.reserve((size_t)block * 4), "cudaMalloc(bad_rows)");
+    CK(ctx->cand_key.reserve(max_lists * P.cap * 4), "cudaMalloc(cand_key)");
+    CK(ctx->cand_idx.reserve(max_lists * P.cap * 4), "cudaMalloc(cand_idx)");
+    CK(ctx->cand_cnt.reserve(max_lists * 4), "cudaMalloc(cand_cnt)");
+    CK(ctx->cand_tau.reserve(max_lists * 8), "cudaMalloc(cand_tau)");
+    CK(ctx->flags.reserve(max_rows * 4), "cudaMalloc(flags)");
+    CK(ctx->bad_rows.reserve(max_rows * 4), "cudaMalloc(bad_rows)");
     CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
     CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
     if (P.use_tc) {
         if (ctx->debug_tile_on) CK(ctx->debug_tile.reserve(128 * 432 * 4), "cudaMalloc(debug_tile)");
-        CK(ctx->row_tau.reserve((size_t)block * 4), "cudaMalloc(row_tau)");
-        if (P.oos) CK(ctx->own_tile.reserve((size_t)((block + 255) / 256) * 4), "cudaMalloc(own_tile)");
+        CK(ctx->row_tau.reserve(max_rows * 4), "cudaMalloc(row_tau)");
+        if (P.oos) CK(ctx->own_tile.reserve((size_t)((max_rows + 255) / 256) * 4), "cudaMalloc(own_tile)");
     }
     ctx->out_rows = n_fit; ctx->out_k1 = k1;
     for (long long off = 0; off < n_fit; off += block) {
         const long long nb = std::min(block, n_fit - off);
-        if ((rc = rms_run_block(ctx, fitset, P, fit_begin + off, nb, off)) != 0) return rc;
+        RmsPlan Pb;
+        plan_block(nb, &Pb);
+        if ((rc = rms_run_block(ctx, fitset, Pb, fit_begin + off, nb, off)) != 0) return rc;
     }
     if (out_dist || out_idx) {
         rc = mdsctk_knn_fetch(ctx, out_dist, out_idx);
@@ -877,7 +917,7 @@ void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx)
                        &ctx->dt_ref_norm1, &ctx->dt_ref_g, &ctx->dt_fit_norm1, &ctx->dt_fit_g, &ctx->fb_rows, &ctx->fb_key,
                        &ctx->fb_idx, &ctx->fb_cnt, &ctx->fb_tau, &ctx->fb_dist, &ctx->fb_oidx, &ctx->fb_stats, &ctx->c_idx, &ctx->c_dist,
                        &ctx->c_ints, &ctx->c_key, &ctx->c_val, &ctx->c_irow, &ctx->c_oval, &ctx->f_in, &ctx->f_ang, &ctx->f_sc,
-                       &ctx->audit_ids, &ctx->audit_seq, &ctx->audit_dist, &ctx->audit_idx, &ctx->s_int, &ctx->s_val, &ctx->s_vec, &ctx->s_basis, &ctx->s_rot, &ctx->s_small, &ctx->s_evec})
+                       &ctx->ref_tiled, &ctx->audit_ids, &ctx->audit_seq, &ctx->audit_dist, &ctx->audit_idx, &ctx->s_int, &ctx->s_val, &ctx->s_vec, &ctx->s_basis, &ctx->s_rot, &ctx->s_small, &ctx->s_evec})
         b2->release();
     ctx->tm.destroy();
     ctx->user_tm.destroy();
@@ -913,6 +953,8 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
     } else if (!strcmp(key, "sweep_version")) {
         if (value != 1 && value != 2) return fail(ctx, MDSCTK_KNN_EINVAL, "sweep_version must be 1 or 2");
         ctx->sweep_version = (int)value;
+    } else if (!strcmp(key, "ref_tiled")) {
+        ctx->ref_tiled_on = value != 0;
     } else if (!strcmp(key, "force_exact")) {
         ctx->force_exact = value != 0;
     } else if (!strcmp(key, "debug_tile")) {

@@ -108,6 +108,7 @@ struct Tc2Args {
     int tmem_unit0[3];            // plane p: its k-steps [2 chunks[p], nks) live in TMEM units tmem_unit0[p]..
     int n_tmem_units, n_res_chunks, nst;
     int dbg;
+    int tiled;                    // the reference operand is in ring-stage order (tile_reference_kernel): coordinates (0, 0, stage)
     uint32_t idesc;               // instruction descriptor (M=256, N=144, fp16 -> fp32; other N only in timing experiments)
     long long *prof;
 };
@@ -356,10 +357,12 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #endif
                     if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(&c.bar_full[s], 2u * B_STAGE);
-                        tma_load_3d_2sm(ring + (size_t)s * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s, kc * 32, r0, 0, kEvictNormal);
+                        if (a.tiled) tma_load_3d_2sm(ring + (size_t)s * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s, 0, 0, (r0 / TRH) * nkc + kc, kEvictNormal);
+                        else tma_load_3d_2sm(ring + (size_t)s * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s, kc * 32, r0, 0, kEvictNormal);
                         if (ng > 1) {
                             if (rank == 0) mbar_expect_tx(&c.bar_full[s1], 2u * B_STAGE);
-                            tma_load_3d_2sm(ring + (size_t)s1 * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s1, (kc + 1) * 32, r0, 0, kEvictNormal);
+                            if (a.tiled) tma_load_3d_2sm(ring + (size_t)s1 * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s1, 0, 0, (r0 / TRH) * nkc + kc + 1, kEvictNormal);
+                            else tma_load_3d_2sm(ring + (size_t)s1 * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s1, (kc + 1) * 32, r0, 0, kEvictNormal);
                         }
                     }
                     __syncwarp();
@@ -925,20 +928,73 @@ bool make_map(CUtensorMap *m, const void *planes, long long n, int A_pad, int ro
                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ring-stage-ordered reference operand as a 3-D tensor (32 atoms, 72 rows, stage); one box = one contiguous stage
+bool make_tiled_map(CUtensorMap *m, const void *tiled, long long n_stages)
+{
+    EncodeTiledFn enc = get_tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {32, 72, (cuuint64_t)n_stages};
+    cuuint64_t strides[2] = {64, (cuuint64_t)tc2::B_STAGE};
+    cuuint32_t box[3] = {32, 72, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(tiled), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 bool rms_tc2_supported(int A_pad) { return tc2_layout(A_pad).ok; }
 
+// Reference operand in RING-STAGE order: [half-tile of 24 frames][chunk of 32 atoms][plane][frame][32 atoms] fp16, i.e. every
+// 4.6 KB stage the sweep's ring loads is one contiguous block of global memory (72 adjacent 64-byte rows) instead of 72
+// rows 6 A_pad bytes apart in the frame-major planes: the copy engine fetches 36 full 128-byte lines per stage.  Frames
+// beyond n and atoms beyond A_pad are zero.  Built once per reference set from the fp16 planes (1.9 GB at 1M x 300).
+__global__ void tile_reference_kernel(const __half *__restrict__ fh, long long n, int A_pad, int nkc, long long n_half_tiles,
+                                      uint4 *__restrict__ out)
+{
+    const long long total = n_half_tiles * nkc * 72 * 4;           // 16-byte vectors
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
+        const int c16 = (int)(v & 3);
+        long long r = v >> 2;
+        const int row = (int)(r % 72); r /= 72;
+        const int kc = (int)(r % nkc);
+        const long long ht = r / nkc;
+        const int plane = row / 24;
+        const long long frame = ht * 24 + row % 24;
+        const int atom = kc * 32 + c16 * 8;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (frame < n && atom < A_pad) val = *reinterpret_cast<const uint4 *>(fh + ((size_t)frame * 3 + plane) * A_pad + atom);
+        out[v] = val;
+    }
+}
+
+size_t rms_tc2_tiled_bytes(long long n_ref, int A_pad)
+{
+    const long long n_half_tiles = 2 * ((n_ref + tc2::TR - 1) / tc2::TR);
+    return (size_t)n_half_tiles * ((A_pad + 31) / 32) * tc2::B_STAGE;
+}
+
+cudaError_t launch_rms_tc2_tile_reference(const void *fh, long long n_ref, int A_pad, void *tiled, cudaStream_t st)
+{
+    if (n_ref <= 0) return cudaSuccess;
+    const long long n_half_tiles = 2 * ((n_ref + tc2::TR - 1) / tc2::TR);
+    tile_reference_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const __half *>(fh), n_ref, A_pad, (A_pad + 31) / 32, n_half_tiles,
+                                                   static_cast<uint4 *>(tiled));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rms_sweep_tc2(const FrameSetView &fit, long long fit_begin, long long n_fit, const FrameSetView &ref, int do_fit,
                                  int n_seg, CandLists<float> cl, float *row_tau, float g_ref_max, int *own_tile_scratch,
-                                 float *debug_tile, int n_sms, cudaStream_t st)
+                                 float *debug_tile, const void *ref_tiled, int n_sms, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
     if (cl.H != n_seg || cl.cap < cl.keep + tc2::SUBS * tc2::SUB_APP) return cudaErrorInvalidValue;
     const Tc2Layout L = tc2_layout(ref.A_pad);
     if (!L.ok) return cudaErrorInvalidConfiguration;
     CUtensorMap mq, mr;
-    if (!make_map(&mq, fit.fh, fit.n, fit.A_pad, tc2::TQ, 1) || !make_map(&mr, ref.fh, ref.n, ref.A_pad, tc2::TRH, 3))
+    if (!make_map(&mq, fit.fh, fit.n, fit.A_pad, tc2::TQ, 1)) return cudaErrorInvalidValue;
+    if (ref_tiled ? !make_tiled_map(&mr, ref_tiled, (long long)(rms_tc2_tiled_bytes(ref.n, ref.A_pad) / tc2::B_STAGE))
+                  : !make_map(&mr, ref.fh, ref.n, ref.A_pad, tc2::TRH, 3))
         return cudaErrorInvalidValue;
     Tc2Args a = {};
     a.q_G = fit.Gh; a.r_G = ref.Gh;
@@ -949,6 +1005,7 @@ cudaError_t launch_rms_sweep_tc2(const FrameSetView &fit, long long fit_begin, l
     a.pre_rel = (a.dbg & 2048) ? -1.0f : 4.9e-4f;           // relative rounding error of one fp16 operand (2^-11)
     a.pre_sqrt_gmax = sqrtf(g_ref_max > 0.f ? g_ref_max : 0.f);
     a.q_fh = static_cast<const __half *>(fit.fh);
+    a.tiled = ref_tiled != nullptr;
     a.nkc = L.nkc; a.nks = L.nks; a.n_tmem_units = L.n_tmem_units; a.n_res_chunks = L.n_res_chunks; a.nst = L.nst;
     for (int p = 0; p < 3; ++p) { a.chunks[p] = L.chunks[p]; a.chunk_base[p] = L.chunk_base[p]; a.tmem_unit0[p] = L.tmem_unit0[p]; }
     a.idesc = tc2::IDESC;

@@ -20,7 +20,8 @@ for name, n, basins, seed, k1, rows in (("C3", 100000, 16, 20260117, 33, 0), ("s
     ctx.rms_set_reference(xyz, mass)
     ref = None
     for ver in [int(v) for v in os.environ.get('VERSIONS', '1 2 2').split()]:
-        ctx.set_option("sweep_version", ver)
+        ctx.set_option("sweep_version", abs(ver))
+        ctx.set_option("ref_tiled", 0 if ver < 0 else 1)       # -2: version 2 with the frame-major reference planes
         fr = (0, rows) if rows else None
         ctx.rms_query(k1, fit_range=fr, fetch=False)
         d, i = ctx.rms_query(k1, fit_range=fr)

@@ -106,8 +106,9 @@ const char *mdsctk_knn_last_error(const mdsctk_knn_ctx *ctx);
  * operand planes that kernel reads -- a later change re-packs from the resident raw frames),
  * "slack" (extra candidates kept per row, -1 = auto),
  * "cert_scale_ppm" (certificate margin multiplier in parts-per-million of the default),
- * "chunk_rows" (fit rows per internal row block of a query, default 131072: bounds the candidate-list memory the
- * way the reference's --block-size bounds its row buffers, knn_rms.cpp:213-221),
+ * "chunk_rows" (fit rows per internal row block of a query; 0 = auto, the default: as many rows as 6 GB of candidate
+ * lists allow for the RMSD path -- 265 216 at k = 64 -- and 131072 for knn_data; bounds the working memory the way the
+ * reference's --block-size bounds its row buffers, knn_rms.cpp:213-221),
  * "data_kernel" (-1 auto, 0 exact FP64 sweep, 1 / 2 tensor-core filter with 3 / 1 fp16 parts + exact re-score),
  * "audit_rows" (RMSD path: certified rows per row block that are recomputed through the exact FP64 path and
  * compared, default 8; a mismatch makes the query return MDSCTK_KNN_EAUDIT; 0 = off),

@@ -141,13 +141,14 @@ struct mdsctk_knn_ctx {
     DevBuf wnorm;  // double[2A]: m_a / M, then sqrt(m_a / M)
     bool have_ref = false, gmax_dirty = true;
     int ref_pack_fam = F_FP16;   // operand families every shard of the current reference set is packed with (fixed at alloc)
-    long long chunk_rows = 131072;   // fit rows per internal row block of a query (bounds the candidate-list memory)
+    long long chunk_rows = 0;        // fit rows per internal row block of a query; 0 = as many as 6 GB of candidate lists allow
     long long audit_rows = 8;        // certified rows per row block recomputed exactly and compared (0 = off)
     bool force_exact = false;        // every row through the exact FP64 path (test hook)
     // ring-stage-ordered copy of the reference fp16 planes (rms_tc2.cu).  Off by default: measured neutral (C3 63.3 vs 63.6 ms,
     // C4 block 866 vs 873 ms) -- the ring's copy latency does not come from the 72 strided rows of a stage -- and it costs 1.9 GB
     bool ref_tiled_on = false, ref_tiled_dirty = true;
     DevBuf ref_tiled;
+    int rms_segments = 0;            // reference segments per fit super-tile (0 = chosen by rms_tc_choose_segments)
     int sweep_version = 2;           // 1xFP16 sweep: 2 = rms_tc2.cu where the fit tile fits (default), 1 = rms_tc.cu
     DevBuf audit_ids, audit_seq, audit_dist, audit_idx;
     float g_ref_max = 0.f;
@@ -518,7 +519,14 @@ int rms_run(mdsctk_knn_ctx *ctx, FrameSet &fitset, long long fit_begin, long lon
     // Row blocks: at most chunk_rows rows, balanced, and -- for the persistent tensor-core sweep, whose work items are 256-row
     // super-tiles taken by the SM pairs in waves -- a whole number of waves each, so that only the last block of a query has a
     // partial wave (the segment count of every block is chosen for ITS item count: rms_tc_choose_segments).
-    long long block = std::min<long long>(n_fit, std::max<long long>(256, ctx->chunk_rows));
+    choose_lists(ctx, P.rms_kernel, k1, &P.keep, &P.cap);
+    // tensor-core sweep: four private sub-lists per (row, segment), merged into one at the end of the segment
+    if (P.use_tc) P.cap = rms_tc_list_stride(P.keep);
+    // few, large blocks: a launch ends with the pairs finishing up to one work item apart (an item is ~25 ms at 1M frames), so
+    // every extra launch costs a few per cent; the candidate lists (rows x segments x cap x 8 B) are what limits a block
+    long long auto_rows = (long long)(6.0e9 / ((double)(P.use_tc ? 4 : 1) * P.cap * 8.0));
+    auto_rows = std::max<long long>(16384, std::min<long long>(auto_rows, 1LL << 20));
+    long long block = std::min<long long>(n_fit, ctx->chunk_rows > 0 ? std::max<long long>(256, ctx->chunk_rows) : auto_rows);
     if (n_fit > block) {
         const long long n_blocks = (n_fit + block - 1) / block;
         block = (n_fit + n_blocks - 1) / n_blocks;
@@ -527,13 +535,10 @@ int rms_run(mdsctk_knn_ctx *ctx, FrameSet &fitset, long long fit_begin, long lon
             if (block >= wave) block = (block + wave - 1) / wave * wave;
         }
     }
-    choose_lists(ctx, P.rms_kernel, k1, &P.keep, &P.cap);
-    // tensor-core sweep: four private sub-lists per (row, segment), merged into one at the end of the segment
-    if (P.use_tc) P.cap = rms_tc_list_stride(P.keep);
     P.oos = &fitset != &ctx->ref;      // out-of-sample: the fit rows are not reference frames
     auto plan_block = [&](long long nb, RmsPlan *Pb) {
         *Pb = P;
-        Pb->n_seg = P.use_tc ? rms_tc_choose_segments(nb, ref.n, ctx->n_sms) : 1;
+        Pb->n_seg = P.use_tc ? (ctx->rms_segments > 0 ? ctx->rms_segments : rms_tc_choose_segments(nb, ref.n, ctx->n_sms)) : 1;
         Pb->H = P.use_tc ? rms_tc_lists_per_segment() * Pb->n_seg : 1;
     };
     size_t max_lists = 0, max_rows = 0;
@@ -828,7 +833,7 @@ int data_run(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long lon
     CK(ctx->out_dist.reserve((size_t)n_fit * k1 * 8), "cudaMalloc(out_dist)");
     CK(ctx->out_idx.reserve((size_t)n_fit * k1 * 4), "cudaMalloc(out_idx)");
     ctx->out_rows = n_fit; ctx->out_k1 = k1;
-    const long long block = std::min<long long>(n_fit, std::max<long long>(256, ctx->chunk_rows));
+    const long long block = std::min<long long>(n_fit, ctx->chunk_rows > 0 ? std::max<long long>(256, ctx->chunk_rows) : 131072);
     mdsctk_knn_stats tot = ctx->stats;
     tot.ms_sweep = tot.ms_rescore = tot.ms_fallback = tot.ms_download = 0;
     tot.launches = 0; tot.fallback_rows = 0; tot.max_filter_err = 0; tot.max_filter_spread = 0; tot.rescored_max = 0;
@@ -945,7 +950,7 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
             return fail(ctx, MDSCTK_KNN_EINVAL, "data_kernel must be -1 (auto), 0 (exact), 1 (tensor, 3xFP16) or 2 (tensor, 1xFP16)");
         ctx->data_kernel = (int)value;
     } else if (!strcmp(key, "chunk_rows")) {
-        if (value < 256) return fail(ctx, MDSCTK_KNN_EINVAL, "chunk_rows must be >= 256");
+        if (value != 0 && value < 256) return fail(ctx, MDSCTK_KNN_EINVAL, "chunk_rows must be 0 (auto) or >= 256");
         ctx->chunk_rows = value;
     } else if (!strcmp(key, "audit_rows")) {
         if (value < 0 || value > 65536) return fail(ctx, MDSCTK_KNN_EINVAL, "audit_rows out of range");
@@ -953,6 +958,9 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
     } else if (!strcmp(key, "sweep_version")) {
         if (value != 1 && value != 2) return fail(ctx, MDSCTK_KNN_EINVAL, "sweep_version must be 1 or 2");
         ctx->sweep_version = (int)value;
+    } else if (!strcmp(key, "rms_segments")) {
+        if (value < 0 || value > 32) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_segments must be 0 (auto) .. 32");
+        ctx->rms_segments = (int)value;
     } else if (!strcmp(key, "ref_tiled")) {
         ctx->ref_tiled_on = value != 0;
     } else if (!strcmp(key, "force_exact")) {

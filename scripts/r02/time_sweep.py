@@ -7,13 +7,15 @@ import mdsctk_b200
 from mdsctk_b200 import synth
 import bench
 ctx = mdsctk_b200.KnnContext(0)
+if os.environ.get('SEGMENTS'):
+    ctx.set_option('rms_segments', int(os.environ['SEGMENTS']))
 if int(os.environ.get('MDSCTK_TC_DEBUG', '0')):
     ctx.set_option('audit_rows', 0)
 ATOMS = int(os.environ.get("ATOMS", 300))
 bench.ATOMS = ATOMS
 mass = synth.traj_masses(ATOMS)
 for name, n, basins, seed, k1, rows in (("C3", 100000, 16, 20260117, 33, 0), ("single-basin", 100000, 1, 20260117, 33, 0),
-                                        ("C4 first block", int(os.environ.get("C4N", 1000000)), 64, 20260118, 65, 131072)):
+                                        ("C4 first block", int(os.environ.get("C4N", 1000000)), 64, 20260118, 65, int(os.environ.get("C4ROWS", 132608)))):
     if os.environ.get("ONLY") and os.environ["ONLY"] not in name:
         continue
     xyz = bench.gen_frames(dict(n_total=n, basins=basins, seed=seed), 0, n)

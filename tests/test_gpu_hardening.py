@@ -103,10 +103,10 @@ def test_pack_outputs_against_numpy(ctx):
 
 def test_row_blocks_and_kernel_switches_give_identical_lists(ctx, trpcage):
     xyz, mass = trpcage
-    d0, i0, _ = query(ctx, xyz, mass, 10, rms_kernel=6, chunk_rows=131072)
+    d0, i0, _ = query(ctx, xyz, mass, 10, rms_kernel=6, chunk_rows=0)
     d1, i1, st = query(ctx, xyz, mass, 10, chunk_rows=256)                       # 4 row blocks
     assert np.array_equal(i0, i1) and np.array_equal(d0, d1) and st["audit_rows"] == 4 * 8
-    ctx.set_option("chunk_rows", 131072)
+    ctx.set_option("chunk_rows", 0)
     for kern in (4, 3, 1, 5, 0, 6):                                               # planes of each family written on demand
         ctx.set_option("rms_kernel", kern)
         d, i = ctx.rms_query(11)
@@ -117,7 +117,7 @@ def test_row_blocks_and_kernel_switches_give_identical_lists(ctx, trpcage):
     da, ia = ctx.data_query(11)
     ctx.set_option("chunk_rows", 300)
     db, ib = ctx.data_query(11)
-    ctx.set_option("chunk_rows", 131072)
+    ctx.set_option("chunk_rows", 0)
     assert np.array_equal(da, db) and np.array_equal(ia, ib)
 
 

@@ -148,6 +148,7 @@ struct mdsctk_knn_ctx {
     // C4 block 866 vs 873 ms) -- the ring's copy latency does not come from the 72 strided rows of a stage -- and it costs 1.9 GB
     bool ref_tiled_on = false, ref_tiled_dirty = true;
     DevBuf ref_tiled;
+    int data_segments = 0;           // same for the knn_data tensor filter
     int rms_segments = 0;            // reference segments per fit super-tile (0 = chosen by rms_tc_choose_segments)
     int sweep_version = 2;           // 1xFP16 sweep: 2 = rms_tc2.cu where the fit tile fits (default), 1 = rms_tc.cu
     DevBuf audit_ids, audit_seq, audit_dist, audit_idx;
@@ -679,7 +680,7 @@ int data_run_tc(mdsctk_knn_ctx *ctx, const double *d_fit, bool fit_is_ref, long 
     const long long slack = ctx->slack >= 0 ? ctx->slack : std::max<long long>(32, k1 / 2);
     const int keep = (int)(((long long)k1 + slack + 7) / 8 * 8);
     const int cap = data_tc_list_stride(keep);
-    const int n_seg = data_tc_choose_segments(n_fit, n_ref, ctx->n_sms);
+    const int n_seg = ctx->data_segments > 0 ? ctx->data_segments : data_tc_choose_segments(n_fit, n_ref, ctx->n_sms);
     S.k_keep = keep; S.lists_per_row = n_seg;
     if ((size_t)dim * 8 + (size_t)keep * n_seg * 2 * 28 > 170 * 1024) return 1;   // re-score working set: exact path instead
     CandLists<float> cl;
@@ -961,6 +962,9 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
     } else if (!strcmp(key, "rms_segments")) {
         if (value < 0 || value > 32) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_segments must be 0 (auto) .. 32");
         ctx->rms_segments = (int)value;
+    } else if (!strcmp(key, "data_segments")) {
+        if (value < 0 || value > 8) return fail(ctx, MDSCTK_KNN_EINVAL, "data_segments must be 0 (auto) .. 8");
+        ctx->data_segments = (int)value;
     } else if (!strcmp(key, "ref_tiled")) {
         ctx->ref_tiled_on = value != 0;
     } else if (!strcmp(key, "force_exact")) {

@@ -205,6 +205,10 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
     const int nkc = a.nkc, nst = a.nst;
+    // ring stages per producer / issuer round.  One: a slot is refilled the moment its six MMAs retire and consumed the moment it
+    // lands (measured: waits for reference stages 3.7k -> 1.8k clk per pass, pass 9.09k -> 8.75k on C4; bit 128 of the experiment
+    // build restores pairs, which halve the number of rounds but make each slot wait for its neighbour twice)
+    const int grp = (a.dbg & 128) ? 2 : 1;
     const long long n_qt = (a.n_q + UMMA_M - 1) / UMMA_M;
     const long long n_rt = (a.n_r + TR - 1) / TR;
     const long long n_items = n_qt * a.n_seg;
@@ -336,8 +340,8 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 }
                 // two chunks per round: one wait / elect round per 9 KB instead of per 4.6 KB (the producer is a single
                 // warp too, and its per-chunk overhead is part of the ring's round-trip time)
-                for (int kc = 0; kc < nkc; kc += 2) {
-                    const int ng = min(2, nkc - kc);
+                for (int kc = 0; kc < nkc; kc += grp) {
+                    const int ng = min(grp, nkc - kc);
                     int s1 = s + 1; uint32_t ph1 = ph;
                     if (s1 == nst) { s1 = 0; ph1 ^= 1; }
                     if (!(a.dbg & 4096)) {               // suspending waits (hardware sleeps the warp until the barrier flips)
@@ -428,7 +432,7 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     if (!rdy) {
                         const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                         int s2 = s; uint32_t ph2 = ph;
-                        for (int u = 0; u < min(2, nkc); ++u) {
+                        for (int u = 0; u < min(grp, nkc); ++u) {
                             mbar_wait_spin(&c.bar_full[s2], ph2, 3);
                             if (++s2 == nst) { s2 = 0; ph2 ^= 1; }
                         }
@@ -457,8 +461,8 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     }
                     ++n_pass;
                     // ---- MMAs of the pass, two stages (four k-steps) per group ----
-                    for (int kc0 = 0; kc0 < nkc; kc0 += 2) {
-                        const int ng = min(2, nkc - kc0);
+                    for (int kc0 = 0; kc0 < nkc; kc0 += grp) {
+                        const int ng = min(grp, nkc - kc0);
                         if (!rdy) {
                             const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                             int s2 = s; uint32_t ph2 = ph;
@@ -476,8 +480,8 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                         int sB = s + 1; if (sB == nst) sB = 0;
                         s += ng;
                         if (s >= nst) { s -= nst; ph ^= 1; }
-                        const bool last_group = kc0 + 2 >= nkc;
-                        const bool rdy_next = test_group(s, ph, last_group ? min(2, nkc) : min(2, nkc - kc0 - 2));
+                        const bool last_group = kc0 + grp >= nkc;
+                        const bool rdy_next = test_group(s, ph, last_group ? min(grp, nkc) : min(grp, nkc - kc0 - grp));
                         if (elect_one()) {
                             // One shared-memory stage (two k-steps, six MMAs) at a time.  Which operand form a plane uses can
                             // only change between stages (the shared-memory part of a plane is whole 64-byte chunks), so there is

@@ -6,9 +6,11 @@ import mdsctk_b200, bench
 n = int(os.environ.get("N", 200000))
 rows = bench.gen_rows(dict(bench.C5, n_total=n), 0, n)
 ctx = mdsctk_b200.KnnContext(0)
+if os.environ.get('SEGMENTS'):
+    ctx.set_option('data_segments', int(os.environ['SEGMENTS']))
 ctx.data_set_reference(rows)
 one_block = os.environ.get('ONE_BLOCK') == '1'          # profiling: the first row block only (131072 rows x all reference rows)
-for metric in (0, 1):
+for metric in ((0,) if os.environ.get('SEGMENTS') else (0, 1)):
     for rep in range(2):
         ctx.data_query(65, metric=metric, fetch=False, fit_range=(0, 131072) if one_block else None)
     st = ctx.stats()

@@ -43,6 +43,17 @@ def worker(rank, world, port, n_total, results):
     t = torch.tensor([count], dtype=torch.int64)
     dist.all_reduce(t)
     ok &= int(t) == n_total
+    # bench.py's cross-N output check: every rank hashes the k-lists of ITS rows with their global row numbers, the
+    # 64-bit sums are added over the ranks as two 32-bit halves -- the result must not depend on the sharding
+    import bench
+    rng = np.random.default_rng(5)
+    all_d = np.sort(rng.random((n_total, 9)), axis=1)
+    all_i = rng.integers(0, n_total, (n_total, 9)).astype(np.int32)
+    h = bench.lists_hash(all_d[begin:begin + count], all_i[begin:begin + count], begin) if count else 0
+    hv = torch.tensor([h & 0xFFFFFFFF, h >> 32], dtype=torch.int64)
+    dist.all_reduce(hv)
+    lo, hi = hv.tolist()
+    ok &= ((lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF) == bench.lists_hash(all_d, all_i, 0)
     results[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -523,8 +523,8 @@ int rms_run(mdsctk_knn_ctx *ctx, FrameSet &fitset, long long fit_begin, long lon
     choose_lists(ctx, P.rms_kernel, k1, &P.keep, &P.cap);
     // tensor-core sweep: four private sub-lists per (row, segment), merged into one at the end of the segment
     if (P.use_tc) P.cap = rms_tc_list_stride(P.keep);
-    // few, large blocks: a launch ends with the pairs finishing up to one work item apart (an item is ~25 ms at 1M frames), so
-    // every extra launch costs a few per cent; the candidate lists (rows x segments x cap x 8 B) are what limits a block
+    // few, large blocks: a launch ends with the pairs finishing up to one work item apart (an item is ~25 ms at 1M frames with
+    // four segments), so every extra launch costs a few per cent; the candidate lists (rows x segments x cap x 8 B) are what limits a block
     long long auto_rows = (long long)(6.0e9 / ((double)(P.use_tc ? 4 : 1) * P.cap * 8.0));
     auto_rows = std::max<long long>(16384, std::min<long long>(auto_rows, 1LL << 20));
     long long block = std::min<long long>(n_fit, ctx->chunk_rows > 0 ? std::max<long long>(256, ctx->chunk_rows) : auto_rows);

@@ -791,26 +791,26 @@ static bool make_plane_map(CUtensorMap *m, const void *planes, long long n, int 
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Reference segments per fit super-tile.  Two things decide: (1) whole waves of work items over the CTA pairs, and
-// (2) -- measured in round 2 -- how the pairs share the reference stream: after the diagonal items every pair sweeps the
-// SAME segment from its first tile, so the 74 pairs read the same reference tiles at nearly the same time and one HBM
-// fetch serves them all through L2; with one long segment each super-tile starts at its own tile and the pairs drift
-// apart (C4 block, 131 072 rows x 1M frames: 864 ms with 1 segment, 727 ms with 4, 704 ms with 12; C3: 72.8 / 63 / 60 ms
-// with 1 / 3 / 4).  More segments cost candidate lists (one per row and segment) and re-score merging (C4: 22 ms with 1,
-// 29 ms with 4, 50 ms with 8), so 4 is the sweet spot; every segment keeps at least 16 reference tiles.
+// Reference segments per fit super-tile.  A work item is (super-tile, segment), dealt statically to the CTA pairs, so two
+// things decide: (1) whole waves of items over the pairs, and (2) -- measured in round 2 -- the length of an item: with one
+// segment an item sweeps ALL reference frames (110 ms at 1M frames) and a launch ends with the pairs finishing up to one
+// item apart (C4 block, 131 072 rows x 1M frames: 864 ms with 1 segment, 727 ms with 4, 704 ms with 12; C3: 72.8 / 63 / 60 ms
+// with 1 / 3 / 4; clk per pass and DRAM traffic are the same -- it is the tail of the launch that shrinks).  More segments
+// cost candidate lists (one per row and segment) and re-score merging (C4: 22 ms with 1, 29 ms with 4, 50 ms with 8), so 4
+// is the sweet spot; every segment keeps at least 16 reference tiles.
 int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms)
 {
     const int n_pairs = n_sms / 2 > 0 ? n_sms / 2 : 1;
     const long long n_qt = (n_fit + tc::UMMA_M - 1) / tc::UMMA_M;
     const long long n_rt = (n_ref + tc::TR - 1) / tc::TR;
-    static const double locality[9] = {0.0, 0.84, 0.93, 0.97, 1.0, 0.97, 0.95, 0.94, 0.93};   // measured sweep + re-score time relative to 4 segments
+    static const double balance[9] = {0.0, 0.84, 0.93, 0.97, 1.0, 0.97, 0.95, 0.94, 0.93};   // measured sweep + re-score time relative to 4 segments
     int best = 1;
     double best_score = 0.0;
     for (int s = 1; s <= 8; ++s) {
         if (s > 1 && n_rt / s < 16) break;
         const long long items = n_qt * s;
         const double eff = (double)items / (double)(((items + n_pairs - 1) / n_pairs) * n_pairs);
-        const double score = eff * locality[s];
+        const double score = eff * balance[s];
         if (score > best_score + 1e-9) { best_score = score; best = s; }
     }
     return best;

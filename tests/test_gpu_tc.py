@@ -47,7 +47,7 @@ def test_tmem_accumulators_match_numpy(ctx, trpcage, kern, rtol):
     assert err.max() < rtol, f"max scaled error {err.max()}"
 
 
-@pytest.mark.parametrize("atoms,version", [(300, 2), (300, 1), (256, 2), (290, 2), (33, 2)])
+@pytest.mark.parametrize("atoms,version", [(300, 2), (300, 1), (256, 2), (290, 2), (33, 2), (20, 2), (5, 2), (304, 2)])
 def test_tmem_accumulators_1xfp16_resident_tile(ctx, atoms, version):
     """The default sweep (rms_tc2.cu) keeps the fit tile in shared memory and, beyond 256 atoms, its trailing k-steps in
     TMEM (tcgen05.mma with the A operand in tensor memory): raw accumulators against numpy on the fp16-rounded operands."""

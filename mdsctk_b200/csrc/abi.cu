@@ -962,6 +962,8 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
     } else if (!strcmp(key, "rms_segments")) {
         if (value < 0 || value > 32) return fail(ctx, MDSCTK_KNN_EINVAL, "rms_segments must be 0 (auto) .. 32");
         ctx->rms_segments = (int)value;
+    } else if (!strcmp(key, "data_streaming")) {
+        data_tc_set_streaming(value != 0);
     } else if (!strcmp(key, "data_segments")) {
         if (value < 0 || value > 8) return fail(ctx, MDSCTK_KNN_EINVAL, "data_segments must be 0 (auto) .. 8");
         ctx->data_segments = (int)value;

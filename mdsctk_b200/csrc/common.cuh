@@ -135,6 +135,7 @@ cudaError_t launch_data_pack(const double *rows, long long n, int dim, int D_pad
                              void *lo, float *norm, float *norm1, float *gres, cudaStream_t st);
 cudaError_t launch_data_stats_check(const double *stats, long long n, int *bad, cudaStream_t st);   // rows with a zero / non-finite spread
 int data_tc_pad_dim(int dim);
+void data_tc_set_streaming(bool on);   // test hook: force the streaming mode of the one-part knn_data filter (default: resident fit tile)
 int data_tc_list_stride(int keep);
 int data_tc_choose_segments(long long n_fit, long long n_ref, int n_sms);
 // fit_begin_in_ref: reference index of fit row 0 when the fit rows are reference rows, else -1

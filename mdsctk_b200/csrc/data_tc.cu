@@ -41,6 +41,9 @@ constexpr int OFF_AHI = 0, OFF_ALO = A_PART, OFF_BHI = 2 * A_PART, OFF_BLO = 2 *
 constexpr int STAGE_BYTES = 2 * A_PART + 2 * B_PART;   // 32768
 constexpr int NST = 6;
 constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;
+constexpr int MAX_NST = 10;                   // barrier slots (resident mode uses up to 10 ring stages)
+constexpr int RES_STAGE = 2 * B_PART;         // 16384 B: resident mode, one ring stage = two 32-dim chunks of this CTA's 128 reference rows
+constexpr int STATIC_SMEM = 9 * 1024;         // bound on the kernel's static shared memory (checked at launch)
 constexpr int SUBS = 4, EPI_WARPS = 16, NTHR = 64 + EPI_WARPS * 32;
 constexpr int SUBW = TR / SUBS;               // 64 reference columns per epilogue warp
 constexpr int EB = 16;                        // columns per tcgen05.ld
@@ -150,6 +153,7 @@ struct DataTcArgs {
     CandLists<float> cl;              // H = n_seg lists per fit row; key = approximate d^2 in input units
     float *row_tau;
     int one;                          // one-part filter: hi x hi only (q_norm / r_norm are then the norms of the hi parts)
+    int res, res_nst;                 // one-part filter with the fit tile RESIDENT in shared memory: on/off, ring stages beside it
 };
 
 __global__ void __launch_bounds__(dtc::NTHR, 1)
@@ -161,9 +165,9 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
     constexpr uint32_t STAGE_TX = 2u * STAGE_BYTES;
 
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_tmem_full[2], bar_tmem_empty[2];
+    __shared__ __align__(8) uint64_t bar_full[MAX_NST], bar_empty[MAX_NST], bar_tmem_full[2], bar_tmem_empty[2], bar_res_full, bar_res_empty;
     __shared__ uint32_t s_tmem_base;
-    __shared__ unsigned s_hist[EPI_WARPS][256];
+    __shared__ unsigned s_hist[EPI_WARPS][64];        // 64-bin radix histogram (select.cuh warp_compact_list6): every KB here is ring
     __shared__ int s_cnt[EPI_WARPS][32];
     __shared__ float s_tau[TQ];
     __shared__ int s_mcnt[TQ];
@@ -178,8 +182,10 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
     const long long pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < MAX_NST; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&bar_tmem_full[b], 1); mbar_init(&bar_tmem_empty[b], 2 * EPI_WARPS); }
+        mbar_init(&bar_res_full, 1);
+        mbar_init(&bar_res_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -215,11 +221,43 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
     if (warp == 0) {
         // =============================== TMA producer ===============================
         int s = 0;
-        uint32_t ph = 0;
+        uint32_t ph = 0, rph = 0;
+        bool first_item = true;
         for (long long it = pair_id; it < n_items; it += n_pairs) {
             long long qt, rt0, rt1, rot; int seg;
             item_range(it, qt, rt0, rt1, seg, rot);
             const int q0 = (int)(qt * UMMA_M + rank * TQ);
+            if (a.res) {
+                // Resident mode: the CTA's 128 fit rows (all D_pad dims, 8 KB per 32-dim chunk) are loaded ONCE per work item;
+                // the ring carries the reference rows only (two chunks per stage) -- half the L2 -> SM stream of the
+                // streaming mode, which is what bounds this kernel (ncu: 1.06 TB per 131 072 x 1M block = 5.7 TB/s).
+                if (!first_item) { mbar_wait(&bar_res_empty, rph, 5); rph ^= 1; }
+                first_item = false;
+                const uint32_t res_leader = map_to_cta(&bar_res_full, 0);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&bar_res_full, 2u * (uint32_t)(nk * A_PART));
+                    for (int kc = 0; kc < nk; ++kc) tma_load_2d_2sm(smem + kc * A_PART, &map_q_hi, res_leader, kc * KC, q0, kEvictNormal);
+                }
+                __syncwarp();
+                unsigned char *ring = smem + nk * A_PART;
+                const int nstage = (nk + 1) / 2;
+                for (long long ti = 0; ti < rt1 - rt0; ++ti) {
+                    const int r0 = (int)(tile_at(ti, rt0, rt1, rot) * TR + rank * TRH);
+                    for (int j = 0; j < nstage; ++j) {
+                        mbar_wait(&bar_empty[s], ph ^ 1, 1);
+                        const uint32_t full_leader = map_to_cta(&bar_full[s], 0);
+                        const int nch = min(2, nk - 2 * j);
+                        if (elect_one()) {
+                            if (rank == 0) mbar_expect_tx(&bar_full[s], 2u * (uint32_t)(nch * B_PART));
+                            for (int u = 0; u < nch; ++u)
+                                tma_load_2d_2sm(ring + s * RES_STAGE + u * B_PART, &map_r_hi, full_leader, (2 * j + u) * KC, r0, kEvictNormal);
+                        }
+                        __syncwarp();
+                        if (++s == a.res_nst) { s = 0; ph ^= 1; }
+                    }
+                }
+                continue;
+            }
             for (long long ti = 0; ti < rt1 - rt0; ++ti) {
                 const int r0 = (int)(tile_at(ti, rt0, rt1, rot) * TR + rank * TRH);
                 for (int kc = 0; kc < nk; ++kc) {
@@ -248,9 +286,12 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
             long long gp = 0;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+            uint32_t rfph = 0;
+            const uint32_t res_lo = umma_desc_lo(smem_u), ring_lo = umma_desc_lo(smem_u + (uint32_t)(nk * A_PART));
             for (long long it = pair_id; it < n_items; it += n_pairs) {
                 long long qt, rt0, rt1, rot; int seg;
                 item_range(it, qt, rt0, rt1, seg, rot);
+                if (a.res) { mbar_wait_spin(&bar_res_full, rfph, 6); rfph ^= 1; }      // this item's fit tile has landed
                 for (long long ti = 0; ti < rt1 - rt0; ++ti, ++gp) {
                     const int buf = (int)(gp & 1);
                     if (gp >= 2) {
@@ -259,6 +300,31 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
                     }
                     tc_fence_after();
                     const uint32_t d = tmem_u + buf * UMMA_N;
+                    if (a.res) {
+                        // resident mode: A from the resident tile, B from the ring; four MMAs (two chunks x two k-steps) per stage,
+                        // descriptors as low words differing by constants
+                        const int nstage = (nk + 1) / 2;
+                        for (int j = 0; j < nstage; ++j) {
+                            mbar_wait_spin(&bar_full[s], ph, 3);
+                            if (elect_one()) {
+                                const uint32_t a0 = res_lo + (uint32_t)(2 * j) * (A_PART >> 4), b0 = ring_lo + (uint32_t)s * (RES_STAGE >> 4);
+                                tc_mma2_lo<true>(d, a0, b0, IDESC, j != 0);
+                                tc_mma2_lo<true>(d, a0 + 2u, b0 + 2u, IDESC, 1);
+                                if (2 * j + 1 < nk) {
+                                    tc_mma2_lo<true>(d, a0 + (A_PART >> 4), b0 + (B_PART >> 4), IDESC, 1);
+                                    tc_mma2_lo<true>(d, a0 + (A_PART >> 4) + 2u, b0 + (B_PART >> 4) + 2u, IDESC, 1);
+                                }
+                                tc_commit2_mc(&bar_empty[s], 3);
+                                if (j == nstage - 1) {
+                                    tc_commit2_mc(&bar_tmem_full[buf], 3);
+                                    if (ti == rt1 - rt0 - 1) tc_commit2_mc(&bar_res_empty, 3);      // item done with its fit tile
+                                }
+                            }
+                            __syncwarp();
+                            if (++s == a.res_nst) { s = 0; ph ^= 1; }
+                        }
+                        continue;
+                    }
                     for (int kc = 0; kc < nk; ++kc) {
                         mbar_wait_spin(&bar_full[s], ph, 3);
                         tc_fence_after();
@@ -333,7 +399,7 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
                 }
                 float tl = s_tau[row];
                 if (total > a.cl.keep) {
-                    tl = fminf(tl, warp_compact_list<float>(lkeys + at, lidxs + at, total, a.cl.keep, hist));
+                    tl = fminf(tl, warp_compact_list6(lkeys + at, lidxs + at, total, a.cl.keep, hist));
                     total = a.cl.keep;
                 }
                 __syncwarp();
@@ -394,17 +460,27 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
                     if (h + EB == SUBW) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(buf ? empty_leader1 : empty_leader0);
+                        // (no cluster-scope release fence: the TMEM reads are ordered by tcgen05.wait::ld + fence::before_thread_sync)
+                        if (lane == 0) mbar_arrive_cluster_nofence(buf ? empty_leader1 : empty_leader0);
                     }
+                    // Nearly every batch holds no candidate once the row's threshold is tight: one fused multiply-add and one min
+                    // per key decide that (the epilogue, not the tensor pipe, paces this kernel: 64 keys per thread and pass),
+                    // the per-key tests and the append run only for a batch whose smallest key passes.  Rows beyond n_q carry
+                    // tau = -1 and never pass; reference columns beyond n_r are sorted out on the slow path.
+                    float kmin = fmaf(-2.0f, dv[0], nr[0]);
 #pragma unroll
-                    for (int j = 0; j < EB; ++j) {
-                        const float key = fmaf(-2.0f, dv[j], nq + nr[j]);
-                        if (key < tau_s && qvalid && rb + h + j < a.n_r) {
-                            if (cnt < SUB_APP) {
-                                my_keys[cnt] = fmaxf(key, 0.0f) * a.inv_scale2;
-                                my_idxs[cnt] = (int)(rb + h + j);
+                    for (int j = 1; j < EB; ++j) kmin = fminf(kmin, fmaf(-2.0f, dv[j], nr[j]));
+                    if (!(kmin + nq > tau_s * 1.000001f)) {      // (the two evaluation orders differ by an ulp: err on the side of the slow path)
+#pragma unroll
+                        for (int j = 0; j < EB; ++j) {
+                            const float key = fmaf(-2.0f, dv[j], nq + nr[j]);
+                            if (key < tau_s && qvalid && rb + h + j < a.n_r) {
+                                if (cnt < SUB_APP) {
+                                    my_keys[cnt] = fmaxf(key, 0.0f) * a.inv_scale2;
+                                    my_idxs[cnt] = (int)(rb + h + j);
+                                }
+                                ++cnt;
                             }
-                            ++cnt;
                         }
                     }
                 }
@@ -438,6 +514,9 @@ static bool make_row_map(CUtensorMap *m, const void *base, long long n, int D_pa
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool g_data_force_streaming = false;
+void data_tc_set_streaming(bool on) { g_data_force_streaming = on; }      // test hook: the round-1 streaming mode of the one-part filter
+static bool data_tc_force_streaming() { return g_data_force_streaming; }
 int data_tc_pad_dim(int dim) { return (dim + dtc::KC - 1) / dtc::KC * dtc::KC; }
 int data_tc_list_stride(int keep) { return (keep + dtc::SUBS * dtc::SUB_APP + 31) / 32 * 32; }
 
@@ -472,14 +551,25 @@ cudaError_t launch_data_sweep_tc(const void *fit_hi, const void *fit_lo, const f
     a.q_norm = fit_norm; a.r_norm = ref_norm; a.q_begin = fit_begin_in_ref; a.n_q = n_fit; a.n_r = n_ref;
     a.D_pad = D_pad; a.n_seg = n_seg; a.inv_scale2 = (float)(1.0 / (scale * scale)); a.cl = cl; a.row_tau = row_tau;
     a.one = one_part;
-    cudaError_t e = cudaFuncSetAttribute(data_sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dtc::SMEM_BYTES);
+    // resident fit tile (one-part filter): when 128 x D_pad fp16 fit rows leave room for >= 3 ring stages of reference rows
+    const int nk = D_pad / dtc::KC;
+    int res_nst = (227 * 1024 - dtc::STATIC_SMEM - 1024 - nk * dtc::A_PART) / dtc::RES_STAGE;
+    if (res_nst > dtc::MAX_NST) res_nst = dtc::MAX_NST;
+    a.res = one_part && res_nst >= 3 && !data_tc_force_streaming();
+    a.res_nst = res_nst;
+    const int smem_bytes = a.res ? nk * dtc::A_PART + res_nst * dtc::RES_STAGE + 1024 : dtc::SMEM_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(data_sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, data_sweep_tc_kernel);
+    if (e == cudaSuccess && fa.sharedSizeBytes > (size_t)dtc::STATIC_SMEM) e = cudaErrorInvalidConfiguration;
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(dtc::NTHR); cfg.dynamicSmemBytes = dtc::SMEM_BYTES; cfg.stream = st;
+    cfg.blockDim = dim3(dtc::NTHR); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = st;
     int max_pairs = n_sms / 2;
     cfg.gridDim = dim3((unsigned)(max_pairs * 2));
     int q = 0;

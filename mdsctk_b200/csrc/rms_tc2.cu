@@ -115,76 +115,6 @@ struct Tc2Args {
 
 namespace tc2 {
 
-// warp_compact_list with a 64-bin histogram (6-bit digits, 6 passes over the 32 key bits): a quarter of the shared memory
-// of the 256-bin version in select.cuh -- every kilobyte of control state is a kilobyte less of operand ring.  Same contract.
-__device__ float warp_compact_list6(float *keys, int *idxs, int cnt, int keep, unsigned *hist)
-{
-    const int lane = threadIdx.x & 31;
-    uint32_t prefix = 0, mask = 0;
-    int remaining = keep;
-    for (int pass = 0; pass < 6; ++pass) {
-        const int shift = pass < 5 ? 26 - 6 * pass : 0;
-        const uint32_t dmask = pass < 5 ? 63u : 3u;
-        hist[lane] = 0; hist[lane + 32] = 0;
-        __syncwarp();
-        for (int i = lane; i < cnt; i += 32) {
-            const uint32_t k = __float_as_uint(keys[i]);
-            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & dmask], 1u);
-        }
-        __syncwarp();
-        unsigned local[2], sum = 0;               // lane owns bins 2 lane, 2 lane + 1
-#pragma unroll
-        for (int j = 0; j < 2; ++j) { local[j] = hist[2 * lane + j]; sum += local[j]; }
-        unsigned incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const unsigned excl = incl - sum;
-        const unsigned hit = __ballot_sync(0xffffffffu, incl >= (unsigned)remaining);
-        const int owner = __ffs(hit) - 1;
-        int bin = 0, before = 0;
-        if (lane == owner) {
-            unsigned run = excl;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (run + local[j] >= (unsigned)remaining) { bin = 2 * lane + j; before = (int)run; break; }
-                run += local[j];
-            }
-        }
-        bin = __shfl_sync(0xffffffffu, bin, owner);
-        before = __shfl_sync(0xffffffffu, before, owner);
-        prefix |= (uint32_t)bin << shift;
-        mask |= dmask << shift;
-        remaining -= before;
-        __syncwarp();
-    }
-    const uint32_t kth = prefix;
-    int out = 0, eq_taken = 0;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    for (int base = 0; base < cnt; base += 32) {
-        const int i = base + lane;
-        const bool valid = i < cnt;
-        const float kv = valid ? keys[i] : __uint_as_float(0x7f800000u);
-        const int iv = valid ? idxs[i] : 0;
-        const uint32_t k = __float_as_uint(kv);
-        const bool eq = valid && k == kth;
-        const unsigned eqm = __ballot_sync(0xffffffffu, eq);
-        const bool take = valid && (k < kth || (eq && eq_taken + __popc(eqm & lt_mask) < remaining));
-        const unsigned tm = __ballot_sync(0xffffffffu, take);
-        if (take) {
-            const int pos = out + __popc(tm & lt_mask);
-            keys[pos] = kv;
-            idxs[pos] = iv;
-        }
-        out += __popc(tm);
-        eq_taken += __popc(eqm);
-        __syncwarp();
-    }
-    return __uint_as_float(kth);
-}
-
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p)
 {
     return *reinterpret_cast<const volatile uint32_t *>(p);

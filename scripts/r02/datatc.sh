@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_data_tc.py tests/test_gpu_parity.py -x -q 2>&1 | tail -30 > gpurun_out/datatc.log
-timeout 300 python scripts/r02/time_data.py >> gpurun_out/datatc.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_data_tc.py tests/test_gpu_parity.py tests/test_sparse.py tests/test_featurize.py -x -q -m gpu 2>&1 | tail -12 > gpurun_out/datatc.log
+STREAMING=1 N=1000000 ONE_BLOCK=1 timeout 300 python scripts/r02/time_data.py 2>&1 | tail -2 >> gpurun_out/datatc.log
+STREAMING=0 N=1000000 ONE_BLOCK=1 timeout 300 python scripts/r02/time_data.py 2>&1 | tail -2 >> gpurun_out/datatc.log
+STREAMING=0 N=200000 timeout 300 python scripts/r02/time_data.py 2>&1 | tail -2 >> gpurun_out/datatc.log
 cat gpurun_out/datatc.log

@@ -9,6 +9,8 @@ ctx = mdsctk_b200.KnnContext(0)
 if os.environ.get('SEGMENTS'):
     ctx.set_option('data_segments', int(os.environ['SEGMENTS']))
 ctx.data_set_reference(rows)
+if os.environ.get('STREAMING'):
+    ctx.set_option('data_streaming', int(os.environ['STREAMING']))
 one_block = os.environ.get('ONE_BLOCK') == '1'          # profiling: the first row block only (131072 rows x all reference rows)
 for metric in ((0,) if os.environ.get('SEGMENTS') else (0, 1)):
     for rep in range(2):

@@ -25,6 +25,11 @@
 #include <cuda_fp16.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
+
+#ifndef MDSCTK_TC_PROF_BUILD
+#define MDSCTK_TC_PROF_BUILD 0        // 1: compile the clock counters read by MDSCTK_TC_PROF=1 (scripts/build_prof.sh)
+#endif
 
 namespace mdsctk {
 
@@ -42,13 +47,16 @@ constexpr int STAGE_BYTES = 2 * A_PART + 2 * B_PART;   // 32768
 constexpr int NST = 6;
 constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;
 constexpr int MAX_NST = 10;                   // barrier slots (resident mode uses up to 10 ring stages)
-constexpr int RES_STAGE = 2 * B_PART;         // 16384 B: resident mode, one ring stage = two 32-dim chunks of this CTA's 128 reference rows
-constexpr int STATIC_SMEM = 9 * 1024;         // bound on the kernel's static shared memory (checked at launch)
+constexpr int RES_KC = 64;                    // resident mode: dims per chunk = 128-byte rows (SWIZZLE_128B): every L2 request is a whole line
+constexpr int RES_CHUNK = TQ * 2 * RES_KC;    // 16384 B: 128 fit rows x 64 dims
+constexpr int RES_STAGE = TRH * 2 * RES_KC;   // 16384 B: one ring stage = 64 dims of this CTA's 128 reference rows
+constexpr int STATIC_SMEM = 12 * 1024;        // bound on the kernel's static shared memory (checked at launch)
 constexpr int SUBS = 4, EPI_WARPS = 16, NTHR = 64 + EPI_WARPS * 32;
 constexpr int SUBW = TR / SUBS;               // 64 reference columns per epilogue warp
 constexpr int EB = 16;                        // columns per tcgen05.ld
 constexpr int SUB_APP = 2 * SUBW;             // 128: private append area per epilogue warp and row
 constexpr int TMEM_COLS = 512;
+static_assert(SUBW == 4 * EB, "the epilogue's pass loop is written out for four batches");
 }  // namespace dtc
 
 // ------------------------------------------------------------------------------ pack ----
@@ -154,9 +162,10 @@ struct DataTcArgs {
     float *row_tau;
     int one;                          // one-part filter: hi x hi only (q_norm / r_norm are then the norms of the hi parts)
     int res, res_nst;                 // one-part filter with the fit tile RESIDENT in shared memory: on/off, ring stages beside it
+    long long *prof;                  // clock counters per pair (prof builds with MDSCTK_TC_PROF=1 only), else NULL
 };
 
-__global__ void __launch_bounds__(dtc::NTHR, 1)
+__global__ void __launch_bounds__(dtc::NTHR, 1)      // 96 registers: 18 warps put 5 on one scheduler, 16 384 / (5 x 32) = 102
 data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                      const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo, DataTcArgs a)
 {
@@ -169,6 +178,7 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
     __shared__ uint32_t s_tmem_base;
     __shared__ unsigned s_hist[EPI_WARPS][64];        // 64-bin radix histogram (select.cuh warp_compact_list6): every KB here is ring
     __shared__ int s_cnt[EPI_WARPS][32];
+    __shared__ __align__(16) float s_rn[EPI_WARPS][SUBW];      // reference norms of the current pass, per epilogue warp
     __shared__ float s_tau[TQ];
     __shared__ int s_mcnt[TQ];
 
@@ -228,29 +238,27 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
             item_range(it, qt, rt0, rt1, seg, rot);
             const int q0 = (int)(qt * UMMA_M + rank * TQ);
             if (a.res) {
-                // Resident mode: the CTA's 128 fit rows (all D_pad dims, 8 KB per 32-dim chunk) are loaded ONCE per work item;
-                // the ring carries the reference rows only (two chunks per stage) -- half the L2 -> SM stream of the
-                // streaming mode, which is what bounds this kernel (ncu: 1.06 TB per 131 072 x 1M block = 5.7 TB/s).
+                // Resident mode: the CTA's 128 fit rows (all D_pad dims, 16 KB per 64-dim chunk) are loaded ONCE per work item;
+                // the ring carries the reference rows only -- half the L2 -> SM stream of the streaming mode, which is what
+                // bounds this kernel (ncu: 1.06 TB per 131 072 x 1M block = 5.7 TB/s) -- in 128-byte rows.
                 if (!first_item) { mbar_wait(&bar_res_empty, rph, 5); rph ^= 1; }
                 first_item = false;
                 const uint32_t res_leader = map_to_cta(&bar_res_full, 0);
+                const int nstage = (a.D_pad + RES_KC - 1) / RES_KC;      // a box reaching past D_pad is zero-filled (and counted in full)
                 if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&bar_res_full, 2u * (uint32_t)(nk * A_PART));
-                    for (int kc = 0; kc < nk; ++kc) tma_load_2d_2sm(smem + kc * A_PART, &map_q_hi, res_leader, kc * KC, q0, kEvictNormal);
+                    if (rank == 0) mbar_expect_tx(&bar_res_full, 2u * (uint32_t)(nstage * RES_CHUNK));
+                    for (int kc = 0; kc < nstage; ++kc) tma_load_2d_2sm(smem + kc * RES_CHUNK, &map_q_hi, res_leader, kc * RES_KC, q0, kEvictNormal);
                 }
                 __syncwarp();
-                unsigned char *ring = smem + nk * A_PART;
-                const int nstage = (nk + 1) / 2;
+                unsigned char *ring = smem + nstage * RES_CHUNK;
                 for (long long ti = 0; ti < rt1 - rt0; ++ti) {
                     const int r0 = (int)(tile_at(ti, rt0, rt1, rot) * TR + rank * TRH);
                     for (int j = 0; j < nstage; ++j) {
                         mbar_wait(&bar_empty[s], ph ^ 1, 1);
                         const uint32_t full_leader = map_to_cta(&bar_full[s], 0);
-                        const int nch = min(2, nk - 2 * j);
                         if (elect_one()) {
-                            if (rank == 0) mbar_expect_tx(&bar_full[s], 2u * (uint32_t)(nch * B_PART));
-                            for (int u = 0; u < nch; ++u)
-                                tma_load_2d_2sm(ring + s * RES_STAGE + u * B_PART, &map_r_hi, full_leader, (2 * j + u) * KC, r0, kEvictNormal);
+                            if (rank == 0) mbar_expect_tx(&bar_full[s], 2u * (uint32_t)RES_STAGE);
+                            tma_load_2d_2sm(ring + s * RES_STAGE, &map_r_hi, full_leader, j * RES_KC, r0, kEvictNormal);
                         }
                         __syncwarp();
                         if (++s == a.res_nst) { s = 0; ph ^= 1; }
@@ -287,7 +295,9 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
             uint32_t rfph = 0;
-            const uint32_t res_lo = umma_desc_lo(smem_u), ring_lo = umma_desc_lo(smem_u + (uint32_t)(nk * A_PART));
+            long long p_full = 0, p_empty = 0;
+            const long long p_t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
+            const uint32_t res_lo = umma_desc_lo(smem_u), ring_lo = umma_desc_lo(smem_u + (uint32_t)((a.D_pad + RES_KC - 1) / RES_KC * RES_CHUNK));
             for (long long it = pair_id; it < n_items; it += n_pairs) {
                 long long qt, rt0, rt1, rot; int seg;
                 item_range(it, qt, rt0, rt1, seg, rot);
@@ -295,24 +305,28 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
                 for (long long ti = 0; ti < rt1 - rt0; ++ti, ++gp) {
                     const int buf = (int)(gp & 1);
                     if (gp >= 2) {
+                        const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                         mbar_wait_spin(&bar_tmem_empty[buf], (eph >> buf) & 1u, 2);
                         eph ^= 1u << buf;
+                        if (MDSCTK_TC_PROF_BUILD && a.prof) p_empty += clock64() - t0;
                     }
                     tc_fence_after();
                     const uint32_t d = tmem_u + buf * UMMA_N;
                     if (a.res) {
-                        // resident mode: A from the resident tile, B from the ring; four MMAs (two chunks x two k-steps) per stage,
-                        // descriptors as low words differing by constants
-                        const int nstage = (nk + 1) / 2;
+                        // resident mode: A from the resident tile, B from the ring; four MMAs (k-steps of 16 dims = 32 B inside the
+                        // 128-byte swizzle atom) per stage, descriptors as low words differing by constants
+                        const int nstage = (a.D_pad + RES_KC - 1) / RES_KC;
                         for (int j = 0; j < nstage; ++j) {
+                            const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
                             mbar_wait_spin(&bar_full[s], ph, 3);
+                            if (MDSCTK_TC_PROF_BUILD && a.prof) p_full += clock64() - t0;
                             if (elect_one()) {
-                                const uint32_t a0 = res_lo + (uint32_t)(2 * j) * (A_PART >> 4), b0 = ring_lo + (uint32_t)s * (RES_STAGE >> 4);
-                                tc_mma2_lo<true>(d, a0, b0, IDESC, j != 0);
-                                tc_mma2_lo<true>(d, a0 + 2u, b0 + 2u, IDESC, 1);
-                                if (2 * j + 1 < nk) {
-                                    tc_mma2_lo<true>(d, a0 + (A_PART >> 4), b0 + (B_PART >> 4), IDESC, 1);
-                                    tc_mma2_lo<true>(d, a0 + (A_PART >> 4) + 2u, b0 + (B_PART >> 4) + 2u, IDESC, 1);
+                                const uint32_t a0 = res_lo + (uint32_t)j * (RES_CHUNK >> 4), b0 = ring_lo + (uint32_t)s * (RES_STAGE >> 4);
+                                tc_mma2_f16_lo_hi(d, a0, b0, kDescHiSw128, IDESC, j != 0);
+                                tc_mma2_f16_lo_hi(d, a0 + 2u, b0 + 2u, kDescHiSw128, IDESC, 1);
+                                if (j * RES_KC + 32 < a.D_pad) {                                   // (D_pad is a multiple of 32)
+                                    tc_mma2_f16_lo_hi(d, a0 + 4u, b0 + 4u, kDescHiSw128, IDESC, 1);
+                                    tc_mma2_f16_lo_hi(d, a0 + 6u, b0 + 6u, kDescHiSw128, IDESC, 1);
                                 }
                                 tc_commit2_mc(&bar_empty[s], 3);
                                 if (j == nstage - 1) {
@@ -349,6 +363,10 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
                     }
                 }
             }
+            if (MDSCTK_TC_PROF_BUILD && a.prof && lane == 0) {
+                long long *pr = a.prof + pair_id * 8;
+                pr[0] = clock64() - p_t0; pr[1] = p_full; pr[2] = p_empty; pr[3] = gp;
+            }
         }
     } else {
         // =============================== epilogue ===================================
@@ -360,16 +378,23 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
         const uint32_t t_warp = tmem_base + ((uint32_t)(quarter * 32) << 16) + sub * SUBW;
         unsigned *hist = s_hist[ew];
         int *wcnt = s_cnt[ew];
+        float *rn = s_rn[ew];
+        float rn0 = 0.f, rn1 = 0.f;
         const size_t row_stride = (size_t)a.cl.H * a.cl.cap;
         float *lkeys = a.cl.key;
         int *lidxs = a.cl.idx;
         size_t lbase0 = 0;
         uint32_t fph = 0;
         long long gp = 0;
+        long long p_wait = 0, p_batch = 0, p_merge = 0;
+        const bool p_on = MDSCTK_TC_PROF_BUILD && a.prof && ew == 0 && rank == 0;
         const uint32_t empty_leader0 = map_to_cta(&bar_tmem_empty[0], 0), empty_leader1 = map_to_cta(&bar_tmem_empty[1], 0);
 
-        auto merge_rows = [&](long long row0, int seg, bool final) {
-            quarter_sync(quarter);
+        // need: this thread's private area cannot take another full pass.  A non-final call costs one barrier (which also
+        // carries the OR of `need` over the quarter) unless some row of the quarter has to be compacted.
+        auto merge_rows = [&](long long row0, int seg, bool final, bool need) {
+            if (final) quarter_sync(quarter);
+            else if (!quarter_any(quarter, need)) return;
             for (int r8 = 0; r8 < 8; ++r8) {
                 const int l = sub * 8 + r8;
                 const int row = quarter * 32 + l;
@@ -433,47 +458,48 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
                 s_tau[row_in_tile] = qvalid ? __ldcg(a.row_tau + qrow) : -1.0f;
             }
             quarter_sync(quarter);
+            {
+                const float *nx = a.r_norm + tile_at(0, rt0, rt1, rot) * TR + sub * SUBW;
+                rn0 = __ldg(nx + lane); rn1 = __ldg(nx + 32 + lane);
+            }
             float *my_keys = lkeys + lbase0 + (size_t)lane * row_stride + a.cl.keep + sub * SUB_APP;
             int *my_idxs = lidxs + lbase0 + (size_t)lane * row_stride + a.cl.keep + sub * SUB_APP;
             for (long long ti = 0; ti < rt1 - rt0; ++ti, ++gp) {
                 const int buf = (int)(gp & 1);
                 const long long rt = tile_at(ti, rt0, rt1, rot);
                 const long long rb = rt * TR + sub * SUBW;
+                const long long t0 = p_on ? clock64() : 0;
+                // this pass's reference norms (prefetched into registers a pass ago) -> the warp's shared-memory row; the
+                // batches below read them as broadcast float4 (a global load per batch sat on the pass's critical path)
+                rn[lane] = rn0; rn[lane + 32] = rn1;
+                if (ti + 1 < rt1 - rt0) {
+                    const float *nx = a.r_norm + tile_at(ti + 1, rt0, rt1, rot) * TR + sub * SUBW;
+                    rn0 = __ldg(nx + lane); rn1 = __ldg(nx + 32 + lane);
+                }
                 if (lane == 0) mbar_wait(&bar_tmem_full[buf], (fph >> buf) & 1u, 4);
                 fph ^= 1u << buf;
                 __syncwarp();
                 tc_fence_after();
+                const long long t1 = p_on ? clock64() : 0;
                 // accumulator units: s^2 * input units^2
                 const float tau_s = s_tau[row_in_tile] / a.inv_scale2;
                 int cnt = wcnt[lane];
-#pragma unroll 1
-                for (int h = 0; h < SUBW; h += EB) {
-                    float dv[EB];
-                    tc_ld16(t_warp + buf * UMMA_N + h, dv);
-                    float nr[EB];
+                // Nearly every batch holds no candidate once the row's threshold is tight: one fused multiply-add and one min
+                // per key decide that, the per-key tests and the append run only for a batch whose smallest key passes.  Rows
+                // beyond n_q carry tau = -1 and never pass; reference columns beyond n_r are sorted out on the slow path.
+                // The next batch's TMEM load is in flight while this one is tested.
+                auto test_batch = [&](const float (&dv)[EB], int h) {
+                    float kmin = __uint_as_float(0x7f800000u);
 #pragma unroll
                     for (int j = 0; j < EB / 4; ++j) {
-                        const float4 g = __ldg(reinterpret_cast<const float4 *>(a.r_norm + rb + h) + j);
-                        nr[4 * j] = g.x; nr[4 * j + 1] = g.y; nr[4 * j + 2] = g.z; nr[4 * j + 3] = g.w;
+                        const float4 g = reinterpret_cast<const float4 *>(rn + h)[j];
+                        kmin = fminf(fminf(kmin, fmaf(-2.0f, dv[4 * j], g.x)), fmaf(-2.0f, dv[4 * j + 1], g.y));
+                        kmin = fminf(fminf(kmin, fmaf(-2.0f, dv[4 * j + 2], g.z)), fmaf(-2.0f, dv[4 * j + 3], g.w));
                     }
-                    tc_wait_ld();
-                    if (h + EB == SUBW) {
-                        tc_fence_before();
-                        __syncwarp();
-                        // (no cluster-scope release fence: the TMEM reads are ordered by tcgen05.wait::ld + fence::before_thread_sync)
-                        if (lane == 0) mbar_arrive_cluster_nofence(buf ? empty_leader1 : empty_leader0);
-                    }
-                    // Nearly every batch holds no candidate once the row's threshold is tight: one fused multiply-add and one min
-                    // per key decide that (the epilogue, not the tensor pipe, paces this kernel: 64 keys per thread and pass),
-                    // the per-key tests and the append run only for a batch whose smallest key passes.  Rows beyond n_q carry
-                    // tau = -1 and never pass; reference columns beyond n_r are sorted out on the slow path.
-                    float kmin = fmaf(-2.0f, dv[0], nr[0]);
-#pragma unroll
-                    for (int j = 1; j < EB; ++j) kmin = fminf(kmin, fmaf(-2.0f, dv[j], nr[j]));
                     if (!(kmin + nq > tau_s * 1.000001f)) {      // (the two evaluation orders differ by an ulp: err on the side of the slow path)
 #pragma unroll
                         for (int j = 0; j < EB; ++j) {
-                            const float key = fmaf(-2.0f, dv[j], nq + nr[j]);
+                            const float key = fmaf(-2.0f, dv[j], nq + rn[h + j]);
                             if (key < tau_s && qvalid && rb + h + j < a.n_r) {
                                 if (cnt < SUB_APP) {
                                     my_keys[cnt] = fmaxf(key, 0.0f) * a.inv_scale2;
@@ -483,11 +509,36 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
                             }
                         }
                     }
-                }
+                };
+                float dva[EB], dvb[EB];
+                const uint32_t t_pass = t_warp + buf * UMMA_N;
+                tc_ld16(t_pass, dva);
+                tc_wait_ld16(dva);
+                tc_ld16(t_pass + EB, dvb);
+                test_batch(dva, 0);
+                tc_wait_ld16(dvb);
+                tc_ld16(t_pass + 2 * EB, dva);
+                test_batch(dvb, EB);
+                tc_wait_ld16(dva);
+                tc_ld16(t_pass + 3 * EB, dvb);
+                test_batch(dva, 2 * EB);
+                tc_wait_ld16(dvb);
+                // the accumulator buffer goes back to the issuer before the last batch is tested
+                // (no cluster-scope release fence: the TMEM reads are ordered by tcgen05.wait::ld + fence::before_thread_sync)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_nofence(buf ? empty_leader1 : empty_leader0);
+                test_batch(dvb, 3 * EB);
                 wcnt[lane] = cnt;
-                merge_rows(row0, seg, false);
+                const long long t2 = p_on ? clock64() : 0;
+                merge_rows(row0, seg, false, cnt > SUB_APP - SUBW);
+                if (p_on) { const long long t3 = clock64(); p_wait += t1 - t0; p_batch += t2 - t1; p_merge += t3 - t2; }
             }
-            merge_rows(row0, seg, true);
+            merge_rows(row0, seg, true, true);
+        }
+        if (p_on && lane == 0) {
+            long long *pr = a.prof + pair_id * 8;
+            pr[4] = p_wait; pr[5] = p_batch; pr[6] = p_merge;
         }
     }
 
@@ -501,16 +552,16 @@ data_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_
 }
 
 // rows[n][D_pad] fp16 as a 2-D tensor (dim, row); box = 32 dims (64 bytes) x `rows` rows
-static bool make_row_map(CUtensorMap *m, const void *base, long long n, int D_pad, int rows)
+static bool make_row_map(CUtensorMap *m, const void *base, long long n, int D_pad, int rows, bool wide = false)
 {
     EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)D_pad, (cuuint64_t)n};
     cuuint64_t strides[1] = {(cuuint64_t)D_pad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)dtc::KC, (cuuint32_t)rows};
+    cuuint32_t box[2] = {(cuuint32_t)(wide ? dtc::RES_KC : dtc::KC), (cuuint32_t)rows};      // wide: 128-byte rows for the resident mode
     cuuint32_t estr[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -551,13 +602,26 @@ cudaError_t launch_data_sweep_tc(const void *fit_hi, const void *fit_lo, const f
     a.q_norm = fit_norm; a.r_norm = ref_norm; a.q_begin = fit_begin_in_ref; a.n_q = n_fit; a.n_r = n_ref;
     a.D_pad = D_pad; a.n_seg = n_seg; a.inv_scale2 = (float)(1.0 / (scale * scale)); a.cl = cl; a.row_tau = row_tau;
     a.one = one_part;
+    a.prof = nullptr;
+#if MDSCTK_TC_PROF_BUILD
+    static long long *d_prof = nullptr;
+    const bool prof = getenv("MDSCTK_TC_PROF") && atoi(getenv("MDSCTK_TC_PROF")) != 0;
+    if (prof) {
+        if (!d_prof && cudaMalloc(&d_prof, 128 * 8 * sizeof(long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
+        cudaMemsetAsync(d_prof, 0, 128 * 8 * sizeof(long long), st);
+        a.prof = d_prof;
+    }
+#endif
     // resident fit tile (one-part filter): when 128 x D_pad fp16 fit rows leave room for >= 3 ring stages of reference rows
     const int nk = D_pad / dtc::KC;
-    int res_nst = (227 * 1024 - dtc::STATIC_SMEM - 1024 - nk * dtc::A_PART) / dtc::RES_STAGE;
+    const int res_chunks = (D_pad + dtc::RES_KC - 1) / dtc::RES_KC;
+    int res_nst = (227 * 1024 - dtc::STATIC_SMEM - 1024 - res_chunks * dtc::RES_CHUNK) / dtc::RES_STAGE;
     if (res_nst > dtc::MAX_NST) res_nst = dtc::MAX_NST;
     a.res = one_part && res_nst >= 3 && !data_tc_force_streaming();
     a.res_nst = res_nst;
-    const int smem_bytes = a.res ? nk * dtc::A_PART + res_nst * dtc::RES_STAGE + 1024 : dtc::SMEM_BYTES;
+    const int smem_bytes = a.res ? res_chunks * dtc::RES_CHUNK + res_nst * dtc::RES_STAGE + 1024 : dtc::SMEM_BYTES;
+    if (a.res && (!make_row_map(&mq_hi, fit_hi, n_fit, D_pad, dtc::TQ, true) || !make_row_map(&mr_hi, ref_hi, n_ref, D_pad, dtc::TRH, true)))
+        return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(data_sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
@@ -580,6 +644,19 @@ cudaError_t launch_data_sweep_tc(const void *fit_hi, const void *fit_lo, const f
     cfg.gridDim = dim3((unsigned)(n_pairs * 2));
     e = cudaLaunchKernelEx(&cfg, data_sweep_tc_kernel, mq_hi, mq_lo, mr_hi, mr_lo, a);
     if (e != cudaSuccess) return e;
+#if MDSCTK_TC_PROF_BUILD
+    if (a.prof) {
+        static long long h[128 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, a.prof, sizeof(h), cudaMemcpyDeviceToHost);
+        double t[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (long long p2 = 0; p2 < n_pairs; ++p2) for (int j = 0; j < 7; ++j) t[j] += (double)h[p2 * 8 + j];
+        if (t[3] > 0)
+            fprintf(stderr, "[data prof] pairs=%lld passes %.0f res=%d nst=%d | issuer clk per pass: total %.0f = wait operands %.0f + wait hand-back %.0f + issue %.0f"
+                            " | epilogue warp 0: wait accumulators %.0f, batches %.0f, merge %.0f\n",
+                    n_pairs, t[3], a.res, a.res_nst, t[0] / t[3], t[1] / t[3], t[2] / t[3], (t[0] - t[1] - t[2]) / t[3], t[4] / t[3], t[5] / t[3], t[6] / t[3]);
+    }
+#endif
     return cudaGetLastError();
 }
 

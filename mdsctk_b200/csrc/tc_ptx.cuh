@@ -85,6 +85,14 @@ __device__ __forceinline__ void quarter_sync(int quarter)
 {
     asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory");
 }
+// quarter_sync that also returns the OR of `pred` over the quarter's 128 threads (one barrier, no shared-memory flag)
+__device__ __forceinline__ bool quarter_any(int quarter, bool pred)
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"((uint32_t)pred), "r"(quarter + 1) : "memory");
+    return r != 0;
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
 {
     asm volatile(
@@ -110,6 +118,10 @@ __device__ __forceinline__ void tma_load_3d_2sm(void *dst, const CUtensorMap *ma
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
 {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1,
                                                 uint64_t policy)
@@ -208,6 +220,20 @@ __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_
 // 32-bit add per operand instead of rebuilding the 64-bit descriptor.  ACC: accumulate flag known at compile time.
 constexpr uint32_t kDescHiSw64 = (uint32_t)((512u >> 4) | (1u << 14) | (4u << 29));   // SBO=512 B, version 1, SWIZZLE_64B
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+// ... and of every SWIZZLE_128B K-major one (128-byte rows, 8-row groups 1024 B apart; a 16-element fp16 k-step = +32 B)
+constexpr uint32_t kDescHiSw128 = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));   // SBO=1024 B, version 1, SWIZZLE_128B
+// fp16 CTA-pair MMA from descriptor low words with the shared high word given
+__device__ __forceinline__ void tc_mma2_f16_lo_hi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(hi)
+        : "memory");
+}
 template <bool BF16>
 __device__ __forceinline__ void tc_mma2_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc)
 {
@@ -370,6 +396,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tc_wait_ld that names the sixteen registers as read-write operands: in a software-pipelined epilogue (the next batch's
+// tcgen05.ld issued before this batch's arithmetic) nothing else stops the compiler from scheduling a use above the wait
+__device__ __forceinline__ void tc_wait_ld16(float (&v)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :: "memory");
+}
 
 // K-major, SWIZZLE_64B shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x 64 B = 512 B)

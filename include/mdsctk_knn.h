@@ -114,8 +114,8 @@ const char *mdsctk_knn_last_error(const mdsctk_knn_ctx *ctx);
  * compared, default 8; a mismatch makes the query return MDSCTK_KNN_EAUDIT; 0 = off),
  * "sweep_version" (1xFP16 sweep: 2 = resident fit tile + pass director where the tile fits, the default; 1 = the
  * streaming kernel of round 1),
- * "ref_tiled" (0/1, default 0: keep a second copy of the reference fp16 planes in the sweep's ring-stage order, every
- * 4.6 KB stage one contiguous block; measured neutral, kept as an experiment),
+ * "rms_wide_stages" (0/1, default 1: the version-2 sweep moves the reference operand in 64-atom stages of 128-byte rows
+ * where three of them fit beside the resident fit tile; 0 = 32-atom stages; same output either way),
  * "force_exact" (0/1: every row goes through the exact FP64 path -- the certificate decides nothing; test hook),
  * "debug_tile" (0/1, see mdsctk_knn_debug_fetch_tile). */
 int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value);

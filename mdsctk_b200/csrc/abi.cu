@@ -146,8 +146,7 @@ struct mdsctk_knn_ctx {
     bool force_exact = false;        // every row through the exact FP64 path (test hook)
     // ring-stage-ordered copy of the reference fp16 planes (rms_tc2.cu).  Off by default: measured neutral (C3 63.3 vs 63.6 ms,
     // C4 block 866 vs 873 ms) -- the ring's copy latency does not come from the 72 strided rows of a stage -- and it costs 1.9 GB
-    bool ref_tiled_on = false, ref_tiled_dirty = true;
-    DevBuf ref_tiled;
+    bool rms_wide_stages = true;
     int data_segments = 0;           // same for the knn_data tensor filter
     int rms_segments = 0;            // reference segments per fit super-tile (0 = chosen by rms_tc_choose_segments)
     int sweep_version = 2;           // 1xFP16 sweep: 2 = rms_tc2.cu where the fit tile fits (default), 1 = rms_tc.cu
@@ -356,7 +355,7 @@ int rms_run_block(mdsctk_knn_ctx *ctx, FrameSet &fitset, const RmsPlan &P, long 
                 CK(launch_rms_sweep_tc2(fit, fit_begin, n_fit, ref, do_fit, P.n_seg, cl, ctx->row_tau.as<float>(), ctx->g_ref_max,
                                         P.oos ? ctx->own_tile.as<int>() : nullptr,
                                         ctx->debug_tile_on ? ctx->debug_tile.as<float>() : nullptr,
-                                        ctx->ref_tiled_on ? ctx->ref_tiled.p : nullptr, ctx->n_sms, ctx->st),
+                                        ctx->rms_wide_stages ? 1 : 0, ctx->n_sms, ctx->st),
                    "rms_sweep_tc2");
                 S.sweep_version = 2;
             } else {
@@ -505,17 +504,7 @@ int rms_run(mdsctk_knn_ctx *ctx, FrameSet &fitset, long long fit_begin, long lon
         }
         CK(cudaStreamSynchronize(ctx->st), "sync max(gres)");
         ctx->gmax_dirty = false;
-        ctx->ref_tiled_dirty = true;
     }
-    if (P.rms_kernel == MDSCTK_KNN_RMS_TC_1XFP16 && ctx->sweep_version != 1 && ctx->ref_tiled_on && rms_tc2_supported(ref.A_pad) &&
-        (ctx->ref_tiled_dirty || !ctx->ref_tiled.p)) {
-        ctx->tm.start(ctx->st);
-        CK(ctx->ref_tiled.reserve(rms_tc2_tiled_bytes(ref.n, ref.A_pad)), "cudaMalloc(ref_tiled)");
-        CK(launch_rms_tc2_tile_reference(ref.fh, ref.n, ref.A_pad, ctx->ref_tiled.p, ctx->st), "tile_reference");
-        ctx->stats.ms_pack += ctx->tm.stop(ctx->st);
-        ctx->ref_tiled_dirty = false;
-    }
-
     P.use_tc = P.rms_kernel != MDSCTK_KNN_RMS_SIMT_FP32;
     // Row blocks: at most chunk_rows rows, balanced, and -- for the persistent tensor-core sweep, whose work items are 256-row
     // super-tiles taken by the SM pairs in waves -- a whole number of waves each, so that only the last block of a query has a
@@ -923,7 +912,7 @@ void mdsctk_knn_destroy(mdsctk_knn_ctx *ctx)
                        &ctx->dt_ref_norm1, &ctx->dt_ref_g, &ctx->dt_fit_norm1, &ctx->dt_fit_g, &ctx->fb_rows, &ctx->fb_key,
                        &ctx->fb_idx, &ctx->fb_cnt, &ctx->fb_tau, &ctx->fb_dist, &ctx->fb_oidx, &ctx->fb_stats, &ctx->c_idx, &ctx->c_dist,
                        &ctx->c_ints, &ctx->c_key, &ctx->c_val, &ctx->c_irow, &ctx->c_oval, &ctx->f_in, &ctx->f_ang, &ctx->f_sc,
-                       &ctx->ref_tiled, &ctx->audit_ids, &ctx->audit_seq, &ctx->audit_dist, &ctx->audit_idx, &ctx->s_int, &ctx->s_val, &ctx->s_vec, &ctx->s_basis, &ctx->s_rot, &ctx->s_small, &ctx->s_evec})
+                       &ctx->audit_ids, &ctx->audit_seq, &ctx->audit_dist, &ctx->audit_idx, &ctx->s_int, &ctx->s_val, &ctx->s_vec, &ctx->s_basis, &ctx->s_rot, &ctx->s_small, &ctx->s_evec})
         b2->release();
     ctx->tm.destroy();
     ctx->user_tm.destroy();
@@ -967,8 +956,8 @@ int mdsctk_knn_set_option(mdsctk_knn_ctx *ctx, const char *key, long long value)
     } else if (!strcmp(key, "data_segments")) {
         if (value < 0 || value > 8) return fail(ctx, MDSCTK_KNN_EINVAL, "data_segments must be 0 (auto) .. 8");
         ctx->data_segments = (int)value;
-    } else if (!strcmp(key, "ref_tiled")) {
-        ctx->ref_tiled_on = value != 0;
+    } else if (!strcmp(key, "rms_wide_stages")) {
+        ctx->rms_wide_stages = value != 0;
     } else if (!strcmp(key, "force_exact")) {
         ctx->force_exact = value != 0;
     } else if (!strcmp(key, "debug_tile")) {

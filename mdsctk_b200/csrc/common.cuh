@@ -84,10 +84,8 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
 bool rms_tc2_supported(int A_pad);
 cudaError_t launch_rms_sweep_tc2(const FrameSetView &fit, long long fit_begin, long long n_fit, const FrameSetView &ref, int do_fit,
                                  int n_seg, CandLists<float> cl, float *row_tau, float g_ref_max, int *own_tile_scratch,
-                                 float *debug_tile, const void *ref_tiled, int n_sms, cudaStream_t st);
+                                 float *debug_tile, int wide_stages, int n_sms, cudaStream_t st);
 // reference fp16 planes re-ordered so that every ring stage of the sweep is one contiguous block (optional; NULL = frame-major planes)
-size_t rms_tc2_tiled_bytes(long long n_ref, int A_pad);
-cudaError_t launch_rms_tc2_tile_reference(const void *fh, long long n_ref, int A_pad, void *tiled, cudaStream_t st);
 cudaError_t launch_rms_guess_own_tile(const float4 *q_sig, long long q_begin, long long n_q, const float4 *r_sig, long long n_r,
                                       int *own_tile, cudaStream_t st);
 int rms_tc_choose_segments(long long n_fit, long long n_ref, int n_sms);

@@ -57,7 +57,8 @@ constexpr int A_CHUNK = TQ * 64;              // 8192 B: 32 atoms (two k-steps) 
 constexpr int B_STAGE = 3 * TRH * 64;         // 4608 B: 32 atoms of this CTA's 72 reference operand rows
 constexpr int SUBS = 4;                       // epilogue warps per TMEM lane quarter
 constexpr int EPI_WARPS = 4 * SUBS;           // 16
-constexpr int NTHR = 64 + EPI_WARPS * 32;     // 576
+constexpr int SCOUT_WARP = 2 + EPI_WARPS;       // warp 18: the pass scout (leader CTA)
+constexpr int NTHR = 64 + EPI_WARPS * 32 + 32; // 608
 constexpr int SUBW = TR / SUBS;               // 12 reference columns per epilogue warp
 constexpr int EB = 2;                         // pairs per lane and epilogue batch
 constexpr int MERGE_EVERY = 4;                // heavy passes between quarter-wide list merges
@@ -68,8 +69,12 @@ constexpr int MAX_TMEM_UNITS = (TMEM_COLS - ACC_COLS) / 8;   // 10 k-steps of on
 constexpr int MAX_NST = 8;
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr uint32_t END_PASS = 0xFFFFFu;
-constexpr int PREFETCH_AHEAD = 3;             // passes between a reference tile's L2 prefetch and its copies into the ring
-constexpr int QCAP = 32;                      // refine-queue entries per epilogue warp (shared memory is the ring's: 320 B per warp)
+#ifndef MDSCTK_TC2_QCAP
+#define MDSCTK_TC2_QCAP 32
+#endif
+constexpr int QCAP = MDSCTK_TC2_QCAP;         // refine-queue entries per epilogue warp (20 B per entry and warp of the ring's shared memory);
+constexpr int QCAP_SMALL = 20;                // ... and the size that buys a third wide ring stage at 300 atoms (>= 13: the histogram)
+constexpr int B_STAGE_WIDE = 2 * B_STAGE;     // 9216 B: 64 atoms (128-byte rows, SWIZZLE_128B) per stage
 constexpr float SC = kRmsHalfScale * kRmsHalfScale, INV_SC = 1.0f / SC;   // accumulators hold SC * S
 constexpr uint32_t IDESC = umma_idesc(0, UMMA_M, UMMA_N);                  // fp16 x fp16 -> fp32
 
@@ -84,11 +89,12 @@ struct Ctl {
 #if MDSCTK_TC_PROF_BUILD
     long long t_commit[MAX_NST], t_issue[MAX_NST];   // clock counters of the ring's round trip (leader CTA)
 #endif
-    float mtile[4];                   // scout -> director: per reference tile (mod 4), the smallest threshold that makes it heavy
+    unsigned long long mtile[4];      // scout -> director, per pass (mod 4): pass number + 1 | (smallest threshold that makes the tile heavy) << 32
+    uint32_t pass_now;                // director -> scout: the pass being issued (the scout stays at most 3 ahead)
     float tau[TQ];                    // running admission threshold per fit row of this CTA
     unsigned short mcnt[TQ];          // merged entries per row
     unsigned cnt8[EPI_WARPS][8];      // fill of each warp's private append area, one BYTE per row of its quarter
-    unsigned scratch[EPI_WARPS][5 * QCAP]; // per warp: refine queue (5 x QCAP words) / 64-bin radix histogram during merges
+    unsigned scratch[4];              // really [EPI_WARPS][5 * qcap]: per warp, refine queue (5 x qcap words) / 64-bin radix histogram during merges
 };
 }  // namespace tc2
 
@@ -107,8 +113,9 @@ struct Tc2Args {
     int chunks[3], chunk_base[3]; // plane p: `chunks` 64-byte chunks resident in shared memory from slot chunk_base
     int tmem_unit0[3];            // plane p: its k-steps [2 chunks[p], nks) live in TMEM units tmem_unit0[p]..
     int n_tmem_units, n_res_chunks, nst;
+    int qcap;                     // refine-queue entries per epilogue warp
+    int wide, bst;                // 128-byte reference rows: 64 atoms (four k-steps) per ring stage; bytes per stage
     int dbg;
-    int tiled;                    // the reference operand is in ring-stage order (tile_reference_kernel): coordinates (0, 0, stage)
     uint32_t idesc;               // instruction descriptor (M=256, N=144, fp16 -> fp32; other N only in timing experiments)
     long long *prof;
 };
@@ -130,15 +137,13 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     using namespace tc2;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem + (size_t)a.n_res_chunks * A_CHUNK;
-    Ctl &c = *reinterpret_cast<Ctl *>(ring + (size_t)a.nst * B_STAGE);
+    const int bst = a.bst;
+    Ctl &c = *reinterpret_cast<Ctl *>(ring + (size_t)a.nst * bst);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
     const int nkc = a.nkc, nst = a.nst;
-    // ring stages per producer / issuer round.  One: a slot is refilled the moment its six MMAs retire and consumed the moment it
-    // lands (measured: waits for reference stages 3.7k -> 1.8k clk per pass, pass 9.09k -> 8.75k on C4; bit 128 of the experiment
-    // build restores pairs, which halve the number of rounds but make each slot wait for its neighbour twice)
-    const int grp = (a.dbg & 128) ? 2 : 1;
+    const int katoms = a.wide ? 64 : 32;          // atoms per ring stage
     const long long n_qt = (a.n_q + UMMA_M - 1) / UMMA_M;
     const long long n_rt = (a.n_r + TR - 1) / TR;
     const long long n_items = n_qt * a.n_seg;
@@ -153,6 +158,8 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mbar_init(&c.bar_res_empty, 1);
         mbar_init(&c.bar_item_ready, 2 * EPI_WARPS);
         c.mailbox = 0;
+        c.pass_now = 0;
+        for (int i = 0; i < 4; ++i) c.mtile[i] = 0ull;
 #if MDSCTK_TC_PROF_BUILD
         for (int i = 0; i < MAX_NST; ++i) { c.t_commit[i] = 0; c.t_issue[i] = 0; }
 #endif
@@ -188,38 +195,77 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         return t < rt1 ? t : t - (rt1 - rt0);
     };
 
+    const bool use_pre = a.pre_rel >= 0.0f && a.do_fit && !a.debug_tile && !(a.dbg & 1024);
     if (warp == 0) {
-        // =============================== TMA producer (both CTAs) + pass scout ====================
-        // Besides feeding the ring, the producer does the director's arithmetic ahead of it: for every reference tile,
-        //     m = min over its 48 frames of  lb^2 - 2e-5 (Gq_max + G_r)      (-inf where lb <= 0)
-        // with lb the von Neumann lower bound of the frame against the box of the super-tile's singular values.  A pass
-        // can hold a neighbour of one of the 256 rows only if m <= the largest admission threshold among them, which is
-        // all the MMA warp has to test per pass (one shared-memory word written here before the tile's first copy is
-        // issued, so it is visible by the time that copy's "full" barrier completes).
-        int s = 0;
-        uint32_t ph = 0, rph = 0;
-        bool first_item = true;
-        long long p_wake = 0, p_n = 0;
-        const uint32_t res_leader = map_to_cta(&c.bar_res_full, 0), full_leader0 = map_to_cta(&c.bar_full[0], 0);
-        const float kNegInf = __uint_as_float(0xff800000u), kPosInf = __uint_as_float(0x7f800000u);
-        const bool use_pre = a.pre_rel >= 0.0f && a.do_fit && !a.debug_tile && !(a.dbg & 1024);
-        for (long long it = pair_id; it < n_items; it += n_pairs) {
-            long long qt, rt0, rt1, rot; int seg;
-            item_range(it, qt, rt0, rt1, seg, rot);
-            const int q0 = (int)(a.q_begin + qt * UMMA_M + rank * TQ);
-            // the fit tile of this item, once: the previous item's MMAs must have retired
-            if (!first_item) { mbar_wait(&c.bar_res_empty, rph, 5); rph ^= 1; }
-            first_item = false;
-            if (elect_one()) {
+        // =============================== TMA producer (both CTAs): ONE thread ====================
+        // The ring's copies are issued by a single thread, as the MMAs are: a round of the loop is a barrier test, an
+        // expect-tx and one bulk-tensor copy, and with the whole warp in it (32 lanes polling the barrier, an election and a
+        // warp barrier per round) a round cost ~700 clk -- the producer, not the tensor pipe, paced the light passes
+        // (measured: the pass took as long with the MMAs skipped).  The scout's arithmetic lives in a warp of its own.
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0, rph = 0;
+            bool first_item = true;
+            long long p_wake = 0, p_n = 0, p_wait = 0, p_issue = 0, p_rounds = 0, p_total0 = MDSCTK_TC_PROF_BUILD ? clock64() : 0;
+            const bool p_on = MDSCTK_TC_PROF_BUILD && a.prof && rank == 0;
+            const uint32_t res_leader = map_to_cta(&c.bar_res_full, 0), full_leader0 = map_to_cta(&c.bar_full[0], 0);
+            for (long long it = pair_id; it < n_items; it += n_pairs) {
+                long long qt, rt0, rt1, rot; int seg;
+                item_range(it, qt, rt0, rt1, seg, rot);
+                const int q0 = (int)(a.q_begin + qt * UMMA_M + rank * TQ);
+                // the fit tile of this item, once: the previous item's MMAs must have retired
+                if (!first_item) { mbar_wait(&c.bar_res_empty, rph, 5); rph ^= 1; }
+                first_item = false;
                 if (rank == 0) mbar_expect_tx(&c.bar_res_full, 2u * (uint32_t)(a.n_res_chunks * A_CHUNK));
                 for (int p = 0; p < 3; ++p)
                     for (int ch = 0; ch < a.chunks[p]; ++ch)
                         tma_load_3d_2sm(smem + (size_t)(a.chunk_base[p] + ch) * A_CHUNK, &map_q, res_leader, ch * 32, q0, p, kEvictNormal);
+                const long long n_tiles = rt1 - rt0;
+                for (long long ti = 0; ti < n_tiles; ++ti) {
+                    const int r0 = (int)(tile_at(ti, rt0, rt1, rot) * TR + rank * TRH);
+                    for (int kc = 0; kc < nkc; ++kc) {
+                        const long long pw0 = p_on ? clock64() : 0;
+                        mbar_wait(&c.bar_empty[s], ph ^ 1, 1);       // suspending wait: the hardware sleeps the thread until the barrier flips
+                        const long long pw1 = p_on ? clock64() : 0;
+#if MDSCTK_TC_PROF_BUILD
+                        if (p_on) {
+                            const long long tc0 = *reinterpret_cast<volatile long long *>(&c.t_commit[s]);
+                            if (tc0 > 0 && pw1 > tc0 && pw1 - tc0 < 1000000) { p_wake += pw1 - tc0; ++p_n; }
+                            *reinterpret_cast<volatile long long *>(&c.t_issue[s]) = pw1;
+                        }
+#endif
+                        if (rank == 0) mbar_expect_tx(&c.bar_full[s], 2u * (uint32_t)bst);
+                        tma_load_3d_2sm(ring + (size_t)s * bst, &map_r, full_leader0 + 8u * (uint32_t)s, kc * katoms, r0, 0, kEvictNormal);
+                        if (p_on) { p_wait += pw1 - pw0; p_issue += clock64() - pw1; ++p_rounds; }
+                        if (++s == nst) { s = 0; ph ^= 1; }
+                    }
+                }
             }
-            __syncwarp();
-            // box of the super-tile's singular values and its largest rounded norm
-            float bx0 = 3.0e38f, bx1 = 0.f, by0 = 3.0e38f, by1 = 0.f, bz0 = 3.0e38f, bz1 = 0.f, gq_max = 0.f;
-            if (use_pre && rank == 0) {
+#if MDSCTK_TC_PROF_BUILD
+            if (p_on) {
+                a.prof[(size_t)blockIdx.x * 8 + 5] = p_wake; a.prof[(size_t)blockIdx.x * 8 + 6] = p_n;
+                long long *pr = a.prof + (size_t)(blockIdx.x + 1) * 8;      // the peer CTA's row is unused: producer counters
+                pr[0] = clock64() - p_total0; pr[1] = 0; pr[2] = p_wait; pr[3] = p_issue; pr[4] = p_rounds;
+            }
+#endif
+        }
+        __syncwarp();
+    } else if (warp == SCOUT_WARP) {
+        // =============================== pass scout (leader CTA) ==================================
+        // The director's arithmetic, done ahead of it: for every reference tile,
+        //     m = min over its 48 frames of  lb^2 - 2e-5 (Gq_max + G_r)      (-inf where lb <= 0)
+        // with lb the von Neumann lower bound of the frame against the box of the super-tile's singular values.  A pass
+        // can hold a neighbour of one of the 256 rows only if m <= the largest admission threshold among them, which is
+        // all the MMA warp has to test per pass.  One 8-byte word per pass, tagged with the pass number; the scout stays at
+        // most three passes ahead of the director (four slots).
+        if (rank == 0 && use_pre) {
+            const float kNegInf = __uint_as_float(0xff800000u), kPosInf = __uint_as_float(0x7f800000u);
+            uint32_t g = 0;                               // pass number, as the director counts them
+            for (long long it = pair_id; it < n_items; it += n_pairs) {
+                long long qt, rt0, rt1, rot; int seg;
+                item_range(it, qt, rt0, rt1, seg, rot);
+                // box of the super-tile's singular values and its largest rounded norm
+                float bx0 = 3.0e38f, bx1 = 0.f, by0 = 3.0e38f, by1 = 0.f, bz0 = 3.0e38f, bz1 = 0.f, gq_max = 0.f;
                 for (int j = 0; j < UMMA_M / 32; ++j) {
                     const long long row = min(qt * UMMA_M + lane + 32 * j, a.n_q - 1);
                     const float4 sq = __ldg(a.q_sig + a.q_begin + row);
@@ -229,85 +275,45 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 }
                 bx0 = wminf(bx0); bx1 = wmaxf(bx1); by0 = wminf(by0); by1 = wmaxf(by1); bz0 = wminf(bz0); bz1 = wmaxf(bz1);
                 gq_max = wmaxf(gq_max);
-            }
-            const float pre_g = a.pre_rel * (sqrtf(gq_max) + a.pre_sqrt_gmax) + 1e-6f;
-            // reference scalars one tile ahead: lane l holds frames l and 32 + l (< 48) of the tile
-            float4 nsA = make_float4(0.f, 0.f, 0.f, 0.f), nsB = nsA;
-            float ngA = 0.f, ngB = 0.f;
-            auto fetch_refs = [&](long long ti2) {
-                const long long rb = tile_at(ti2, rt0, rt1, rot) * TR;
-                nsA = __ldg(a.r_sig + rb + lane); ngA = __ldg(a.r_G + rb + lane);
-                if (lane < TR - 32) { nsB = __ldg(a.r_sig + rb + 32 + lane); ngB = __ldg(a.r_G + rb + 32 + lane); }
-            };
-            const long long n_tiles = rt1 - rt0;
-            if (use_pre && rank == 0) fetch_refs(0);
-            for (long long ti = 0; ti < n_tiles; ++ti) {
-                const int r0 = (int)(tile_at(ti, rt0, rt1, rot) * TR + rank * TRH);
-                // (bit 256, experiment: warm L2 with this CTA's half of the tile PREFETCH_AHEAD passes on -- measured: no gain,
-                // the ring's copies already hit L2)
-                if (ti + PREFETCH_AHEAD < n_tiles && lane < nkc && (a.dbg & 256))
-                    tma_prefetch_3d(&map_r, lane * 32, (int)(tile_at(ti + PREFETCH_AHEAD, rt0, rt1, rot) * TR + rank * TRH), 0);
-                if (rank == 0) {
-                    float m = kNegInf;
-                    if (use_pre) {
-                        const float4 sA = nsA, sB = nsB;
-                        const float gA = ngA, gB = ngB;
-                        if (ti + 1 < n_tiles) fetch_refs(ti + 1);
-                        auto score = [&](const float4 &sg, float g) {
-                            const float d0 = fmaxf(fmaxf(bx0 - sg.x, sg.x - bx1), 0.0f), d1 = fmaxf(fmaxf(by0 - sg.y, sg.y - by1), 0.0f),
-                                        d2 = fmaxf(fmaxf(bz0 - sg.z, sg.z - bz1), 0.0f);
-                            const float lb = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2))) - pre_g;
-                            // key = rounded-structure RMSD^2 + accumulation bias/noise (< 2e-5 E0): keep clear of it
-                            const float v = fmaf(lb, lb, -2e-5f * (gq_max + g));
-                            return (lb > 0.0f && v == v) ? v : kNegInf;
-                        };
-                        m = fminf(score(sA, gA), lane < TR - 32 ? score(sB, gB) : kPosInf);
+                const float pre_g = a.pre_rel * (sqrtf(gq_max) + a.pre_sqrt_gmax) + 1e-6f;
+                // reference scalars one tile ahead: lane l holds frames l and 32 + l (< 48) of the tile
+                float4 nsA = make_float4(0.f, 0.f, 0.f, 0.f), nsB = nsA;
+                float ngA = 0.f, ngB = 0.f;
+                auto fetch_refs = [&](long long ti2) {
+                    const long long rb = tile_at(ti2, rt0, rt1, rot) * TR;
+                    nsA = __ldg(a.r_sig + rb + lane); ngA = __ldg(a.r_G + rb + lane);
+                    if (lane < TR - 32) { nsB = __ldg(a.r_sig + rb + 32 + lane); ngB = __ldg(a.r_G + rb + 32 + lane); }
+                };
+                const long long n_tiles = rt1 - rt0;
+                fetch_refs(0);
+                for (long long ti = 0; ti < n_tiles; ++ti, ++g) {
+                    const float4 sA = nsA, sB = nsB;
+                    const float gA = ngA, gB = ngB;
+                    if (ti + 1 < n_tiles) fetch_refs(ti + 1);
+                    auto score = [&](const float4 &sg, float gr) {
+                        const float d0 = fmaxf(fmaxf(bx0 - sg.x, sg.x - bx1), 0.0f), d1 = fmaxf(fmaxf(by0 - sg.y, sg.y - by1), 0.0f),
+                                    d2 = fmaxf(fmaxf(bz0 - sg.z, sg.z - bz1), 0.0f);
+                        const float lb = sqrtf(fmaf(d0, d0, fmaf(d1, d1, d2 * d2))) - pre_g;
+                        // key = rounded-structure RMSD^2 + accumulation bias/noise (< 2e-5 E0): keep clear of it
+                        const float v = fmaf(lb, lb, -2e-5f * (gq_max + gr));
+                        return (lb > 0.0f && v == v) ? v : kNegInf;
+                    };
+                    float m = fminf(score(sA, gA), lane < TR - 32 ? score(sB, gB) : kPosInf);
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    }
-                    if (lane == 0) *reinterpret_cast<volatile float *>(&c.mtile[ti & 3]) = m;
-                    __syncwarp();
-                }
-                // two chunks per round: one wait / elect round per 9 KB instead of per 4.6 KB (the producer is a single
-                // warp too, and its per-chunk overhead is part of the ring's round-trip time)
-                for (int kc = 0; kc < nkc; kc += grp) {
-                    const int ng = min(grp, nkc - kc);
-                    int s1 = s + 1; uint32_t ph1 = ph;
-                    if (s1 == nst) { s1 = 0; ph1 ^= 1; }
-                    if (!(a.dbg & 4096)) {               // suspending waits (hardware sleeps the warp until the barrier flips)
-                        mbar_wait(&c.bar_empty[s], ph ^ 1, 1);
-                        if (ng > 1) mbar_wait(&c.bar_empty[s1], ph1 ^ 1, 1);
-                    } else {
-                        mbar_wait_spin(&c.bar_empty[s], ph ^ 1, 1);
-                        if (ng > 1) mbar_wait_spin(&c.bar_empty[s1], ph1 ^ 1, 1);
-                    }
-#if MDSCTK_TC_PROF_BUILD
-                    if (a.prof && rank == 0 && lane == 0) {
-                        const long long tc0 = *reinterpret_cast<volatile long long *>(&c.t_commit[s]);
-                        const long long now = clock64();
-                        if (tc0 > 0 && now > tc0 && now - tc0 < 1000000) { p_wake += now - tc0; ++p_n; }
-                        *reinterpret_cast<volatile long long *>(&c.t_issue[s]) = now;
-                    }
-#endif
-                    if (elect_one()) {
-                        if (rank == 0) mbar_expect_tx(&c.bar_full[s], 2u * B_STAGE);
-                        if (a.tiled) tma_load_3d_2sm(ring + (size_t)s * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s, 0, 0, (r0 / TRH) * nkc + kc, kEvictNormal);
-                        else tma_load_3d_2sm(ring + (size_t)s * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s, kc * 32, r0, 0, kEvictNormal);
-                        if (ng > 1) {
-                            if (rank == 0) mbar_expect_tx(&c.bar_full[s1], 2u * B_STAGE);
-                            if (a.tiled) tma_load_3d_2sm(ring + (size_t)s1 * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s1, 0, 0, (r0 / TRH) * nkc + kc + 1, kEvictNormal);
-                            else tma_load_3d_2sm(ring + (size_t)s1 * B_STAGE, &map_r, full_leader0 + 8u * (uint32_t)s1, (kc + 1) * 32, r0, 0, kEvictNormal);
+                    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    // slot g & 3 held pass g - 4: the director is done with it once it has begun pass g - 3
+                    if (lane == 0) {
+                        uint32_t polls = 0;
+                        while ((int32_t)(g - ld_volatile_u32(&c.pass_now)) > 3) {
+                            __nanosleep(100);
+                            if (++polls > 100000000u) { printf("rms_sweep_tc2: scout timeout block=%d pass=%u\n", blockIdx.x, g); __trap(); }
                         }
+                        *reinterpret_cast<volatile unsigned long long *>(&c.mtile[g & 3]) = (unsigned long long)(g + 1u) | ((unsigned long long)__float_as_uint(m) << 32);
                     }
                     __syncwarp();
-                    s += ng;
-                    if (s >= nst) { s -= nst; ph ^= 1; }
                 }
             }
         }
-#if MDSCTK_TC_PROF_BUILD
-        if (a.prof && rank == 0 && lane == 0) { a.prof[(size_t)blockIdx.x * 8 + 5] = p_wake; a.prof[(size_t)blockIdx.x * 8 + 6] = p_n; }
-#endif
     } else if (warp == 1) {
         // =============================== MMA issuer + pass director (leader CTA) ================
         // One warp is the whole control path of the tensor pipe, and a single warp retires an instruction every few
@@ -316,9 +322,11 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // loop is kept to the bone: the director is one comparison (the scout above did the arithmetic), the readiness
         // test of the NEXT group's stages is issued before the MMAs of the current one, descriptors advance by constant
         // offsets, and nothing but the MMAs and their commits sits between two groups.
+        // (The MMAs are issued by an elected lane of the CONVERGED warp: with the loop run by one thread inside a divergent
+        // branch every tcgen05.mma blocks its thread for the ~72 clk it executes and a commit for ~220 -- measured, C3 62 -> 90 ms.)
         if (rank == 0) {
             int s = 0;
-            uint32_t ph = 0, tph = 0, rfph = 0, iph = 0, seq = 0;
+            uint32_t ph = 0, tph = 0, rfph = 0, iph = 0, seq = 0, gpass = 0;
             bool rdy = false;
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t res_lo = umma_desc_lo(__shfl_sync(0xffffffffu, smem_u32(smem), 0));
@@ -336,17 +344,9 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const bool uniform_split = lim0 == lim1 && lim1 == lim2 && !(a.dbg & 8192);
             const int nks = (a.dbg & 2) ? 0 : a.nks;
             const uint32_t idesc = a.idesc;
+            const uint32_t bhi = a.wide ? kDescHiSw128 : kDescHiSw64;
             const bool no_director = (a.dbg & 64) != 0;
             long long t_total0 = MDSCTK_TC_PROF_BUILD ? clock64() : 0, t_wait_full = 0, t_wait_empty = 0, n_pass = 0, n_heavy = 0, t_tma = 0, n_tma = 0;
-            auto test_group = [&](int s0, uint32_t p0, int ng) {      // non-blocking: are the ng stages from s0 full?
-                bool ok = mbar_test_wait(&c.bar_full[s0], p0);
-                if (ng > 1) {
-                    int s1 = s0 + 1; uint32_t p1 = p0;
-                    if (s1 == nst) { s1 = 0; p1 ^= 1; }
-                    ok = mbar_test_wait(&c.bar_full[s1], p1) && ok;
-                }
-                return ok;
-            };
             for (long long it = pair_id; it < n_items; it += n_pairs) {
                 long long qt, rt0, rt1, rot; int seg;
                 item_range(it, qt, rt0, rt1, seg, rot);
@@ -361,17 +361,22 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     // the first stage of the pass must have landed before the scout's word for this tile is read
                     if (!rdy) {
                         const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
-                        int s2 = s; uint32_t ph2 = ph;
-                        for (int u = 0; u < min(grp, nkc); ++u) {
-                            mbar_wait_spin(&c.bar_full[s2], ph2, 3);
-                            if (++s2 == nst) { s2 = 0; ph2 ^= 1; }
-                        }
+                        mbar_wait_spin(&c.bar_full[s], ph, 3);
                         if (MDSCTK_TC_PROF_BUILD && a.prof) t_wait_full += clock64() - t0;
                         rdy = true;
                     }
                     // ---- director: can any of the 48 frames hold a neighbour of any of the 256 rows? ----
                     const float tq = lane < 8 ? *reinterpret_cast<volatile float *>(&c.qtau[lane]) : 0.0f;   // only decreases: stale is safe
-                    const float m = *reinterpret_cast<volatile float *>(&c.mtile[ti & 3]);
+                    if (lane == 0) *reinterpret_cast<volatile uint32_t *>(&c.pass_now) = gpass;
+                    float m = __uint_as_float(0xff800000u);          // no scout: every pass is live
+                    if (use_pre) {
+                        unsigned long long w;
+                        uint32_t polls = 0;
+                        while ((uint32_t)(w = *reinterpret_cast<volatile unsigned long long *>(&c.mtile[gpass & 3])) != gpass + 1u)
+                            if (++polls > 200000000u) { printf("rms_sweep_tc2: director timeout block=%d pass=%u\n", blockIdx.x, gpass); __trap(); }
+                        m = __uint_as_float((uint32_t)(w >> 32));
+                    }
+                    ++gpass;
                     const bool heavy = !no_director && m <= wmaxf(tq);
                     // ---- the previous heavy pass must have been handed back before anything touches TMEM or the mailbox ----
                     if (pending_release) {
@@ -390,35 +395,26 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                         ++n_heavy;
                     }
                     ++n_pass;
-                    // ---- MMAs of the pass, two stages (four k-steps) per group ----
-                    for (int kc0 = 0; kc0 < nkc; kc0 += grp) {
-                        const int ng = min(grp, nkc - kc0);
+                    // ---- MMAs of the pass, one ring stage (two k-steps, or four with 128-byte rows) per round ----
+                    for (int kc0 = 0; kc0 < nkc; ++kc0) {
                         if (!rdy) {
                             const long long t0 = (MDSCTK_TC_PROF_BUILD && a.prof) ? clock64() : 0;
-                            int s2 = s; uint32_t ph2 = ph;
-                            for (int u = 0; u < ng; ++u) {
-                                mbar_wait_spin(&c.bar_full[s2], ph2, 3);
+                            mbar_wait_spin(&c.bar_full[s], ph, 3);
 #if MDSCTK_TC_PROF_BUILD
-                                if (a.prof && u == 0) { t_tma += clock64() - *reinterpret_cast<volatile long long *>(&c.t_issue[s2]); ++n_tma; }
+                            if (a.prof) { t_tma += clock64() - *reinterpret_cast<volatile long long *>(&c.t_issue[s]); ++n_tma; t_wait_full += clock64() - t0; }
 #endif
-                                if (++s2 == nst) { s2 = 0; ph2 ^= 1; }
-                            }
-                            if (MDSCTK_TC_PROF_BUILD && a.prof) t_wait_full += clock64() - t0;
                         }
-                        // stages of this group, and the readiness test of the next one (issued now, looked at afterwards)
+                        // this round's stage, and the readiness test of the next one (issued now, looked at afterwards)
                         const int sA = s;
-                        int sB = s + 1; if (sB == nst) sB = 0;
-                        s += ng;
-                        if (s >= nst) { s -= nst; ph ^= 1; }
-                        const bool last_group = kc0 + grp >= nkc;
-                        const bool rdy_next = test_group(s, ph, last_group ? min(grp, nkc) : min(grp, nkc - kc0 - grp));
+                        if (++s == nst) { s = 0; ph ^= 1; }
+                        const bool rdy_next = mbar_test_wait(&c.bar_full[s], ph);
                         if (elect_one()) {
-                            // One shared-memory stage (two k-steps, six MMAs) at a time.  Which operand form a plane uses can
-                            // only change between stages (the shared-memory part of a plane is whole 64-byte chunks), so there is
-                            // one uniform branch per plane and stage and the MMAs themselves are straight-line code whose
-                            // descriptors differ by constants: the issuing thread must not need more than the ~72 clk an MMA
-                            // executes for (measured: 114 clk per MMA with per-MMA address arithmetic and predication).
-                            const int ks0 = 2 * kc0;
+                            // Which operand form a plane uses can only change between pairs of k-steps (the shared-memory part of
+                            // a plane is whole 64-byte chunks), so there is one uniform branch per pair and the MMAs themselves
+                            // are straight-line code whose descriptors differ by constants: the issuing thread must not need
+                            // more than the ~72 clk an MMA executes for (measured: 114 clk per MMA with per-MMA address
+                            // arithmetic and predication).
+                            const int ks0 = (a.wide ? 4 : 2) * kc0;
                             auto issue_stage = [&](uint32_t b, int ks, uint32_t acc0, bool two) {
                                 const uint32_t so = (uint32_t)(ks >> 1) * (A_CHUNK >> 4);
                                 if (ks < lim0) { tc_mma2_lo<true>(tmem_u, ss0 + so, b, idesc, acc0); if (two) tc_mma2_lo<true>(tmem_u, ss0 + so + 2u, b + 2u, idesc, 1u); }
@@ -431,31 +427,24 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                             auto issue_fast = [&](uint32_t b, int ks, uint32_t acc0) {
                                 if (ks + 1 < lim0) {
                                     const uint32_t so = (uint32_t)(ks >> 1) * (A_CHUNK >> 4);
-                                    tc2_issue_stage_ss(tmem_u, ss0 + so, ss1 + so, ss2 + so, b, idesc, acc0);
+                                    tc2_issue_stage_ss(tmem_u, ss0 + so, ss1 + so, ss2 + so, b, idesc, acc0, bhi);
                                 } else {
                                     const uint32_t to = 8u * (uint32_t)ks;
-                                    tc2_issue_stage_ts(tmem_u, ts0 + to, ts1 + to, ts2 + to, b, idesc, acc0, ks + 1 < nks);
+                                    tc2_issue_stage_ts(tmem_u, ts0 + to, ts1 + to, ts2 + to, b, idesc, acc0, ks + 1 < nks, bhi);
                                 }
                             };
                             if (ks0 < nks) {
-                                if (uniform_split) issue_fast(ring_lo + (uint32_t)sA * (B_STAGE >> 4), ks0, kc0 != 0);
-                                else issue_stage(ring_lo + (uint32_t)sA * (B_STAGE >> 4), ks0, kc0 != 0, ks0 + 1 < nks);
+                                const uint32_t b0 = ring_lo + (uint32_t)sA * ((uint32_t)bst >> 4);
+                                if (uniform_split) issue_fast(b0, ks0, kc0 != 0);
+                                else issue_stage(b0, ks0, kc0 != 0, ks0 + 1 < nks);
+                                // wide stage: k-steps 2 and 3 of its 64 atoms sit 64 bytes into the 128-byte rows
+                                if (a.wide && ks0 + 2 < nks) issue_fast(b0 + 4u, ks0 + 2, 1u);
                             }
                             tc_commit2_mc(&c.bar_empty[sA], 3);
 #if MDSCTK_TC_PROF_BUILD
-                            if (a.prof) { *reinterpret_cast<volatile long long *>(&c.t_commit[sA]) = clock64(); }
+                            if (a.prof) *reinterpret_cast<volatile long long *>(&c.t_commit[sA]) = clock64();
 #endif
-                            if (ng > 1) {
-                                if (ks0 + 2 < nks) {
-                                    if (uniform_split) issue_fast(ring_lo + (uint32_t)sB * (B_STAGE >> 4), ks0 + 2, 1u);
-                                    else issue_stage(ring_lo + (uint32_t)sB * (B_STAGE >> 4), ks0 + 2, 1u, ks0 + 3 < nks);
-                                }
-                                tc_commit2_mc(&c.bar_empty[sB], 3);
-#if MDSCTK_TC_PROF_BUILD
-                                if (a.prof) { *reinterpret_cast<volatile long long *>(&c.t_commit[sB]) = clock64(); }
-#endif
-                            }
-                            if (last_group) {
+                            if (kc0 == nkc - 1) {
                                 if (heavy) tc_commit2_mc(&c.bar_tmem_full, 3);
                                 if (ti == n_tiles - 1) tc_commit2_mc(&c.bar_res_empty, 3);      // item done with its fit tile
                             }
@@ -492,9 +481,10 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const uint32_t ready_leader = map_to_cta(&c.bar_item_ready, 0);
         const uint32_t qtau_leader = map_to_cta(&c.qtau[rank * 4 + quarter], 0);
         const unsigned lt_mask = (1u << lane) - 1u;
-        unsigned *hist = c.scratch[ew];
-        float *q_c2 = reinterpret_cast<float *>(hist), *q_c1 = q_c2 + QCAP, *q_c0 = q_c2 + 2 * QCAP, *q_e0 = q_c2 + 3 * QCAP;
-        int *q_tag = reinterpret_cast<int *>(hist) + 4 * QCAP;          // (reference column within the warp's 12) << 8 | own lane | 32 (nofit)
+        const int QC = a.qcap;
+        unsigned *hist = c.scratch + (size_t)ew * 5 * QC;
+        float *q_c2 = reinterpret_cast<float *>(hist), *q_c1 = q_c2 + QC, *q_c0 = q_c2 + 2 * QC, *q_e0 = q_c2 + 3 * QC;
+        int *q_tag = reinterpret_cast<int *>(hist) + 4 * QC;          // (reference column within the warp's 12) << 8 | own lane | 32 (nofit)
         unsigned *wcnt8 = c.cnt8[ew];
         const size_t row_stride = (size_t)a.cl.H * a.cl.cap;
         uint32_t hph = 0, eph = 0, last_msg = 0;
@@ -537,9 +527,9 @@ rms_sweep_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         auto push = [&](bool pred, float c2, float c1, float c0, float e0, int tag) {
             unsigned m = __ballot_sync(0xffffffffu, pred);
             while (m) {                               // warp-uniform: at most two rounds (32 candidates, QCAP slots)
-                if (qn == QCAP) drain();
+                if (qn == QC) drain();
                 const int rank = __popc(m & lt_mask);
-                const bool now = pred && rank < QCAP - qn;
+                const bool now = pred && rank < QC - qn;
                 if (now) {
                     const int p = qn + rank;
                     q_c2[p] = c2; q_c1[p] = c1; q_c0[p] = c0; q_e0[p] = e0; q_tag[p] = tag;
@@ -801,17 +791,23 @@ namespace {
 
 struct Tc2Layout {
     int nks, nkc, chunks[3], chunk_base[3], tmem_unit0[3], n_tmem_units, n_res_chunks, nst, smem_bytes;
+    int qcap, wide, bst;
     bool ok;
 };
 
 // Where the CTA's fit tile lives: whole 64-byte chunks (two k-steps) per plane in shared memory, the trailing
 // k-steps of each plane in the spare TMEM columns (at most 10 k-steps in all), and a ring of >= 4 reference stages.
-Tc2Layout tc2_layout(int A_pad)
+static int tc2_ctl_bytes(int qcap)
+{
+    return (int)((offsetof(tc2::Ctl, scratch) + (size_t)tc2::EPI_WARPS * 5 * qcap * sizeof(unsigned) + 15) / 16 * 16);
+}
+
+Tc2Layout tc2_layout(int A_pad, int want_wide)
 {
     Tc2Layout L = {};
     L.nks = A_pad / 16;
     L.nkc = (A_pad + 31) / 32;
-    const int ctl = (int)((sizeof(tc2::Ctl) + 15) / 16 * 16);
+    const int ctl = tc2_ctl_bytes(tc2::QCAP);
     int best_nst = 0;
     bool best_equal = false;
     // z gives up k-steps to TMEM first (then y, x): try every split and keep the one with the deepest ring
@@ -846,90 +842,57 @@ Tc2Layout tc2_layout(int A_pad)
                 }
             }
     L.ok = best_nst >= 4 && A_pad % 16 == 0;
+    L.qcap = tc2::QCAP; L.wide = 0; L.bst = tc2::B_STAGE;
     L.smem_bytes = L.n_res_chunks * tc2::A_CHUNK + L.nst * tc2::B_STAGE + ctl;
+    // Wide stages (64 atoms, 128-byte rows): half the producer / issuer rounds per pass -- a round costs each of the two
+    // single threads ~500 clk whatever it moves, which is what paced the light passes -- if three of them fit (a smaller
+    // refine queue may have to pay for the third).  Needs the same split for every plane (straight-line issue blocks).
+    if (L.ok && want_wide && best_equal) {
+        for (int qc : {tc2::QCAP, tc2::QCAP_SMALL}) {
+            const int room = tc2::SMEM_MAX - L.n_res_chunks * tc2::A_CHUNK - tc2_ctl_bytes(qc);
+            int nw = room / tc2::B_STAGE_WIDE;
+            if (nw > tc2::MAX_NST) nw = tc2::MAX_NST;
+            if (nw >= 3) {
+                L.wide = 1; L.bst = tc2::B_STAGE_WIDE; L.nst = nw; L.qcap = qc; L.nkc = (A_pad + 63) / 64;
+                L.smem_bytes = L.n_res_chunks * tc2::A_CHUNK + nw * tc2::B_STAGE_WIDE + tc2_ctl_bytes(qc);
+                break;
+            }
+        }
+    }
     return L;
 }
 
-bool make_map(CUtensorMap *m, const void *planes, long long n, int A_pad, int rows, int box_planes)
+bool make_map(CUtensorMap *m, const void *planes, long long n, int A_pad, int rows, int box_planes, bool wide = false)
 {
     EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)A_pad, (cuuint64_t)n, 3};
     cuuint64_t strides[2] = {(cuuint64_t)A_pad * 3 * 2, (cuuint64_t)A_pad * 2};
-    cuuint32_t box[3] = {32, (cuuint32_t)rows, (cuuint32_t)box_planes};
+    cuuint32_t box[3] = {wide ? 64u : 32u, (cuuint32_t)rows, (cuuint32_t)box_planes};      // wide: 128-byte rows, reaching past A_pad is zero-filled
     cuuint32_t estr[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// ring-stage-ordered reference operand as a 3-D tensor (32 atoms, 72 rows, stage); one box = one contiguous stage
-bool make_tiled_map(CUtensorMap *m, const void *tiled, long long n_stages)
-{
-    EncodeTiledFn enc = get_tensor_map_encoder();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {32, 72, (cuuint64_t)n_stages};
-    cuuint64_t strides[2] = {64, (cuuint64_t)tc2::B_STAGE};
-    cuuint32_t box[3] = {32, 72, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(tiled), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
 
-bool rms_tc2_supported(int A_pad) { return tc2_layout(A_pad).ok; }
-
-// Reference operand in RING-STAGE order: [half-tile of 24 frames][chunk of 32 atoms][plane][frame][32 atoms] fp16, i.e. every
-// 4.6 KB stage the sweep's ring loads is one contiguous block of global memory (72 adjacent 64-byte rows) instead of 72
-// rows 6 A_pad bytes apart in the frame-major planes: the copy engine fetches 36 full 128-byte lines per stage.  Frames
-// beyond n and atoms beyond A_pad are zero.  Built once per reference set from the fp16 planes (1.9 GB at 1M x 300).
-__global__ void tile_reference_kernel(const __half *__restrict__ fh, long long n, int A_pad, int nkc, long long n_half_tiles,
-                                      uint4 *__restrict__ out)
-{
-    const long long total = n_half_tiles * nkc * 72 * 4;           // 16-byte vectors
-    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long long)gridDim.x * blockDim.x) {
-        const int c16 = (int)(v & 3);
-        long long r = v >> 2;
-        const int row = (int)(r % 72); r /= 72;
-        const int kc = (int)(r % nkc);
-        const long long ht = r / nkc;
-        const int plane = row / 24;
-        const long long frame = ht * 24 + row % 24;
-        const int atom = kc * 32 + c16 * 8;
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (frame < n && atom < A_pad) val = *reinterpret_cast<const uint4 *>(fh + ((size_t)frame * 3 + plane) * A_pad + atom);
-        out[v] = val;
-    }
-}
-
-size_t rms_tc2_tiled_bytes(long long n_ref, int A_pad)
-{
-    const long long n_half_tiles = 2 * ((n_ref + tc2::TR - 1) / tc2::TR);
-    return (size_t)n_half_tiles * ((A_pad + 31) / 32) * tc2::B_STAGE;
-}
-
-cudaError_t launch_rms_tc2_tile_reference(const void *fh, long long n_ref, int A_pad, void *tiled, cudaStream_t st)
-{
-    if (n_ref <= 0) return cudaSuccess;
-    const long long n_half_tiles = 2 * ((n_ref + tc2::TR - 1) / tc2::TR);
-    tile_reference_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const __half *>(fh), n_ref, A_pad, (A_pad + 31) / 32, n_half_tiles,
-                                                   static_cast<uint4 *>(tiled));
-    return cudaGetLastError();
-}
+bool rms_tc2_supported(int A_pad) { return tc2_layout(A_pad, 0).ok; }
 
 cudaError_t launch_rms_sweep_tc2(const FrameSetView &fit, long long fit_begin, long long n_fit, const FrameSetView &ref, int do_fit,
                                  int n_seg, CandLists<float> cl, float *row_tau, float g_ref_max, int *own_tile_scratch,
-                                 float *debug_tile, const void *ref_tiled, int n_sms, cudaStream_t st)
+                                 float *debug_tile, int wide_stages, int n_sms, cudaStream_t st)
 {
     if (n_fit <= 0) return cudaSuccess;
     if (cl.H != n_seg || cl.cap < cl.keep + tc2::SUBS * tc2::SUB_APP) return cudaErrorInvalidValue;
-    const Tc2Layout L = tc2_layout(ref.A_pad);
+    int want_wide = wide_stages && !(tc_experiment_bits() & 8192);      // (not with the generic-issue experiment)
+#if MDSCTK_TC_EXPERIMENTS
+    if (const char *we = getenv("MDSCTK_TC_WIDE")) want_wide = want_wide && atoi(we) != 0;
+#endif
+    const Tc2Layout L = tc2_layout(ref.A_pad, want_wide);
     if (!L.ok) return cudaErrorInvalidConfiguration;
     CUtensorMap mq, mr;
     if (!make_map(&mq, fit.fh, fit.n, fit.A_pad, tc2::TQ, 1)) return cudaErrorInvalidValue;
-    if (ref_tiled ? !make_tiled_map(&mr, ref_tiled, (long long)(rms_tc2_tiled_bytes(ref.n, ref.A_pad) / tc2::B_STAGE))
-                  : !make_map(&mr, ref.fh, ref.n, ref.A_pad, tc2::TRH, 3))
-        return cudaErrorInvalidValue;
+    if (!make_map(&mr, ref.fh, ref.n, ref.A_pad, tc2::TRH, 3, L.wide != 0)) return cudaErrorInvalidValue;
     Tc2Args a = {};
     a.q_G = fit.Gh; a.r_G = ref.Gh;
     a.q_begin = fit_begin; a.n_q = n_fit; a.n_r = ref.n;
@@ -939,8 +902,8 @@ cudaError_t launch_rms_sweep_tc2(const FrameSetView &fit, long long fit_begin, l
     a.pre_rel = (a.dbg & 2048) ? -1.0f : 4.9e-4f;           // relative rounding error of one fp16 operand (2^-11)
     a.pre_sqrt_gmax = sqrtf(g_ref_max > 0.f ? g_ref_max : 0.f);
     a.q_fh = static_cast<const __half *>(fit.fh);
-    a.tiled = ref_tiled != nullptr;
     a.nkc = L.nkc; a.nks = L.nks; a.n_tmem_units = L.n_tmem_units; a.n_res_chunks = L.n_res_chunks; a.nst = L.nst;
+    a.qcap = L.qcap; a.wide = L.wide; a.bst = L.bst;
     for (int p = 0; p < 3; ++p) { a.chunks[p] = L.chunks[p]; a.chunk_base[p] = L.chunk_base[p]; a.tmem_unit0[p] = L.tmem_unit0[p]; }
     a.idesc = tc2::IDESC;
 #if MDSCTK_TC_EXPERIMENTS
@@ -986,12 +949,16 @@ cudaError_t launch_rms_sweep_tc2(const FrameSetView &fit, long long fit_begin, l
         static long long h[1024 * 8];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
-        double sum[8] = {0}; int nb = 0;
+        double sum[8] = {0}, psum[8] = {0}; int nb = 0;
         for (int b = 0; b < 1024; b += 2) {
             if (h[b * 8] == 0) continue;
             nb++;
-            for (int k = 0; k < 8; ++k) sum[k] += (double)h[b * 8 + k];
+            for (int k = 0; k < 8; ++k) { sum[k] += (double)h[b * 8 + k]; psum[k] += (double)h[(b + 1) * 8 + k]; }
         }
+        if (nb && sum[3] > 0)
+            fprintf(stderr, "[tc2 prof] producer (leader CTA) clk per pass: total %.0f = scout %.0f + wait for free stages %.0f + issue copies %.0f + rest; "
+                            "rounds per pass %.2f | issuer per pass: MMA issue %.0f, commits %.0f, next-stage tests %.0f, director %.0f\n",
+                    psum[0] / sum[3], 0.0, psum[2] / sum[3], psum[3] / sum[3], psum[4] / sum[3], psum[5] / sum[3], psum[6] / sum[3], psum[7] / sum[3], psum[1] / sum[3]);
         if (nb)
             fprintf(stderr, "[tc2 prof] pairs=%d passes %.0f heavy %.1f%% | clk per pass: total %.0f = wait hand-back %.0f + wait operands %.0f + "
                             "issue and rest | ring round trip: commit -> producer %.0f clk, copy issued -> seen full %.0f clk | layout: %d chunks "

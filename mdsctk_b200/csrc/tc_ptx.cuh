@@ -274,8 +274,9 @@ __device__ __forceinline__ void tc_mma2_ts_lo(uint32_t d_tmem, uint32_t a_tmem, 
 // is 32 bytes further, + 2), b: of the reference half-tile; d0: accumulator region of plane 0 (planes 1, 2 at + 144,
 // + 288 columns); acc0 = 0 starts a new accumulation.  Everything the tensor pipe needs differs from these by constants,
 // so the issuing thread spends ~2 instructions per MMA (it has 72 clk per MMA before it becomes the bottleneck).
+// bhi: high word of the B descriptor (kDescHiSw64 for 64-byte reference rows, kDescHiSw128 for 128-byte ones); A is SWIZZLE_64B.
 __device__ __forceinline__ void tc2_issue_stage_ss(uint32_t d0, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b, uint32_t idesc,
-                                                   uint32_t acc0)
+                                                   uint32_t acc0, uint32_t bhi)
 {
     asm volatile(
         "{\n\t"
@@ -291,14 +292,14 @@ __device__ __forceinline__ void tc2_issue_stage_ss(uint32_t d0, uint32_t a0, uin
         "add.u32 x0, %1, 2;\n\t"
         "add.u32 x1, %2, 2;\n\t"
         "add.u32 x2, %3, 2;\n\t"
-        "mov.b64 db, {%4, hi};\n\t"
+        "mov.b64 db, {%4, %7};\n\t"
         "mov.b64 da, {%1, hi};\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
         "mov.b64 da, {%2, hi};\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [d1], da, db, %5, p;\n\t"
         "mov.b64 da, {%3, hi};\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [d2], da, db, %5, p;\n\t"
-        "mov.b64 db, {y, hi};\n\t"
+        "mov.b64 db, {y, %7};\n\t"
         "mov.b64 da, {x0, hi};\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, q;\n\t"
         "mov.b64 da, {x1, hi};\n\t"
@@ -306,13 +307,13 @@ __device__ __forceinline__ void tc2_issue_stage_ss(uint32_t d0, uint32_t a0, uin
         "mov.b64 da, {x2, hi};\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [d2], da, db, %5, q;\n\t"
         "}"
-        ::"r"(d0), "r"(a0), "r"(a1), "r"(a2), "r"(b), "r"(idesc), "r"(acc0)
+        ::"r"(d0), "r"(a0), "r"(a1), "r"(a2), "r"(b), "r"(idesc), "r"(acc0), "r"(bhi)
         : "memory");
 }
 // Same with the three A operands in tensor memory (t0..t2: TMEM addresses of the first k-step, the second 8 columns
 // further); two = 0: only the first k-step exists (odd number of k-steps).
 __device__ __forceinline__ void tc2_issue_stage_ts(uint32_t d0, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t b, uint32_t idesc,
-                                                   uint32_t acc0, uint32_t two)
+                                                   uint32_t acc0, uint32_t two, uint32_t bhi)
 {
     asm volatile(
         "{\n\t"
@@ -328,17 +329,17 @@ __device__ __forceinline__ void tc2_issue_stage_ts(uint32_t d0, uint32_t t0, uin
         "add.u32 x0, %1, 8;\n\t"
         "add.u32 x1, %2, 8;\n\t"
         "add.u32 x2, %3, 8;\n\t"
-        "mov.b64 db, {%4, hi};\n\t"
+        "mov.b64 db, {%4, %8};\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %5, p;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [d1], [%2], db, %5, p;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [d2], [%3], db, %5, p;\n\t"
-        "mov.b64 db, {y, hi};\n\t"
+        "mov.b64 db, {y, %8};\n\t"
         "setp.eq.u32 p, %0, %0;\n\t"
         "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [x0], db, %5, p;\n\t"
         "@q tcgen05.mma.cta_group::2.kind::f16 [d1], [x1], db, %5, p;\n\t"
         "@q tcgen05.mma.cta_group::2.kind::f16 [d2], [x2], db, %5, p;\n\t"
         "}"
-        ::"r"(d0), "r"(t0), "r"(t1), "r"(t2), "r"(b), "r"(idesc), "r"(acc0), "r"(two)
+        ::"r"(d0), "r"(t0), "r"(t1), "r"(t2), "r"(b), "r"(idesc), "r"(acc0), "r"(two), "r"(bhi)
         : "memory");
 }
 // eight consecutive 32-bit columns of this thread's TMEM lane <- registers (operand staging; complete after tc_wait_st)

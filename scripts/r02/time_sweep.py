@@ -23,7 +23,7 @@ for name, n, basins, seed, k1, rows in (("C3", 100000, 16, 20260117, 33, 0), ("s
     ref = None
     for ver in [int(v) for v in os.environ.get('VERSIONS', '1 2 2').split()]:
         ctx.set_option("sweep_version", abs(ver))
-        ctx.set_option("ref_tiled", 0 if ver < 0 else 1)       # -2: version 2 with the frame-major reference planes
+        ctx.set_option("rms_wide_stages", 0 if ver < 0 else 1)       # -2: version 2 with 32-atom ring stages
         fr = (0, rows) if rows else None
         ctx.rms_query(k1, fit_range=fr, fetch=False)
         d, i = ctx.rms_query(k1, fit_range=fr)

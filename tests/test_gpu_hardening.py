@@ -112,6 +112,10 @@ def test_row_blocks_and_kernel_switches_give_identical_lists(ctx, trpcage):
         d, i = ctx.rms_query(11)
         assert ctx.stats()["rms_kernel"] == kern
         assert np.array_equal(i, i0) and np.array_equal(d, d0), kern
+    ctx.set_option("rms_wide_stages", 0)                                          # 32-atom ring stages (64-byte rows)
+    d, i = ctx.rms_query(11)
+    ctx.set_option("rms_wide_stages", 1)
+    assert np.array_equal(i, i0) and np.array_equal(d, d0)
     pts = np.fromfile(os.path.join(DATA, "swissroll.pts"), dtype=np.float64).reshape(-1, 3)
     ctx.data_set_reference(pts)
     da, ia = ctx.data_query(11)

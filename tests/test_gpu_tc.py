@@ -47,15 +47,19 @@ def test_tmem_accumulators_match_numpy(ctx, trpcage, kern, rtol):
     assert err.max() < rtol, f"max scaled error {err.max()}"
 
 
-@pytest.mark.parametrize("atoms,version", [(300, 2), (300, 1), (256, 2), (290, 2), (33, 2), (20, 2), (5, 2), (304, 2)])
-def test_tmem_accumulators_1xfp16_resident_tile(ctx, atoms, version):
+@pytest.mark.parametrize("atoms,version,wide", [(300, 2, 1), (300, 2, 0), (300, 1, 1), (256, 2, 1), (290, 2, 1), (290, 2, 0), (33, 2, 1),
+                                                (33, 2, 0), (20, 2, 1), (5, 2, 1), (304, 2, 1), (128, 2, 1), (64, 2, 1), (80, 2, 1)])
+def test_tmem_accumulators_1xfp16_resident_tile(ctx, atoms, version, wide):
     """The default sweep (rms_tc2.cu) keeps the fit tile in shared memory and, beyond 256 atoms, its trailing k-steps in
-    TMEM (tcgen05.mma with the A operand in tensor memory): raw accumulators against numpy on the fp16-rounded operands."""
+    TMEM (tcgen05.mma with the A operand in tensor memory): raw accumulators against numpy on the fp16-rounded operands.
+    wide: 64-atom ring stages of 128-byte rows (SWIZZLE_128B reference operand against the SWIZZLE_64B fit tile), the
+    default where three fit; 0: 32-atom stages."""
     from mdsctk_b200 import synth
     xyz = synth.traj_frames(400, atoms, 2, 9)
     mass = (12.0 + np.arange(atoms) % 3).astype(np.float32)
     ctx.set_option("rms_kernel", TC_F1)
     ctx.set_option("sweep_version", version)
+    ctx.set_option("rms_wide_stages", wide)
     ctx.set_option("debug_tile", 1)
     try:
         ctx.rms_set_reference(xyz, mass)
@@ -64,6 +68,7 @@ def test_tmem_accumulators_1xfp16_resident_tile(ctx, atoms, version):
         tile = ctx.debug_fetch_tile()
     finally:
         ctx.set_option("debug_tile", 0)
+        ctx.set_option("rms_wide_stages", 1)
         ctx.set_option("sweep_version", 2)
         ctx.set_option("rms_kernel", 0)
     P = packed_planes(xyz, mass)

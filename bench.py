@@ -124,8 +124,8 @@ def measured_peaks(rms_kernel):
 
 def measured_traffic(key):
     """DRAM bytes per launch of the dominant kernel from an ncu --set full capture of THIS workload
-    (profiles/traffic_r02.json), else null."""
-    p = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    (profiles/traffic_r02b.json: the captures of scripts/r02/ncu_r02b.sh), else null."""
+    p = os.path.join(ROOT, "profiles", "traffic_r02b.json")
     if os.path.exists(p):
         return json.load(open(p)).get(key)
     return None

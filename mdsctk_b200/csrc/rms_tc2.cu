@@ -17,16 +17,31 @@
 //   pass director       In a pass whose 48 reference frames all fail the singular-value pre-bound against the
 //                       super-tile (frames of another conformational basin: nearly every pass once the rows'
 //                       thresholds are tight) nobody reads the accumulators, so nobody needs to hand them back.  The
-//                       MMA warp evaluates that bound itself, one pass ahead of the tensor pipe, and tells the
+//                       MMA warp tests that bound (a scout warp evaluates it ahead of the tensor pipe), and tells the
 //                       epilogue warps of both CTAs only about the passes that can hold a neighbour ("heavy" passes,
 //                       through a mailbox word in shared memory).  Light passes run back to back on the tensor
 //                       pipe with no TMEM hand-over at all; the epilogue warps sleep through them.  The contraction
 //                       itself stays dense: every MMA of every pass is issued.
+//   few, fat rounds     What then paced a light pass was neither the MMAs nor the copies but the two single threads
+//                       that drive them: a round of the producer (barrier wait, expect-tx, one bulk-tensor copy) and
+//                       of the issuer (barrier test, MMAs, commit) costs each ~500 clk whatever it moves (measured:
+//                       the pass took 6.1k clk with the MMAs skipped, 7.9k with them, whether the ring was 5, 6 or
+//                       8 stages deep; one commit per two stages changed nothing; issuing from ONE thread in a
+//                       divergent branch instead of an elected lane of the converged warp made every tcgen05.mma
+//                       block for its 72 clk).  So the reference operand moves in 64-atom stages of 128-byte rows
+//                       (SWIZZLE_128B against the fit tile's SWIZZLE_64B; 9 KB, twelve MMAs per round) wherever
+//                       three such stages fit beside the fit tile -- at 300 atoms the refine queues give up 12 of
+//                       their 32 entries for the third -- the producer is one thread, and the scout's arithmetic
+//                       has a warp of its own: 304-atom light pass 7.9k -> 5.9k clk, C4 block 856 -> 704 ms.
+//
+// Warps: 0 copy producer (one thread, both CTAs), 1 MMA issuer + director (leader CTA), 2-17 epilogue, 18 pass scout (leader).
 //
 // Synchronisation (per CTA pair; "leader" = CTA rank 0, which issues the pair's MMAs):
 //   bar_full[s] / bar_empty[s]   reference ring: TMA complete_tx on the leader / tcgen05.commit multicast to both CTAs
 //   bar_res_full / bar_res_empty resident fit tile of an item loaded / every MMA of the item retired (both CTAs)
 //   bar_item_ready (leader)      32 epilogue warps: TMEM-resident k-steps written, quarter thresholds published
+//   mtile[4] / pass_now (leader) scout -> director: pass number + 1 | threshold that makes the tile heavy; director -> scout: pass
+//                                being issued (the scout stays at most three passes ahead)
 //   mailbox (both CTAs)          (item seq << 20) | (heavy pass index + 1), or | 0xFFFFF = end of item; written by the
 //                                director only after every epilogue warp has handed back the previous heavy pass,
 //                                so one word per CTA is enough

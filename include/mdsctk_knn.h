@@ -228,6 +228,12 @@ int mdsctk_knn_debug_fetch_tile(mdsctk_knn_ctx *ctx, float *out);
  * Returns MDSCTK_KNN_ESTATE when that array is not packed for the current kernel; *n_bytes = its size. */
 int mdsctk_knn_debug_fetch_array(mdsctk_knn_ctx *ctx, int which, void *out, size_t out_capacity, size_t *n_bytes);
 
+/* Diagnostic, host arithmetic only (no GPU, no context): the shared-memory / TMEM layout the version-2 RMSD sweep would use for
+ * n_atoms atoms.  out12 = { supported (else the streaming kernel runs), wide stages, ring stages, bytes per stage, refine-queue
+ * entries per warp, dynamic shared memory bytes, fit-tile chunks in shared memory, fit-tile k-steps in TMEM, stages per pass,
+ * k-steps per pass, control-block bytes, shared-memory limit }. */
+int mdsctk_knn_debug_rms_layout(int n_atoms, int wide_stages, int *out12);
+
 /* CUDA-event stopwatch on the context's own stream (the stream every kernel of this library
  * is launched on): start records an event, stop records a second one, waits for it and returns
  * the elapsed device time in milliseconds. */

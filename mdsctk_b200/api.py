@@ -26,7 +26,7 @@ SYMBOLS = [
     "mdsctk_knn_fetch", "mdsctk_knn_rms_rows", "mdsctk_knn_timer_start", "mdsctk_knn_timer_stop",
     "mdsctk_knn_debug_fetch_tile", "mdsctk_knn_csc_build_sym", "mdsctk_knn_csc_build_general", "mdsctk_knn_csc_fetch",
     "mdsctk_knn_phipsi", "mdsctk_knn_sincos", "mdsctk_knn_data_rows", "mdsctk_knn_spectral_decomp",
-    "mdsctk_knn_debug_fetch_array", "mdsctk_knn_spectral_decomp_ex",
+    "mdsctk_knn_debug_fetch_array", "mdsctk_knn_debug_rms_layout", "mdsctk_knn_spectral_decomp_ex",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
     L.mdsctk_knn_debug_fetch_tile.argtypes = [vp, fp]
     L.mdsctk_knn_timer_stop.argtypes = [vp, dp]
     L.mdsctk_knn_debug_fetch_array.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.mdsctk_knn_debug_rms_layout.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.mdsctk_knn_csc_build_sym.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_build_general.argtypes = [vp, ip, dp, ll, C.c_int, C.c_int, C.c_int, ip, C.POINTER(ll)]
     L.mdsctk_knn_csc_fetch.argtypes = [vp, ip, dp]

@@ -1446,6 +1446,13 @@ int mdsctk_knn_debug_fetch_array(mdsctk_knn_ctx *ctx, int which, void *out, size
     return 0;
 }
 
+int mdsctk_knn_debug_rms_layout(int n_atoms, int wide_stages, int *out12)
+{
+    if (n_atoms <= 0 || !out12) return MDSCTK_KNN_EINVAL;
+    rms_tc2_layout_info((n_atoms + 15) / 16 * 16, wide_stages, out12);
+    return 0;
+}
+
 int mdsctk_knn_timer_start(mdsctk_knn_ctx *ctx)
 {
     if (!ctx) return MDSCTK_KNN_EINVAL;

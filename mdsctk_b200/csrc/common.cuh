@@ -82,6 +82,7 @@ cudaError_t launch_rms_sweep_tc(int mode, const FrameSetView &fit, const void *f
 // Second-generation 1xFP16 sweep (rms_tc2.cu): fit tile resident in shared memory + TMEM, reference-only ring, pass
 // director.  Same lists / arguments as launch_rms_sweep_tc with mode 6; supported when the fit tile fits (A_pad <= 304).
 bool rms_tc2_supported(int A_pad);
+void rms_tc2_layout_info(int A_pad, int want_wide, int out[12]);
 cudaError_t launch_rms_sweep_tc2(const FrameSetView &fit, long long fit_begin, long long n_fit, const FrameSetView &ref, int do_fit,
                                  int n_seg, CandLists<float> cl, float *row_tau, float g_ref_max, int *own_tile_scratch,
                                  float *debug_tile, int wide_stages, int n_sms, cudaStream_t st);

@@ -861,16 +861,26 @@ Tc2Layout tc2_layout(int A_pad, int want_wide)
     L.smem_bytes = L.n_res_chunks * tc2::A_CHUNK + L.nst * tc2::B_STAGE + ctl;
     // Wide stages (64 atoms, 128-byte rows): half the producer / issuer rounds per pass -- a round costs each of the two
     // single threads ~500 clk whatever it moves, which is what paced the light passes -- if three of them fit (a smaller
-    // refine queue may have to pay for the third).  Needs the same split for every plane (straight-line issue blocks).
-    if (L.ok && want_wide && best_equal) {
-        for (int qc : {tc2::QCAP, tc2::QCAP_SMALL}) {
-            const int room = tc2::SMEM_MAX - L.n_res_chunks * tc2::A_CHUNK - tc2_ctl_bytes(qc);
-            int nw = room / tc2::B_STAGE_WIDE;
-            if (nw > tc2::MAX_NST) nw = tc2::MAX_NST;
-            if (nw >= 3) {
-                L.wide = 1; L.bst = tc2::B_STAGE_WIDE; L.nst = nw; L.qcap = qc; L.nkc = (A_pad + 63) / 64;
-                L.smem_bytes = L.n_res_chunks * tc2::A_CHUNK + nw * tc2::B_STAGE_WIDE + tc2_ctl_bytes(qc);
-                break;
+    // refine queue may have to pay for the third).  Needs the same split for every plane (straight-line issue blocks), so
+    // the splits are searched again: t k-steps of every plane in TMEM; a ring of up to five stages is worth more than the
+    // full-size refine queue (heavy passes drain it in batches of that size), the queue more than a still deeper ring.
+    if (L.ok && want_wide) {
+        long best_score = -1;
+        for (int t = 0; 3 * t <= tc2::MAX_TMEM_UNITS && t <= L.nks; ++t) {
+            if ((L.nks - t) & 1) continue;
+            const int chunks = 3 * ((L.nks - t) / 2);
+            for (int qc : {tc2::QCAP, tc2::QCAP_SMALL}) {
+                const int room = tc2::SMEM_MAX - chunks * tc2::A_CHUNK - tc2_ctl_bytes(qc);
+                int nw = room / tc2::B_STAGE_WIDE;
+                if (nw > tc2::MAX_NST) nw = tc2::MAX_NST;
+                const long score = 1000L * (nw < 5 ? nw : 5) + 100L * (qc == tc2::QCAP) + nw;
+                if (nw >= 3 && score > best_score) {
+                    best_score = score;
+                    L.wide = 1; L.bst = tc2::B_STAGE_WIDE; L.nst = nw; L.qcap = qc; L.nkc = (A_pad + 63) / 64;
+                    L.n_tmem_units = 3 * t; L.n_res_chunks = chunks;
+                    for (int p = 0; p < 3; ++p) { L.chunks[p] = chunks / 3; L.chunk_base[p] = p * (chunks / 3); L.tmem_unit0[p] = p * t; }
+                    L.smem_bytes = chunks * tc2::A_CHUNK + nw * tc2::B_STAGE_WIDE + tc2_ctl_bytes(qc);
+                }
             }
         }
     }
@@ -892,6 +902,15 @@ bool make_map(CUtensorMap *m, const void *planes, long long n, int A_pad, int ro
 }  // namespace
 
 bool rms_tc2_supported(int A_pad) { return tc2_layout(A_pad, 0).ok; }
+
+// host-side description of the layout the launcher would pick (no GPU involved): tests/test_abi_cpu.py sweeps every atom count
+void rms_tc2_layout_info(int A_pad, int want_wide, int out[12])
+{
+    const Tc2Layout L = tc2_layout(A_pad, want_wide);
+    out[0] = L.ok; out[1] = L.wide; out[2] = L.nst; out[3] = L.bst; out[4] = L.qcap; out[5] = L.smem_bytes;
+    out[6] = L.n_res_chunks; out[7] = L.n_tmem_units; out[8] = L.nkc; out[9] = L.nks;
+    out[10] = tc2_ctl_bytes(L.qcap); out[11] = tc2::SMEM_MAX;
+}
 
 cudaError_t launch_rms_sweep_tc2(const FrameSetView &fit, long long fit_begin, long long n_fit, const FrameSetView &ref, int do_fit,
                                  int n_seg, CandLists<float> cl, float *row_tau, float g_ref_max, int *own_tile_scratch,

@@ -1,5 +1,7 @@
 #!/bin/bash
-# clean timing (no clock counters compiled in): experiment library, C3 and the C4 block, ms only
+# clean timing (no clock counters compiled in): experiment library, C3 and the C4 block, ms only.
+# Record of the run quoted in profiles/README.md; MDSCTK_TC_CGRP (ring slots per commit) and the exp1 library (lane-0 polls,
+# -DMDSCTK_TC2_POLL1=1) were experiment code of that working tree and are gone -- both measured neutral or worse.
 mkdir -p gpurun_out
 : > gpurun_out/clean.log
 run() { echo "== $1 atoms=$2 dbg=$3 cgrp=$4" >> gpurun_out/clean.log

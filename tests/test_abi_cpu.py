@@ -62,3 +62,31 @@ def test_product_never_imports_oracle():
 def test_built_for_sm100a_with_lineinfo():
     flags = " ".join(build.NVCC_FLAGS)
     assert "arch=compute_100a,code=sm_100a" in flags and "-lineinfo" in flags
+
+
+def test_rms_sweep_layout_fits_for_every_atom_count(lib):
+    """Host arithmetic of the version-2 RMSD sweep's shared-memory / TMEM layout (rms_tc2.cu tc2_layout), every atom count the
+    kernel accepts: the dynamic shared memory fits, the control block is what is left after operands, ring depth and
+    refine-queue size stay in the ranges the kernel was tested with."""
+    out = (ctypes.c_int * 12)()
+    supported = wide = 0
+    for atoms in range(1, 400):
+        for want in (0, 1):
+            assert lib.mdsctk_knn_debug_rms_layout(atoms, want, out) == 0
+            ok, is_wide, nst, bst, qcap, smem, chunks, tmem_units, nkc, nks, ctl, smem_max = list(out)
+            a_pad = (atoms + 15) // 16 * 16
+            if a_pad > 304:
+                assert not ok                                   # the streaming kernel of round 1 takes over
+                continue
+            assert ok, atoms
+            assert nks == a_pad // 16 and 2 * chunks + tmem_units == 3 * nks and tmem_units <= 10
+            assert smem == chunks * 8192 + nst * bst + ctl <= smem_max == 227 * 1024
+            assert qcap in (32, 20) and qcap * 5 >= 64          # the warp's queue area doubles as a 64-bin histogram
+            if is_wide:
+                assert want and bst == 9216 and 3 <= nst <= 8 and nkc == (a_pad + 63) // 64
+            else:
+                assert bst == 4608 and 4 <= nst <= 8 and nkc == (a_pad + 31) // 32 and qcap == 32
+            supported += 1
+            wide += is_wide
+    assert supported == 2 * 304 and wide >= 250                 # wide stages wherever the planes split evenly and three fit
+    assert lib.mdsctk_knn_debug_rms_layout(0, 1, out) < 0

@@ -48,7 +48,8 @@ def test_tmem_accumulators_match_numpy(ctx, trpcage, kern, rtol):
 
 
 @pytest.mark.parametrize("atoms,version,wide", [(300, 2, 1), (300, 2, 0), (300, 1, 1), (256, 2, 1), (290, 2, 1), (290, 2, 0), (33, 2, 1),
-                                                (33, 2, 0), (20, 2, 1), (5, 2, 1), (304, 2, 1), (128, 2, 1), (64, 2, 1), (80, 2, 1)])
+                                                (33, 2, 0), (20, 2, 1), (5, 2, 1), (304, 2, 1), (128, 2, 1), (64, 2, 1), (80, 2, 1), (288, 2, 1), (280, 2, 0),
+                                                (224, 2, 1), (200, 2, 1), (240, 2, 1), (176, 2, 1)])
 def test_tmem_accumulators_1xfp16_resident_tile(ctx, atoms, version, wide):
     """The default sweep (rms_tc2.cu) keeps the fit tile in shared memory and, beyond 256 atoms, its trailing k-steps in
     TMEM (tcgen05.mma with the A operand in tensor memory): raw accumulators against numpy on the fp16-rounded operands.

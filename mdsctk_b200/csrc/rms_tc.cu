@@ -697,8 +697,13 @@ rms_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     }
 }
 
-// Timing-experiment switches (MDSCTK_TC_DEBUG bits, TcArgs::dbg).  Several of them give INVALID results, so the
-// production library never reads the environment: they exist only in builds with -DMDSCTK_TC_EXPERIMENTS=1.
+// Timing-experiment switches (MDSCTK_TC_DEBUG bits, TcArgs::dbg / Tc2Args::dbg).  Several of them give INVALID results, so the
+// production library never reads the environment: they exist only in builds with -DMDSCTK_TC_EXPERIMENTS=1
+// (scripts/build_variant.sh exp -DMDSCTK_TC_EXPERIMENTS=1; scripts/build_prof.sh adds the clock counters).  Bits the
+// version-2 sweep (rms_tc2.cu) honours: 1 skip the QCP bounds (invalid), 2 skip the MMAs (invalid), 8 no early-out of far
+// batches, 64 every pass light (invalid), 512 short mailbox polls, 1024 no scout (every pass live), 2048 no pre-bound,
+// 8192 generic per-MMA issue path, 32768 no own-tile guess; MDSCTK_TC_N overrides the MMA's N (invalid), MDSCTK_TC_WIDE=0
+// forces 32-atom ring stages.
 int tc_experiment_bits()
 {
 #if MDSCTK_TC_EXPERIMENTS

@@ -506,6 +506,25 @@ def run_data(D, wl, args, steps=2, warmup=1, parity_rows=256):
         cpu = {"value": r * n_total / dt, "unit": UNIT, "cores": thr, "kind": "port",
                "sample": f"oracle knn_data (sequential double sum of squares, mdsctk.cpp:330-335, OpenMP): first {r} fit rows x all "
                          f"{n_total} reference rows, {dt:.1f} s"}
+        # the reference's OWN distance function + permutation sort (oracle/_ref: the slice of mdsctk.cpp / mdsctk.h that compiles,
+        # built from /root/reference in the container and shipped as a .so) on a smaller sample of the same rows; a checker and a
+        # baseline like the oracle above, and never fatal: the oracle check stands on its own
+        try:
+            from oracle import ref_slice as rs
+            if rs.available():
+                rr = min(64, r)
+                t = time.perf_counter()
+                d2, i2 = rs.knn_data(full, wl["k"], fit=full[:rr], nthreads=thr)
+                dt2 = time.perf_counter() - t
+                parity["rows_vs_reference_code"] = rr
+                parity["bit_identical_to_reference_code"] = bool(np.array_equal(gd[:rr, 1:], d2) and np.array_equal(gi[:rr, 1:], i2))
+                parity["ok"] = parity["ok"] and parity["bit_identical_to_reference_code"]
+                cpu = {"value": rr * n_total / dt2, "unit": UNIT, "cores": thr, "kind": "reference",
+                       "sample": f"the reference's euclidean_distance + permutation<double>::sort (mdsctk.cpp:330-335, mdsctk.h:177-199, compiled "
+                                 f"unmodified: oracle/ref_slice.sh) under the row loop of knn_data.cpp:195-250, OpenMP: first {rr} fit rows x all "
+                                 f"{n_total} reference rows, {dt2:.1f} s (oracle port on {r} rows: {r * n_total / dt:.3g} pairs/s)"}
+        except Exception as e:                                   # noqa: BLE001
+            parity["reference_code_error"] = str(e)[:200]
     dev_ms, e2e_s, sweep_ms, post_ms = D.reduce([dev_ms, e2e_s, sweep_ms, post_ms], "MAX")
     launches, fallback_rows = [int(x) for x in D.reduce([float(launches), float(fallback_rows)], "SUM")]
     st = ctx.stats()

@@ -15,7 +15,9 @@ _LIB = None
 
 
 def build():
+    """liboracle.so, and -- where /root/reference is present -- oracle/_ref (the compilable slice of the reference itself)."""
     subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    subprocess.check_call(["make", "-s", "-C", _HERE, "_ref"])
 
 
 def lib():

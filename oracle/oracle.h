@@ -6,17 +6,23 @@
  * --impl reference legs may build, load or call this code, and there only as
  * the checker / timed CPU baseline.
  *
- * PARITY UNPINNED: the reference (jlphillipsphd/mdsctk) ships no golden
- * vectors, no known-answer tests and cannot be compiled in this image (it
- * needs libgromacs, Boost.program_options, Berkeley DB and ARPACK, none of
- * which are present).  The RMSD arithmetic lives in GROMACS
- * 5.0-5.1 (un-vendored, un-pinned: /root/reference/CMakeLists.txt:194-209),
- * whose do_fit / rmsdev / reset_x algorithm is restated here.  The oracle is
- * anchored on the reference's call sites instead:
+ * PARITY: PINNED FOR THE VECTOR PATH, UNPINNED FOR THE RMSD PATH.  The reference (jlphillipsphd/mdsctk) ships no golden
+ * vectors and no known-answer tests and cannot be compiled as a whole in this image (it needs libgromacs,
+ * Boost.program_options, Berkeley DB and ARPACK, none of which are present).
+ *   Pinned against outputs of the reference itself: the plain C++ arithmetic of mdsctk.cpp / mdsctk.h -- euclidean_distance,
+ *   correlation_distance, permutation<T>::sort, euclidean_distance_sparse, entropic_affinity_sigma(s), sp_dsymv / sp_dgemv,
+ *   torsion -- compiles on its own; oracle/ref_slice.sh cuts those definitions out of /root/reference where they lie into
+ *   oracle/_ref/ (git-ignored) and builds them unmodified.  tests/test_ref_slice.py holds this oracle to them bit for bit
+ *   (knn_data in and out of sample, both metrics, D up to 512; the sparse metric; sigmas; torsions), and
+ *   tests/golden/refslice_vectors.npz carries reference-made vectors to the GPU box.
+ *   Unpinned: the RMSD arithmetic lives in GROMACS 5.0-5.1 (un-vendored, un-pinned: /root/reference/CMakeLists.txt:194-209),
+ *   whose do_fit / rmsdev / reset_x algorithm is restated here and cross-checked only by an independent FP64 Kabsch and
+ *   the invariance properties in tests/test_oracle.py.
+ * The oracle is anchored on the reference's call sites:
  *   knn_rms.cpp:38-41    distance() = do_fit + rmsdev * 10
  *   knn_rms.cpp:181-206  mass weights, reset_x on every frame
  *   knn_rms.cpp:224-293  k clamp, row blocks, rank-0 drop, file layout
- *   knn_data.cpp:141-250 reader, blocks, writer
+ *   knn_data.cpp:141-250 reader, blocks, writer (argument order of distance(): fitting row first)
  *   mdsctk.h:177-199     permutation<T>::sort(k) = partial_sort
  *   mdsctk.cpp:330-360   euclidean_distance / correlation_distance
  * and cross-checked by the invariance properties in tests/test_oracle.py.

@@ -152,7 +152,9 @@ void oracle_entropic_affinity_sigmas(int n, int k, double K, const double *A, do
         const double *a = A + (size_t)x * k;
         BU[x] = log((2.0 * log(p1 * (N - 1.0) / (1.0 - p1))) / (a[1] * a[1] - a[0] * a[0]));
         const double bL1 = log((2.0 * logNK / (1.0 - (1.0 / N))) / (a[k - 1] * a[k - 1] - a[0] * a[0]));
-        const double bL2 = log((2.0 * sqrt(logNK)) / sqrt((a[k - 1] * a[k - 1]) * (a[k - 1] * a[k - 1]) - (a[0] * a[0]) * (a[0] * a[0])));
+        /* SQR(x)*SQR(x) of the reference expands (unparenthesised macro, mdsctk.h:84) to x*x*x*x = ((x*x)*x)*x: keep that order
+         * (pinned against the reference's own code, tests/test_ref_slice.py) */
+        const double bL2 = log((2.0 * sqrt(logNK)) / sqrt(a[k - 1] * a[k - 1] * a[k - 1] * a[k - 1] - a[0] * a[0] * a[0] * a[0]));
         BL[x] = bL1 > bL2 ? bL1 : bL2;
         order[2 * x] = a[Ki - 1];
         order[2 * x + 1] = (double)x;

@@ -166,6 +166,25 @@ def test_knn_data_correlation_and_oos(ctx):
     assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
 
 
+@pytest.mark.parametrize("tag,seed,n,dim,n_fit,k", [("d64", 11, 300, 64, 40, 12), ("d512", 12, 257, 512, 33, 33), ("d5", 13, 120, 5, 20, 7)])
+def test_knn_data_equals_reference_made_goldens(ctx, tag, seed, n, dim, n_fit, k):
+    """tests/golden/refslice_vectors.npz was written by the REFERENCE'S OWN CODE (oracle/_ref: euclidean_distance /
+    correlation_distance of mdsctk.cpp:330-360 and permutation<double>::sort of mdsctk.h:177-199, compiled unmodified, under
+    the row loop of knn_data.cpp:195-250) on these seeded inputs (tests/golden/make_ref_slice_golden.py): same bytes from the GPU."""
+    import importlib.util
+    import mdsctk_b200
+    spec = importlib.util.spec_from_file_location("make_ref_slice_golden", os.path.join(GOLDEN, "make_ref_slice_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(GOLDEN, "refslice_vectors.npz"))
+    X, F = gen.dense_case(seed, n, dim, n_fit)
+    for corr, mn in ((False, "euc"), (True, "cor")):
+        dist, idx = mdsctk_b200.knn_data(X, k, correlation=corr, ctx=ctx)
+        assert np.array_equal(idx, g[f"{tag}_{mn}_idx"]) and np.array_equal(dist, g[f"{tag}_{mn}_dist"]), mn
+        dist, idx = mdsctk_b200.knn_data(X, k, correlation=corr, fit_rows=F, ctx=ctx)
+        assert np.array_equal(idx, g[f"{tag}_{mn}_oos_idx"]) and np.array_equal(dist, g[f"{tag}_{mn}_oos_dist"]), (mn, "oos")
+
+
 def test_knn_data_wide_rows(ctx):
     import mdsctk_b200
     from mdsctk_b200 import synth

@@ -511,7 +511,7 @@ def run_data(D, wl, args, steps=2, warmup=1, parity_rows=256):
         # baseline like the oracle above, and never fatal: the oracle check stands on its own
         try:
             from oracle import ref_slice as rs
-            if rs.available():
+            if os.path.exists(rs.SO):                            # prebuilt by build(); never built (nor /root/reference looked at) here
                 rr = min(64, r)
                 t = time.perf_counter()
                 d2, i2 = rs.knn_data(full, wl["k"], fit=full[:rr], nthreads=thr)
